@@ -1,0 +1,184 @@
+// pool_misc.cu -- the small memory-bound kernels of the int_op_only path:
+//   maxpool3x3s2   ResNet head max-pool with the float32 round trip
+//                  x = self.head[-1](x.float()).int()   /root/reference/models/fix_resnet.py:358-359
+//   pool_requant   FXQAvgPool2d int branch + classifier requant
+//                  /root/reference/models/fix_quant_ops.py:126-134, fix_resnet.py:367-374
+//   convert_input  int32 NCHW (reference tensor) -> NHWC4 8-bit
+//   requant_i32    int_op_only_fix_quant as a standalone op, fix_quant_ops.py:90-114
+// All are HBM-bound streaming kernels: 16-byte vector accesses, channel-fastest thread
+// mapping so every warp touches contiguous memory.
+#include "f8_common.cuh"
+
+namespace {
+
+constexpr int THREADS = 256;
+
+// in: int32 NHWC [n,hin,win,cpad] (post-ReLU head accumulator).  One thread = 4 channels
+// of one output pixel.  int -> float is monotone, so max-then-convert equals the
+// reference's convert-then-max; -inf padding never wins because every window holds at
+// least one real element.
+__global__ void __launch_bounds__(THREADS)
+maxpool_kernel(const int32_t *__restrict__ in, int n, int hin, int win, int hout, int wout,
+               int cpad, const f8::Epilogue ep) {
+    const int c4n = cpad >> 2;
+    const long long total = (long long)n * hout * wout * c4n;
+    for (long long idx = blockIdx.x * (long long)THREADS + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * THREADS) {
+        const int c4 = (int)(idx % c4n);
+        long long t = idx / c4n;
+        const int q = (int)(t % wout);
+        t /= wout;
+        const int p = (int)(t % hout);
+        const int img = (int)(t / hout);
+        int4 m = make_int4(INT32_MIN, INT32_MIN, INT32_MIN, INT32_MIN);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int ih = p * 2 - 1 + r;
+            if ((unsigned)ih >= (unsigned)hin) continue;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int iw = q * 2 - 1 + s;
+                if ((unsigned)iw >= (unsigned)win) continue;
+                const int4 v = __ldg(reinterpret_cast<const int4 *>(
+                    in + (((size_t)img * hin + ih) * win + iw) * cpad + c4 * 4));
+                m.x = max(m.x, v.x); m.y = max(m.y, v.y);
+                m.z = max(m.z, v.z); m.w = max(m.w, v.w);
+            }
+        }
+        int32_t v[4] = {f8::f2i_x86((float)m.x), f8::f2i_x86((float)m.y),
+                        f8::f2i_x86((float)m.z), f8::f2i_x86((float)m.w)};
+        const size_t o = (((size_t)img * hout + p) * wout + q) * cpad + c4 * 4;
+        if (ep.relu) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[c] = max(v[c], 0);
+        }
+        if (ep.carry_out)
+            *reinterpret_cast<int4 *>(ep.carry_out + o) = make_int4(v[0], v[1], v[2], v[3]);
+        if (ep.out0) {
+            uint32_t pk = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                pk |= ((uint32_t)f8::requant(v[c], ep.shift0, ep.signed0) & 0xffu) << (8 * c);
+            *reinterpret_cast<uint32_t *>(ep.out0 + o) = pk;
+        }
+        if (ep.out1) {
+            uint32_t pk = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                pk |= ((uint32_t)f8::requant(v[c], ep.shift1, ep.signed1) & 0xffu) << (8 * c);
+            *reinterpret_cast<uint32_t *>(ep.out1 + o) = pk;
+        }
+    }
+}
+
+// in: int32 NHWC [n, hw, cpad] -> out0: 8-bit [n, cpad].  Sum wraps mod 2^32, which equals
+// the reference's int64 sum followed by .int() (fix_quant_ops.py:130-133).
+__global__ void __launch_bounds__(THREADS)
+pool_requant_kernel(const int32_t *__restrict__ in, int n, int hw, int cpad,
+                    const f8::Epilogue ep) {
+    const long long total = (long long)n * cpad;
+    for (long long idx = blockIdx.x * (long long)THREADS + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * THREADS) {
+        const int c = (int)(idx % cpad);
+        const int img = (int)(idx / cpad);
+        const int32_t *src = in + (size_t)img * hw * cpad + c;
+        uint32_t acc = 0;
+        for (int i = 0; i < hw; ++i) acc += (uint32_t)__ldg(src + (size_t)i * cpad);
+        const int32_t v = (int32_t)acc;
+        if (ep.carry_out) ep.carry_out[idx] = v;
+        if (ep.out0) ep.out0[idx] = (uint8_t)(f8::requant(v, ep.shift0, ep.signed0) & 0xff);
+    }
+}
+
+// x int32 [n,3,h,w] -> out 8-bit [n,h,w,4]; channel 3 = 0.  Keeps the low byte: u8 0..255
+// and s8 -127..127 both survive the truncation unchanged.
+__global__ void __launch_bounds__(THREADS)
+convert_input_kernel(const int32_t *__restrict__ x, uint32_t *__restrict__ out, int n, int hw) {
+    const long long total = (long long)n * hw;
+    for (long long idx = blockIdx.x * (long long)THREADS + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * THREADS) {
+        const int img = (int)(idx / hw);
+        const int px = (int)(idx - (long long)img * hw);
+        const int32_t *src = x + (size_t)img * 3 * hw + px;
+        const uint32_t c0 = (uint32_t)__ldg(src) & 0xffu;
+        const uint32_t c1 = (uint32_t)__ldg(src + hw) & 0xffu;
+        const uint32_t c2 = (uint32_t)__ldg(src + 2 * (size_t)hw) & 0xffu;
+        out[idx] = c0 | (c1 << 8) | (c2 << 16);
+    }
+}
+
+__global__ void __launch_bounds__(THREADS)
+requant_i32_kernel(const int32_t *__restrict__ x, int32_t *__restrict__ y, size_t count,
+                   int shift, int is_signed) {
+    for (size_t i = blockIdx.x * (size_t)THREADS + threadIdx.x; i < count;
+         i += (size_t)gridDim.x * THREADS)
+        y[i] = f8::requant(x[i], shift, is_signed);
+}
+
+unsigned grid_for(long long total) {
+    long long b = (total + THREADS - 1) / THREADS;
+    const long long cap = 148LL * 8 * 8;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+f8::Epilogue make_ep(const f8_conv_args &a) {
+    f8::Epilogue ep{};
+    ep.bias = a.bias;
+    ep.carry_in = a.carry_in;
+    ep.carry_out = a.carry_out;
+    ep.out0 = static_cast<uint8_t *>(a.out[0]);
+    ep.out1 = static_cast<uint8_t *>(a.out[1]);
+    ep.carry_shift = a.carry_shift;
+    ep.relu = a.relu;
+    ep.shift0 = a.out_shift[0]; ep.signed0 = a.out_signed[0];
+    ep.shift1 = a.out_shift[1]; ep.signed1 = a.out_signed[1];
+    ep.cout = a.cout; ep.cout_pad = a.cout_pad;
+    return ep;
+}
+
+}  // namespace
+
+namespace f8host {
+
+int launch_maxpool(const f8_conv_args &a, cudaStream_t s) {
+    if (a.kh != 3 || a.kw != 3 || a.stride != 2 || a.pad != 1 || a.cin_pad != a.cout_pad ||
+        a.cin_pad % 4 != 0) {
+        set_error("maxpool: only 3x3 stride 2 pad 1 (fix_resnet.py:439)");
+        return F8_ERR_UNSUPPORTED;
+    }
+    const long long total = (long long)a.n * a.hout * a.wout * (a.cin_pad >> 2);
+    maxpool_kernel<<<grid_for(total), THREADS, 0, s>>>(static_cast<const int32_t *>(a.in), a.n,
+                                                       a.hin, a.win, a.hout, a.wout, a.cin_pad,
+                                                       make_ep(a));
+    F8_CUDA(cudaGetLastError());
+    return F8_OK;
+}
+
+int launch_pool_requant(const f8_conv_args &a, cudaStream_t s) {
+    const long long total = (long long)a.n * a.cin_pad;
+    pool_requant_kernel<<<grid_for(total), THREADS, 0, s>>>(static_cast<const int32_t *>(a.in),
+                                                            a.n, a.hin * a.win, a.cin_pad,
+                                                            make_ep(a));
+    F8_CUDA(cudaGetLastError());
+    return F8_OK;
+}
+
+int launch_convert_input(const int32_t *x, void *out, int n, int h, int w, int, cudaStream_t s) {
+    const long long total = (long long)n * h * w;
+    convert_input_kernel<<<grid_for(total), THREADS, 0, s>>>(x, static_cast<uint32_t *>(out), n,
+                                                             h * w);
+    F8_CUDA(cudaGetLastError());
+    return F8_OK;
+}
+
+int launch_requant_i32(const int32_t *x, int32_t *y, size_t count, int shift, int is_signed,
+                       cudaStream_t s) {
+    requant_i32_kernel<<<grid_for((long long)count), THREADS, 0, s>>>(x, y, count, shift,
+                                                                      is_signed);
+    F8_CUDA(cudaGetLastError());
+    return F8_OK;
+}
+
+}  // namespace f8host

@@ -1,0 +1,209 @@
+/*
+ * f8b200.h -- C ABI of libf8b200.so, the B200 (sm_100a) engine for F8Net's int_op_only
+ * forward path.
+ *
+ * The reference (snap-research/F8Net) has no FFI: its int_op_only path is Python calling
+ * torch ATen CPU int32 kernels.  The entry points below are what a binding for that path
+ * binds instead; each one names the reference interface it replaces.  INTEGRATION.md shows
+ * the reference-side stub (ctypes) a maintainer would add.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no torch / C++ types; every call returns 0 (F8_OK)
+ *     or a negative f8_status, never throws; f8_last_error() gives the message (thread local).
+ *   - device memory for activations, logits and the workspace is OWNED BY THE CALLER
+ *     (torch tensors on the host side); a plan owns only its repacked weights.
+ *   - all work is enqueued on the caller's stream (cudaStream_t passed as void*); no hidden
+ *     synchronisation.  A plan is immutable after creation, so f8_plan_run is re-entrant
+ *     across streams as long as each caller brings its own workspace.
+ *   - activations between layers are NHWC, 8 bit (u8 or s8 as the consumer's
+ *     input_symmetric says), channels padded to a multiple of 32 with zeros; residual
+ *     carries are NHWC int32 with the same channel padding.
+ */
+#ifndef F8B200_H_
+#define F8B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define F8_ABI_VERSION 1
+
+typedef enum f8_status {
+    F8_OK = 0,
+    F8_ERR_ARG = -1,          /* malformed descriptor / null pointer / shape mismatch          */
+    F8_ERR_CUDA = -2,         /* a CUDA runtime call failed; see f8_last_error()               */
+    F8_ERR_UNSUPPORTED = -3,  /* valid for the reference but outside this engine (e.g. shift>30)*/
+    F8_ERR_NOMEM = -4
+} f8_status;
+
+/* Layout of the input handed to f8_plan_run (reference call surface: model(x) with x int32
+ * NCHW, fix_resnet.py:352 / fix_mobilenet_v1.py:120 / fix_mobilenet_v2.py:207). */
+typedef enum f8_input_layout {
+    F8_IN_NCHW_I32 = 0,   /* the reference's own tensor: int32 [N,3,H,W], values in 8-bit range */
+    F8_IN_NHWC4_8 = 1     /* engine-native: 8-bit [N,H,W,4] (channel 3 = 0), u8 or s8 per head   */
+} f8_input_layout;
+
+typedef enum f8_op_kind {
+    F8_OP_CONVERT_INPUT = 0,  /* NCHW int32 -> NHWC4 8 bit                                      */
+    F8_OP_CONV_DENSE = 1,     /* groups == 1 conv or nn.Linear, tensor cores, fused epilogue    */
+    F8_OP_CONV_DW = 2,        /* depthwise 3x3, CUDA-core int MAC, fused epilogue               */
+    F8_OP_MAXPOOL = 3,        /* ResNet head 3x3 s2 p1 max-pool with float32 round trip         */
+    F8_OP_POOL_REQUANT = 4    /* FXQAvgPool2d sum over HxW + requant for the classifier         */
+} f8_op_kind;
+
+/*
+ * One fused launch.  "Epilogue" = everything the reference does between one int layer's
+ * accumulator and the 8-bit input of the next int layer(s), in the reference's order:
+ *
+ *   v  = acc + bias                                   nn.Conv2d/nn.Linear bias (fix_quant_ops.py:706)
+ *   if carry_in:  d = carry_shift                     IntBlock residual, fix_resnet.py:40-76,
+ *       d >= 0 ? carry <<= d : v <<= -d  (wrap)       fix_mobilenet_v2.py:34-48
+ *       v = max(v + carry (wrap), INT32_MIN+1)
+ *   if relu:      v = max(v, 0)                        nn.ReLU in body / post_relu / head / tail
+ *   if carry_out: carry_out = v                        int32 tensor a later residual add reads
+ *   for j in 0,1 if out[j]:                            int_op_only_fix_quant of the consumer,
+ *       out[j] = requant(v, out_shift[j], out_signed[j])   fix_quant_ops.py:90-114
+ *   if out_f32:   out_f32 = (float) v                  classifier(x).float(), fix_resnet.py:383
+ *
+ * requant(v, n, s): n > 0: round-half-even(v / 2^n) by the reference's exact formula;
+ * n <= 0: wrapping v << -n; then clamp to [-127,127] (s) or [0,255].
+ * Buffers are referred to by index into the plan's buffer table; -1 = unused.
+ */
+typedef struct f8_op {
+    int32_t kind;              /* f8_op_kind */
+    /* geometry (per image) */
+    int32_t cin, cout;         /* logical channels                                   */
+    int32_t cin_pad, cout_pad; /* channel counts of the NHWC buffers                 */
+    int32_t kh, kw, stride, pad;
+    int32_t hin, win, hout, wout;
+    int32_t in_signed;         /* activation operand: 1 = s8 (input_symmetric), 0 = u8 */
+    /* operands */
+    int32_t in_buf;            /* 8-bit NHWC input (int32 NHWC for MAXPOOL / POOL_REQUANT);
+                                  -2 = the plan input x (CONVERT_INPUT, or head conv when
+                                  the caller passes F8_IN_NHWC4_8)                     */
+    const int32_t *weight;     /* HOST, reference layout [O, C/g, kh, kw] or [O, K]  */
+    const int32_t *bias;       /* HOST, [O]                                          */
+    /* epilogue */
+    int32_t carry_in_buf;
+    int32_t carry_shift;
+    int32_t relu;
+    int32_t carry_out_buf;
+    int32_t out_buf[2];
+    int32_t out_shift[2];
+    int32_t out_signed[2];
+    int32_t out_f32;           /* 1: write float logits to the plan output          */
+} f8_op;
+
+/* One workspace buffer: bytes per image and its offset (in per-image bytes) inside the
+ * workspace; the address at run time is  workspace + offset_per_image * N.  Offsets are
+ * chosen by the caller (the host planner reuses dead buffers); multiples of 256. */
+typedef struct f8_buffer {
+    int64_t bytes_per_image;
+    int64_t offset_per_image;
+} f8_buffer;
+
+typedef struct f8_model_desc {
+    int32_t abi_version;       /* F8_ABI_VERSION */
+    int32_t n_ops;
+    const f8_op *ops;
+    int32_t n_buffers;
+    const f8_buffer *buffers;
+    int64_t workspace_per_image;  /* max over buffers of offset + bytes (multiple of 256) */
+    int32_t image_h, image_w;     /* 224 x 224 */
+    int32_t num_classes;          /* 1000 */
+    int32_t head_signed;          /* head conv input_symmetric */
+} f8_model_desc;
+
+typedef struct f8_plan f8_plan;
+
+/* Replaces: Model.int_model() + .cpu() hand-over (fix_train.py:930-935) -- the engine takes
+ * the int32 tensors of IntModel.state_dict() as they are and repacks them to int8 tiles. */
+int f8_plan_create(const f8_model_desc *desc, int device, f8_plan **out);
+void f8_plan_destroy(f8_plan *plan);
+
+/* Bytes of caller-owned device workspace needed to run up to max_batch images at once. */
+int f8_plan_workspace_bytes(const f8_plan *plan, int max_batch, size_t *bytes);
+
+/* Replaces: output = model(input) (fix_train.py:693) i.e. IntModel.forward, int_op_only
+ * branch.  x_dev: device input in x_layout; logits_dev: float32 [n, num_classes] holding the
+ * exact int32 logits (fix_resnet.py:383).  chunk: images per pass through the layer list
+ * (<= the batch the workspace was sized for; 0 = n). */
+int f8_plan_run(f8_plan *plan, const void *x_dev, int x_layout, int n, float *logits_dev,
+                void *workspace_dev, size_t workspace_bytes, int chunk, void *stream);
+
+/* Same, with HOST buffers (pinned or pageable): copies x host->device, runs, copies the
+ * logits back, all on `stream`, then synchronises the stream.  x_stage_dev must hold the
+ * input (n * 3*H*W*4 bytes for NCHW_I32, n * H*W*4 for NHWC4_8).  This is the entry the
+ * reference-facing call surface uses for CPU tensors. */
+int f8_plan_run_host(f8_plan *plan, const void *x_host, int x_layout, int n, float *logits_host,
+                     void *x_stage_dev, float *logits_dev, void *workspace_dev,
+                     size_t workspace_bytes, int chunk, void *stream);
+
+/* Number of kernel launches one f8_plan_run(n, chunk) enqueues. */
+int f8_plan_launch_count(const f8_plan *plan, int n, int chunk);
+/* Which dense-conv backend the plan uses: 0 = mma.sync (legacy IMMA), 1 = tcgen05 (UMMA+TMA) */
+int f8_plan_set_backend(f8_plan *plan, int backend);
+
+/* ------------------------------------------------------------------------------------
+ * Per-kernel entry points (layer-level parity tests; same kernels the plan launches).
+ * All pointers are DEVICE pointers except where noted.
+ * ---------------------------------------------------------------------------------- */
+typedef struct f8_conv_args {
+    int32_t n;
+    int32_t cin, cout, cin_pad, cout_pad;
+    int32_t kh, kw, stride, pad;
+    int32_t hin, win, hout, wout;
+    int32_t in_signed;
+    const void *in;            /* 8-bit NHWC [n,hin,win,cin_pad] (int32 for maxpool / pool) */
+    const void *wpack;         /* from f8_pack_weights                                    */
+    const int32_t *bias;       /* [cout_pad], zero padded                                 */
+    const int32_t *carry_in;   /* int32 NHWC [n,hout,wout,cout_pad] or NULL               */
+    int32_t carry_shift;
+    int32_t relu;
+    int32_t *carry_out;        /* or NULL                                                 */
+    void *out[2];              /* 8-bit NHWC [n,hout,wout,cout_pad] or NULL               */
+    int32_t out_shift[2];
+    int32_t out_signed[2];
+    float *out_f32;            /* [n*hout*wout, out_f32_ld] or NULL                       */
+    int32_t out_f32_ld;
+} f8_conv_args;
+
+/* Bytes of the packed weight image for a layer and the packing itself (host -> host).
+ * kind: F8_OP_CONV_DENSE or F8_OP_CONV_DW.  weight: reference layout int32. */
+size_t f8_pack_weights_bytes(int kind, int cin, int cout, int cin_pad, int cout_pad, int kh,
+                             int kw);
+int f8_pack_weights(int kind, const int32_t *weight, int cin, int cout, int cin_pad,
+                    int cout_pad, int kh, int kw, void *dst_host);
+
+/* Replaces: int nn.Conv2d.__call__ (groups == 1) / nn.Linear.__call__ + the consumer-side
+ * int_op_only_fix_quant, ReLU and residual add around it (fix_resnet.py:28-77). */
+int f8_conv_dense(const f8_conv_args *a, int backend, void *stream);
+/* Replaces: int nn.Conv2d.__call__ with groups == in_channels (fix_mobilenet_v1.py:33,
+ * fix_mobilenet_v2.py:28) + consumer-side requant / ReLU. */
+int f8_conv_dw3x3(const f8_conv_args *a, void *stream);
+/* Replaces: self.head[-1](x.float()).int()  (fix_resnet.py:358-359). in = int32 NHWC. */
+int f8_maxpool3x3s2(const f8_conv_args *a, void *stream);
+/* Replaces: FXQAvgPool2d.forward int branch + int_op_only_fix_quant for the classifier
+ * (fix_quant_ops.py:126-134, fix_resnet.py:367-374). in = int32 NHWC [n,h,w,c_pad],
+ * out[0] = 8-bit [n,c_pad]. */
+int f8_pool_requant(const f8_conv_args *a, void *stream);
+/* Replaces: the int32 NCHW tensor hand-over at model(x): repack to NHWC4 8 bit.
+ * x int32 [n,3,h,w] -> out 8-bit [n,h,w,4]. */
+int f8_convert_input(const int32_t *x, void *out, int n, int h, int w, void *stream);
+/* Replaces: int_op_only_fix_quant as a standalone op (fix_quant_ops.py:90-114):
+ * y[i] = requant(x[i], input_fl - fl, is_signed), int32 in / int32 out. */
+int f8_requant_i32(const int32_t *x, int32_t *y, size_t count, int fl, int input_fl,
+                   int is_signed, void *stream);
+
+const char *f8_last_error(void);
+int f8_abi_version(void);
+/* 1 when the library was built with the tcgen05 path and the device is sm_100 */
+int f8_has_umma(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* F8B200_H_ */
