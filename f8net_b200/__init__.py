@@ -1,0 +1,18 @@
+"""f8net_b200 -- B200 (sm_100a) engine for F8Net's integer-only (int_op_only) forward path.
+
+Only what the hot path needs lives here: the CUDA kernels + C ABI (csrc/, libf8b200.so), the
+integer-graph description of the four networks (arch), the host planner that fuses the
+reference's tensor-op chain into kernel epilogues (planner) and the reference-facing call
+surface (engine).  ``synth`` makes the seeded synthetic workloads of bench.py / the tests.
+"""
+from .arch import ARCHS, graph_for, graph_from_module  # noqa: F401
+
+
+def compile(*args, **kwargs):
+    from .engine import compile as _compile
+    return _compile(*args, **kwargs)
+
+
+def build(force=False):
+    from .build import build as _build
+    return _build(force=force)

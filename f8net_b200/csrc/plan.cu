@@ -1,0 +1,502 @@
+// plan.cu -- the C ABI of libf8b200.so (include/f8b200.h): weight repacking, the execution
+// plan (an ordered list of fused launches over caller-owned device buffers) and the
+// per-kernel entry points used by the layer-level parity tests.
+//
+// What a plan replaces in the reference: the hand-over of Model.int_model()
+// (/root/reference/fix_train.py:930-935) and every output = model(input) call
+// (/root/reference/fix_train.py:693) on the int_op_only branch of IntModel.forward
+// (/root/reference/models/fix_resnet.py:352-383, fix_mobilenet_v1.py:120-147,
+// fix_mobilenet_v2.py:207-241).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "f8_common.cuh"
+
+namespace f8host {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    (void)cudaGetLastError();
+    return F8_ERR_CUDA;
+}
+
+}  // namespace f8host
+
+using f8host::set_error;
+
+namespace {
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct PlanOp {
+    f8_op op;
+    size_t w_off = 0;   // byte offset of the packed weights inside the device blob
+    size_t b_off = 0;   // byte offset of the padded bias
+};
+
+}  // namespace
+
+struct f8_plan {
+    int device = 0;
+    int backend = 0;
+    std::vector<PlanOp> ops;
+    std::vector<f8_buffer> bufs;
+    int64_t ws_per_image = 0;
+    int image_h = 0, image_w = 0, num_classes = 0, head_signed = 0;
+    int convert_op = -1;        // index of the F8_OP_CONVERT_INPUT op, if any
+    uint8_t *blob = nullptr;    // device: packed weights + biases of every op
+    size_t blob_bytes = 0;
+};
+
+// ---------------------------------------------------------------------------------------
+// weight packing (host -> host)
+// ---------------------------------------------------------------------------------------
+extern "C" size_t f8_pack_weights_bytes(int kind, int cin, int cout, int cin_pad, int cout_pad,
+                                        int kh, int kw) {
+    (void)cin; (void)cout;
+    if (kind == F8_OP_CONV_DW) return (size_t)12 * (size_t)cin_pad;   // [12][cpad/4] u32
+    if (kind == F8_OP_CONV_DENSE) {
+        const f8host::DensePack p = f8host::dense_pack_geometry(cin_pad, cout_pad, kh, kw);
+        return (size_t)p.rows * (size_t)p.K_pad;
+    }
+    return 0;
+}
+
+extern "C" int f8_pack_weights(int kind, const int32_t *weight, int cin, int cout, int cin_pad,
+                               int cout_pad, int kh, int kw, void *dst_host) {
+    if (!weight || !dst_host || cin <= 0 || cout <= 0 || cin_pad < cin || cout_pad < cout) {
+        set_error("pack_weights: bad arguments");
+        return F8_ERR_ARG;
+    }
+    const size_t bytes = f8_pack_weights_bytes(kind, cin, cout, cin_pad, cout_pad, kh, kw);
+    if (!bytes) {
+        set_error("pack_weights: kind %d has no weights", kind);
+        return F8_ERR_ARG;
+    }
+    std::memset(dst_host, 0, bytes);
+    if (kind == F8_OP_CONV_DW) {
+        // reference layout [C,1,3,3]; dp4a operand k of channel ch holds taps 4k..4k+3
+        if (kh != 3 || kw != 3 || cin != cout || cin_pad != cout_pad || (cin_pad & 3)) {
+            set_error("pack_weights: depthwise needs 3x3, cin == cout, cpad %% 4 == 0");
+            return F8_ERR_UNSUPPORTED;
+        }
+        const int c4n = cin_pad >> 2;
+        uint32_t *dst = static_cast<uint32_t *>(dst_host);
+        for (int ch = 0; ch < cin; ++ch) {
+            const int c4 = ch >> 2, c = ch & 3;
+            for (int t = 0; t < 9; ++t) {
+                const int32_t w = weight[(size_t)ch * 9 + t];
+                if (w < -128 || w > 127) {
+                    set_error("pack_weights: weight %d outside the 8-bit range", w);
+                    return F8_ERR_UNSUPPORTED;
+                }
+                const int k = t >> 2, byte = t & 3;
+                dst[(size_t)(c * 3 + k) * c4n + c4] |= ((uint32_t)w & 0xffu) << (8 * byte);
+            }
+        }
+        return F8_OK;
+    }
+    const f8host::DensePack p = f8host::dense_pack_geometry(cin_pad, cout_pad, kh, kw);
+    int8_t *dst = static_cast<int8_t *>(dst_host);
+    for (int o = 0; o < cout; ++o)
+        for (int c = 0; c < cin; ++c)
+            for (int r = 0; r < kh; ++r)
+                for (int s = 0; s < kw; ++s) {
+                    const int32_t w = weight[(((size_t)o * cin + c) * kh + r) * kw + s];
+                    if (w < -128 || w > 127) {
+                        set_error("pack_weights: weight %d outside the 8-bit range", w);
+                        return F8_ERR_UNSUPPORTED;
+                    }
+                    const size_t k = p.mode == 1
+                                         ? (size_t)r * p.row_bytes + (size_t)(s + p.shift_px) * 4 + c
+                                         : ((size_t)r * kw + s) * cin_pad + c;
+                    dst[(size_t)o * p.K_pad + k] = (int8_t)w;
+                }
+    return F8_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------
+static bool buf_ok(const f8_model_desc *d, int b) { return b >= -1 && b < d->n_buffers; }
+
+static int check_shift(int s, const char *what) {
+    if (s > 30 || s < -30) {   // what the reference's `1 << net_fl` on int32 can express
+        set_error("%s shift %d is outside +-30", what, s);
+        return F8_ERR_UNSUPPORTED;
+    }
+    return F8_OK;
+}
+
+extern "C" int f8_plan_create(const f8_model_desc *desc, int device, f8_plan **out) {
+    if (!desc || !out) { set_error("plan_create: null argument"); return F8_ERR_ARG; }
+    *out = nullptr;
+    if (desc->abi_version != F8_ABI_VERSION) {
+        set_error("plan_create: ABI version %d, library is %d", desc->abi_version, F8_ABI_VERSION);
+        return F8_ERR_ARG;
+    }
+    if (desc->n_ops <= 0 || !desc->ops || desc->n_buffers < 0 || (desc->n_buffers && !desc->buffers)) {
+        set_error("plan_create: empty descriptor");
+        return F8_ERR_ARG;
+    }
+    f8_plan *p = new (std::nothrow) f8_plan();
+    if (!p) { set_error("plan_create: out of host memory"); return F8_ERR_NOMEM; }
+    p->device = device;
+    p->ws_per_image = desc->workspace_per_image;
+    p->image_h = desc->image_h; p->image_w = desc->image_w;
+    p->num_classes = desc->num_classes; p->head_signed = desc->head_signed;
+    p->bufs.assign(desc->buffers, desc->buffers + desc->n_buffers);
+    for (const f8_buffer &b : p->bufs) {
+        if (b.bytes_per_image < 0 || b.offset_per_image < 0 || (b.offset_per_image % 256) ||
+            b.offset_per_image + b.bytes_per_image > desc->workspace_per_image) {
+            set_error("plan_create: buffer table inconsistent with workspace_per_image");
+            delete p;
+            return F8_ERR_ARG;
+        }
+    }
+    // pass 1: validate, size the blob
+    size_t blob = 0;
+    p->ops.resize(desc->n_ops);
+    for (int i = 0; i < desc->n_ops; ++i) {
+        PlanOp &po = p->ops[i];
+        po.op = desc->ops[i];
+        const f8_op &o = po.op;
+        int rc = F8_OK;
+        if (!buf_ok(desc, o.carry_in_buf) || !buf_ok(desc, o.carry_out_buf) ||
+            !buf_ok(desc, o.out_buf[0]) || !buf_ok(desc, o.out_buf[1]) ||
+            !(o.in_buf >= -2 && o.in_buf < desc->n_buffers)) {
+            set_error("plan_create: op %d refers to a buffer outside the table", i);
+            rc = F8_ERR_ARG;
+        }
+        if (!rc) rc = check_shift(o.carry_shift, "residual");
+        if (!rc) rc = check_shift(o.out_shift[0], "requant");
+        if (!rc) rc = check_shift(o.out_shift[1], "requant");
+        if (!rc && (o.kind == F8_OP_CONV_DENSE || o.kind == F8_OP_CONV_DW)) {
+            if (!o.weight || !o.bias) {
+                set_error("plan_create: op %d has no weight / bias", i);
+                rc = F8_ERR_ARG;
+            } else {
+                po.w_off = blob;
+                blob += align_up(f8_pack_weights_bytes(o.kind, o.cin, o.cout, o.cin_pad,
+                                                       o.cout_pad, o.kh, o.kw), kAlign);
+                po.b_off = blob;
+                blob += align_up((size_t)o.cout_pad * sizeof(int32_t), kAlign);
+            }
+        }
+        if (!rc && o.kind == F8_OP_CONVERT_INPUT) {
+            if (p->convert_op >= 0 || o.out_buf[0] < 0) {
+                set_error("plan_create: at most one CONVERT_INPUT op, with out_buf[0] set");
+                rc = F8_ERR_ARG;
+            }
+            p->convert_op = i;
+        }
+        if (rc) { delete p; return rc; }
+    }
+    // pass 2: pack on the host, one upload
+    std::vector<uint8_t> host(blob ? blob : 1, 0);
+    for (PlanOp &po : p->ops) {
+        const f8_op &o = po.op;
+        if (o.kind != F8_OP_CONV_DENSE && o.kind != F8_OP_CONV_DW) continue;
+        int rc = f8_pack_weights(o.kind, o.weight, o.cin, o.cout, o.cin_pad, o.cout_pad, o.kh,
+                                 o.kw, host.data() + po.w_off);
+        if (rc) { delete p; return rc; }
+        std::memcpy(host.data() + po.b_off, o.bias, (size_t)o.cout * sizeof(int32_t));
+        po.op.weight = nullptr;   // host pointers are not kept: the caller owns them
+        po.op.bias = nullptr;
+    }
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&p->blob), host.size());
+    if (e == cudaSuccess) e = cudaMemcpy(p->blob, host.data(), host.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (p->blob) cudaFree(p->blob);
+        delete p;
+        return f8host::cuda_fail(e, "plan_create upload");
+    }
+    p->blob_bytes = host.size();
+    *out = p;
+    return F8_OK;
+}
+
+extern "C" void f8_plan_destroy(f8_plan *plan) {
+    if (!plan) return;
+    if (plan->blob) cudaFree(plan->blob);
+    delete plan;
+}
+
+extern "C" int f8_plan_workspace_bytes(const f8_plan *plan, int max_batch, size_t *bytes) {
+    if (!plan || !bytes || max_batch <= 0) { set_error("workspace_bytes: bad arguments"); return F8_ERR_ARG; }
+    *bytes = (size_t)plan->ws_per_image * (size_t)max_batch;
+    return F8_OK;
+}
+
+extern "C" int f8_plan_set_backend(f8_plan *plan, int backend) {
+    if (!plan || backend < 0 || backend > 1) { set_error("set_backend: bad arguments"); return F8_ERR_ARG; }
+    if (backend == 1 && !f8_has_umma(plan->device)) {
+        set_error("set_backend: tcgen05 backend not available on device %d", plan->device);
+        return F8_ERR_UNSUPPORTED;
+    }
+    plan->backend = backend;
+    return F8_OK;
+}
+
+extern "C" int f8_plan_launch_count(const f8_plan *plan, int x_layout, int n, int chunk) {
+    if (!plan || n <= 0) return 0;
+    if (chunk <= 0 || chunk > n) chunk = n;
+    const int passes = (n + chunk - 1) / chunk;
+    int per = (int)plan->ops.size();
+    if (x_layout == F8_IN_NHWC4_8 && plan->convert_op >= 0) --per;
+    return per * passes;
+}
+
+static int run_op(const f8_plan *p, const PlanOp &po, int n, const uint8_t *x, bool x_is_nhwc4,
+                  float *logits, uint8_t *ws, int cap, cudaStream_t s) {
+    const f8_op &o = po.op;
+    auto buf = [&](int b) -> uint8_t * {
+        if (b < 0) return nullptr;
+        if (x_is_nhwc4 && p->convert_op >= 0 && b == p->ops[p->convert_op].op.out_buf[0])
+            return const_cast<uint8_t *>(x);
+        return ws + (size_t)p->bufs[b].offset_per_image * (size_t)cap;
+    };
+    if (o.kind == F8_OP_CONVERT_INPUT) {
+        if (x_is_nhwc4) return F8_OK;
+        return f8host::launch_convert_input(reinterpret_cast<const int32_t *>(x), buf(o.out_buf[0]),
+                                            n, o.hin, o.win, o.in_signed, s);
+    }
+    f8_conv_args a{};
+    a.n = n;
+    a.cin = o.cin; a.cout = o.cout; a.cin_pad = o.cin_pad; a.cout_pad = o.cout_pad;
+    a.kh = o.kh; a.kw = o.kw; a.stride = o.stride; a.pad = o.pad;
+    a.hin = o.hin; a.win = o.win; a.hout = o.hout; a.wout = o.wout;
+    a.in_signed = o.in_signed;
+    a.in = o.in_buf == -2 ? x : buf(o.in_buf);
+    a.wpack = p->blob + po.w_off;
+    a.bias = reinterpret_cast<const int32_t *>(p->blob + po.b_off);
+    a.carry_in = reinterpret_cast<const int32_t *>(buf(o.carry_in_buf));
+    a.carry_shift = o.carry_shift;
+    a.relu = o.relu;
+    a.carry_out = reinterpret_cast<int32_t *>(buf(o.carry_out_buf));
+    for (int j = 0; j < 2; ++j) {
+        a.out[j] = buf(o.out_buf[j]);
+        a.out_shift[j] = o.out_shift[j];
+        a.out_signed[j] = o.out_signed[j];
+    }
+    a.out_f32 = o.out_f32 ? logits : nullptr;
+    a.out_f32_ld = p->num_classes;
+    switch (o.kind) {
+        case F8_OP_CONV_DENSE: return f8_conv_dense(&a, p->backend, s);
+        case F8_OP_CONV_DW: return f8host::launch_dw3x3(a, s);
+        case F8_OP_MAXPOOL: return f8host::launch_maxpool(a, s);
+        case F8_OP_POOL_REQUANT: return f8host::launch_pool_requant(a, s);
+        default: set_error("plan_run: unknown op kind %d", o.kind); return F8_ERR_ARG;
+    }
+}
+
+static int plan_run_impl(f8_plan *plan, const void *x_dev, int x_layout, int n,
+                         float *logits_dev, void *workspace_dev, size_t workspace_bytes,
+                         int chunk, void *stream, std::vector<cudaEvent_t> *events);
+
+extern "C" int f8_plan_run(f8_plan *plan, const void *x_dev, int x_layout, int n,
+                           float *logits_dev, void *workspace_dev, size_t workspace_bytes,
+                           int chunk, void *stream) {
+    return plan_run_impl(plan, x_dev, x_layout, n, logits_dev, workspace_dev, workspace_bytes,
+                         chunk, stream, nullptr);
+}
+
+// Per-launch device times of one f8_plan_run: CUDA events recorded on `stream` right before
+// and after every launch.  op_ms[i] = time of op i summed over the passes (chunks).
+extern "C" int f8_plan_profile(f8_plan *plan, const void *x_dev, int x_layout, int n,
+                               float *logits_dev, void *workspace_dev, size_t workspace_bytes,
+                               int chunk, void *stream, float *op_ms, int n_ops) {
+    if (!plan || !op_ms || n_ops != (int)plan->ops.size()) {
+        set_error("plan_profile: op_ms must hold one float per plan op (%d)",
+                  plan ? (int)plan->ops.size() : -1);
+        return F8_ERR_ARG;
+    }
+    std::vector<cudaEvent_t> ev;
+    int rc = plan_run_impl(plan, x_dev, x_layout, n, logits_dev, workspace_dev, workspace_bytes,
+                           chunk, stream, &ev);
+    cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    for (int i = 0; i < n_ops; ++i) op_ms[i] = 0.f;
+    if (!rc && e == cudaSuccess) {
+        const size_t per = 2 * plan->ops.size();
+        for (size_t base = 0; base + per <= ev.size(); base += per)
+            for (int i = 0; i < n_ops; ++i) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, ev[base + 2 * i], ev[base + 2 * i + 1]) == cudaSuccess)
+                    op_ms[i] += ms;
+            }
+    }
+    for (cudaEvent_t x : ev) cudaEventDestroy(x);
+    if (rc) return rc;
+    if (e != cudaSuccess) return f8host::cuda_fail(e, "plan_profile sync");
+    return F8_OK;
+}
+
+static int plan_run_impl(f8_plan *plan, const void *x_dev, int x_layout, int n,
+                         float *logits_dev, void *workspace_dev, size_t workspace_bytes,
+                         int chunk, void *stream, std::vector<cudaEvent_t> *events) {
+    if (!plan || !x_dev || !logits_dev || !workspace_dev || n <= 0) {
+        set_error("plan_run: bad arguments");
+        return F8_ERR_ARG;
+    }
+    if (x_layout != F8_IN_NCHW_I32 && x_layout != F8_IN_NHWC4_8) {
+        set_error("plan_run: unknown input layout %d", x_layout);
+        return F8_ERR_ARG;
+    }
+    if (x_layout == F8_IN_NCHW_I32 && plan->convert_op < 0) {
+        set_error("plan_run: plan has no CONVERT_INPUT op for an int32 NCHW input");
+        return F8_ERR_ARG;
+    }
+    if (chunk <= 0 || chunk > n) chunk = n;
+    if ((size_t)plan->ws_per_image * (size_t)chunk > workspace_bytes) {
+        set_error("plan_run: workspace of %zu bytes is too small for %d images per pass (%zu needed)",
+                  workspace_bytes, chunk, (size_t)plan->ws_per_image * (size_t)chunk);
+        return F8_ERR_ARG;
+    }
+    int cur = -1;
+    F8_CUDA(cudaGetDevice(&cur));
+    if (cur != plan->device) F8_CUDA(cudaSetDevice(plan->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool nhwc4 = x_layout == F8_IN_NHWC4_8;
+    const size_t x_img = nhwc4 ? (size_t)plan->image_h * plan->image_w * 4
+                               : (size_t)plan->image_h * plan->image_w * 3 * sizeof(int32_t);
+    for (int i0 = 0; i0 < n; i0 += chunk) {
+        const int nn = (n - i0 < chunk) ? (n - i0) : chunk;
+        const uint8_t *x = static_cast<const uint8_t *>(x_dev) + (size_t)i0 * x_img;
+        float *lg = logits_dev + (size_t)i0 * plan->num_classes;
+        for (const PlanOp &po : plan->ops) {
+            if (events) {
+                cudaEvent_t a, b;
+                F8_CUDA(cudaEventCreate(&a));
+                events->push_back(a);
+                F8_CUDA(cudaEventCreate(&b));
+                events->push_back(b);
+                F8_CUDA(cudaEventRecord(a, s));
+            }
+            int rc = run_op(plan, po, nn, x, nhwc4, lg, static_cast<uint8_t *>(workspace_dev),
+                            chunk, s);
+            if (rc) return rc;
+            if (events) F8_CUDA(cudaEventRecord(events->back(), s));
+        }
+    }
+    return F8_OK;
+}
+
+extern "C" int f8_plan_run_host(f8_plan *plan, const void *x_host, int x_layout, int n,
+                                float *logits_host, void *x_stage_dev, float *logits_dev,
+                                void *workspace_dev, size_t workspace_bytes, int chunk,
+                                int sync, void *stream) {
+    if (!plan || !x_host || !logits_host || !x_stage_dev || !logits_dev || n <= 0) {
+        set_error("plan_run_host: bad arguments");
+        return F8_ERR_ARG;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t x_img = x_layout == F8_IN_NHWC4_8
+                             ? (size_t)plan->image_h * plan->image_w * 4
+                             : (size_t)plan->image_h * plan->image_w * 3 * sizeof(int32_t);
+    int cur = -1;
+    F8_CUDA(cudaGetDevice(&cur));
+    if (cur != plan->device) F8_CUDA(cudaSetDevice(plan->device));
+    F8_CUDA(cudaMemcpyAsync(x_stage_dev, x_host, x_img * (size_t)n, cudaMemcpyHostToDevice, s));
+    int rc = f8_plan_run(plan, x_stage_dev, x_layout, n, logits_dev, workspace_dev,
+                         workspace_bytes, chunk, stream);
+    if (rc) return rc;
+    F8_CUDA(cudaMemcpyAsync(logits_host, logits_dev,
+                            (size_t)n * plan->num_classes * sizeof(float),
+                            cudaMemcpyDeviceToHost, s));
+    if (sync) F8_CUDA(cudaStreamSynchronize(s));
+    return F8_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// per-kernel entry points
+// ---------------------------------------------------------------------------------------
+static int check_args(const f8_conv_args *a, const char *who) {
+    if (!a || !a->in || a->n <= 0) { set_error("%s: bad arguments", who); return F8_ERR_ARG; }
+    int rc = check_shift(a->carry_shift, who);
+    if (!rc) rc = check_shift(a->out_shift[0], who);
+    if (!rc) rc = check_shift(a->out_shift[1], who);
+    return rc;
+}
+
+extern "C" int f8_conv_dense(const f8_conv_args *a, int backend, void *stream) {
+    int rc = check_args(a, "conv_dense");
+    if (rc) return rc;
+    if (!a->wpack || !a->bias) { set_error("conv_dense: no weights / bias"); return F8_ERR_ARG; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (backend == 1) {
+        rc = f8host::launch_conv_umma(*a, s);
+        if (rc != F8_ERR_UNSUPPORTED) return rc;   // shapes outside the tcgen05 kernel: IMMA path
+    }
+    return f8host::launch_conv_mma(*a, s);
+}
+
+extern "C" int f8_conv_dw3x3(const f8_conv_args *a, void *stream) {
+    int rc = check_args(a, "conv_dw3x3");
+    if (rc) return rc;
+    if (!a->wpack || !a->bias) { set_error("conv_dw3x3: no weights / bias"); return F8_ERR_ARG; }
+    return f8host::launch_dw3x3(*a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int f8_maxpool3x3s2(const f8_conv_args *a, void *stream) {
+    int rc = check_args(a, "maxpool3x3s2");
+    if (rc) return rc;
+    return f8host::launch_maxpool(*a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int f8_pool_requant(const f8_conv_args *a, void *stream) {
+    int rc = check_args(a, "pool_requant");
+    if (rc) return rc;
+    return f8host::launch_pool_requant(*a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int f8_convert_input(const int32_t *x, void *out, int n, int h, int w, void *stream) {
+    if (!x || !out || n <= 0 || h <= 0 || w <= 0) { set_error("convert_input: bad arguments"); return F8_ERR_ARG; }
+    return f8host::launch_convert_input(x, out, n, h, w, 0, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int f8_requant_i32(const int32_t *x, int32_t *y, size_t count, int fl, int input_fl,
+                              int is_signed, void *stream) {
+    if (!x || !y) { set_error("requant_i32: null pointer"); return F8_ERR_ARG; }
+    const int shift = input_fl - fl;
+    int rc = check_shift(shift, "requant_i32");
+    if (rc) return rc;
+    if (!count) return F8_OK;
+    return f8host::launch_requant_i32(x, y, count, shift, is_signed, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" const char *f8_last_error(void) { return f8host::g_err; }
+extern "C" int f8_abi_version(void) { return F8_ABI_VERSION; }
+
+extern "C" int f8_has_umma(int device) {
+#ifdef F8_WITH_UMMA
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return major == 10;
+#else
+    (void)device;
+    return 0;
+#endif
+}
+
+#ifndef F8_WITH_UMMA
+namespace f8host {
+int launch_conv_umma(const f8_conv_args &, cudaStream_t) { return F8_ERR_UNSUPPORTED; }
+}  // namespace f8host
+#endif

@@ -1,0 +1,229 @@
+"""Reference-facing host API: a drop-in for ``IntModel.forward`` on the int_op_only path.
+
+    engine = f8net_b200.compile(int_model)                    # a reference IntModel, or
+    engine = f8net_b200.compile(state_dict, arch="resnet18")  # its state_dict (+ arch name)
+    logits = engine(x)      # x: int32 [N,3,224,224] NCHW, values in the head's 8-bit range
+
+mirrors ``output = model(input)`` (/root/reference/fix_train.py:693) for the IntModel built
+at /root/reference/fix_train.py:930-935: same input tensor, same float32 ``[N, 1000]`` output
+holding the exact int32 logits (/root/reference/models/fix_resnet.py:383).  All arithmetic
+runs in libf8b200.so on the GPU; torch is used for device memory and streams only.
+"""
+import ctypes
+from typing import Optional
+
+import numpy as np
+
+from . import _capi as C
+from .arch import ARCHS, NetSpec, graph_for, graph_from_module
+from .planner import Plan, build_plan
+
+
+def _to_numpy_sd(sd):
+    out = {}
+    for k, v in sd.items():
+        if hasattr(v, "detach"):
+            v = v.detach().cpu().numpy()
+        out[k] = np.asarray(v)
+    return out
+
+
+def infer_arch(sd):
+    """Architecture name from the state_dict key set."""
+    keys = set(sd.keys())
+    if "tail.0.weight" in keys:
+        return "mobilenet_v2"
+    if not any(".shortcut." in k for k in keys) and "stage_4_layer_0.body.0.weight" in keys:
+        return "mobilenet_v1"
+    n_blocks = len({k.split(".")[0] for k in keys if k.startswith("stage_")})
+    bottleneck = any(k.endswith(".body.4.weight") for k in keys)
+    table = {(8, False): 18, (16, False): 34, (16, True): 50, (33, True): 101, (50, True): 152}
+    depth = table.get((n_blocks, bottleneck))
+    if depth is None:
+        raise ValueError("cannot infer the architecture from the state_dict; pass arch=")
+    return f"resnet{depth}"
+
+
+class Engine:
+    """One compiled plan on one GPU.  Stateless at inference like the reference's IntModel:
+    the only mutable state is scratch memory, so use one Engine per stream."""
+
+    def __init__(self, net: NetSpec, state_dict, device=None, chunk: int = 32, backend=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("f8net_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self._torch = torch
+        self.lib = C.lib()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None
+                                   else torch.device(device).index or 0)
+        self.net = net
+        self.plan: Plan = build_plan(net, _to_numpy_sd(state_dict))
+        self.chunk = int(chunk)
+        desc, keep = self.plan.to_desc()
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            C.check(self.lib.f8_plan_create(ctypes.byref(desc), self.device.index,
+                                            ctypes.byref(handle)))
+        del keep
+        self._h = handle
+        if backend is None:
+            backend = 1 if self.lib.f8_has_umma(self.device.index) else 0
+        self.set_backend(backend)
+        self._ws = None
+        self._stage = None
+        self._logits = None
+        self.head_fraclen = int(np.asarray(state_dict["head.0.input_fraclen"]).reshape(-1)[0]) \
+            if "head.0.input_fraclen" in state_dict else None
+
+    # ------------------------------------------------------------------------------------
+    def set_backend(self, backend: int):
+        """0 = mma.sync IMMA kernels, 1 = tcgen05 (UMMA + TMA) where the shape allows."""
+        C.check(self.lib.f8_plan_set_backend(self._h, int(backend)))
+        self.backend = int(backend)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.f8_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def workspace_per_image(self):
+        return self.plan.workspace_per_image
+
+    def launches(self, n, layout=C.F8_IN_NCHW_I32, chunk=None):
+        return int(self.lib.f8_plan_launch_count(self._h, layout, int(n), int(chunk or self.chunk)))
+
+    def _workspace(self, chunk):
+        need = self.plan.workspace_per_image * chunk
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = self._torch.empty(need, dtype=self._torch.uint8, device=self.device)
+        return self._ws
+
+    # ------------------------------------------------------------------------------------
+    def run_device(self, x, out=None, chunk=None, stream=None):
+        """x: CUDA tensor, either int32 [N,3,H,W] (the reference's tensor) or 8-bit
+        [N,H,W,4] (engine-native NHWC, channel 3 zero).  Enqueues on the current stream
+        (or ``stream``) and returns the float32 [N, classes] logits tensor, no sync."""
+        torch = self._torch
+        if x.device != self.device:
+            raise ValueError(f"input is on {x.device}, the engine on {self.device}")
+        S = self.net.image_size
+        if x.dtype == torch.int32 and tuple(x.shape[1:]) == (3, S, S):
+            layout = C.F8_IN_NCHW_I32
+        elif x.dtype in (torch.uint8, torch.int8) and tuple(x.shape[1:]) == (S, S, 4):
+            layout = C.F8_IN_NHWC4_8
+            want = torch.int8 if self.net.head.sym else torch.uint8
+            if x.dtype != want:
+                raise TypeError(f"head conv is {'signed' if self.net.head.sym else 'unsigned'}: "
+                                f"expected {want}, got {x.dtype}")
+        else:
+            raise TypeError(f"expected int32 [N,3,{S},{S}] or 8-bit [N,{S},{S},4]; got "
+                            f"{x.dtype} {tuple(x.shape)}")
+        if not x.is_contiguous():
+            x = x.contiguous()
+        n = x.shape[0]
+        if out is None:
+            out = torch.empty((n, self.net.num_classes), dtype=torch.float32, device=self.device)
+        elif out.dtype != torch.float32 or not out.is_contiguous() or out.numel() < n * self.net.num_classes:
+            raise ValueError("out must be a contiguous float32 tensor of at least [N, classes]")
+        if n == 0:
+            return out
+        chunk = min(int(chunk or self.chunk), n)
+        ws = self._workspace(chunk)
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        C.check(self.lib.f8_plan_run(self._h, x.data_ptr(), layout, n, out.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), chunk, st.cuda_stream))
+        return out
+
+    def run_host(self, x, chunk=None, out=None, sync=True, stream=None):
+        """x: CPU tensor (int32 NCHW or 8-bit NHWC4; pinned for full PCIe speed).  Copies in,
+        runs, copies the logits back through f8_plan_run_host and returns a CPU tensor.
+        ``sync=False`` (x and out pinned) leaves the stream running so a second Engine on
+        another stream can overlap its copies with this one's compute."""
+        torch = self._torch
+        S = self.net.image_size
+        if x.dtype == torch.int32:
+            layout = C.F8_IN_NCHW_I32
+        elif x.dtype in (torch.uint8, torch.int8):
+            layout = C.F8_IN_NHWC4_8
+        else:
+            raise TypeError(f"expected an int32 or 8-bit tensor, got {x.dtype}")
+        x = x.contiguous()
+        n = x.shape[0]
+        if out is None:
+            out = torch.empty((n, self.net.num_classes), dtype=torch.float32)
+        if n == 0:
+            return out
+        nbytes = x.numel() * x.element_size()
+        if self._stage is None or self._stage.numel() < nbytes:
+            self._stage = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        if self._logits is None or self._logits.numel() < n * self.net.num_classes:
+            self._logits = torch.empty(n * self.net.num_classes, dtype=torch.float32,
+                                       device=self.device)
+        chunk = min(int(chunk or self.chunk), n)
+        ws = self._workspace(chunk)
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        C.check(self.lib.f8_plan_run_host(self._h, x.data_ptr(), layout, n, out.data_ptr(),
+                                          self._stage.data_ptr(), self._logits.data_ptr(),
+                                          ws.data_ptr(), ws.numel(), chunk, int(bool(sync)),
+                                          st.cuda_stream))
+        return out
+
+    def profile(self, x, chunk=None):
+        """Per-launch device times (ms) of one run_device(x): list of (op name, kind, ms)."""
+        torch = self._torch
+        layout = C.F8_IN_NCHW_I32 if x.dtype == torch.int32 else C.F8_IN_NHWC4_8
+        n = x.shape[0]
+        chunk = min(int(chunk or self.chunk), n)
+        ws = self._workspace(chunk)
+        out = torch.empty((n, self.net.num_classes), dtype=torch.float32, device=self.device)
+        nops = len(self.plan.ops)
+        ms = (ctypes.c_float * nops)()
+        st = torch.cuda.current_stream(self.device)
+        C.check(self.lib.f8_plan_profile(self._h, x.data_ptr(), layout, n, out.data_ptr(),
+                                         ws.data_ptr(), ws.numel(), chunk, st.cuda_stream,
+                                         ms, nops))
+        return [(op.name, op.kind, float(ms[i])) for i, op in enumerate(self.plan.ops)]
+
+    def __call__(self, x, strict=False):
+        """``IntModel.forward(x)``: int32 NCHW in, float32 logits out, on x's device.
+        ``strict`` checks that x lies in the head's 8-bit range (the reference assumes it,
+        fix_train.py:682-692; the engine keeps the low byte)."""
+        torch = self._torch
+        if strict and x.dtype == torch.int32:
+            lo, hi = (-127, 127) if self.net.head.sym else (0, 255)
+            mn, mx = int(x.min()), int(x.max())
+            if mn < lo or mx > hi:
+                raise ValueError(f"input range [{mn},{mx}] outside the head's [{lo},{hi}]")
+        if x.is_cuda:
+            return self.run_device(x)
+        return self.run_host(x)
+
+    forward = __call__
+
+
+def compile(model_or_state_dict, arch: Optional[str] = None, head_signed: Optional[bool] = None,
+            device=None, chunk: int = 32, backend=None) -> Engine:
+    """Build an Engine from a reference ``IntModel`` (module tree walked for stride / groups /
+    input_symmetric), or from its ``state_dict()`` plus the architecture name -- the
+    attributes the dict lacks are then re-derived from the architecture;
+    ``head_signed`` mirrors FLAGS.normalize (fix_resnet.py:437-438) and defaults to False."""
+    if hasattr(model_or_state_dict, "state_dict") and hasattr(model_or_state_dict, "head"):
+        net = graph_from_module(model_or_state_dict)
+        sd = model_or_state_dict.state_dict()
+    else:
+        sd = model_or_state_dict
+        if callable(sd):            # the reference saves the bound method (fix_train.py:946)
+            sd = sd()
+        if arch is None:
+            arch = infer_arch(sd)
+        if arch not in ARCHS and not arch.startswith("resnet"):
+            raise ValueError(f"unknown arch {arch!r}")
+        net = graph_for(arch, bool(head_signed))
+    return Engine(net, sd, device=device, chunk=chunk, backend=backend)

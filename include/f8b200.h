@@ -16,7 +16,7 @@
  *     synchronisation.  A plan is immutable after creation, so f8_plan_run is re-entrant
  *     across streams as long as each caller brings its own workspace.
  *   - activations between layers are NHWC, 8 bit (u8 or s8 as the consumer's
- *     input_symmetric says), channels padded to a multiple of 32 with zeros; residual
+ *     input_symmetric says), channels padded to a multiple of 16 with zeros; residual
  *     carries are NHWC int32 with the same channel padding.
  */
 #ifndef F8B200_H_
@@ -30,6 +30,12 @@ extern "C" {
 #endif
 
 #define F8_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define F8_API __attribute__((visibility("default")))
+#else
+#define F8_API
+#endif
 
 typedef enum f8_status {
     F8_OK = 0,
@@ -121,31 +127,40 @@ typedef struct f8_plan f8_plan;
 
 /* Replaces: Model.int_model() + .cpu() hand-over (fix_train.py:930-935) -- the engine takes
  * the int32 tensors of IntModel.state_dict() as they are and repacks them to int8 tiles. */
-int f8_plan_create(const f8_model_desc *desc, int device, f8_plan **out);
-void f8_plan_destroy(f8_plan *plan);
+F8_API int f8_plan_create(const f8_model_desc *desc, int device, f8_plan **out);
+F8_API void f8_plan_destroy(f8_plan *plan);
 
 /* Bytes of caller-owned device workspace needed to run up to max_batch images at once. */
-int f8_plan_workspace_bytes(const f8_plan *plan, int max_batch, size_t *bytes);
+F8_API int f8_plan_workspace_bytes(const f8_plan *plan, int max_batch, size_t *bytes);
 
 /* Replaces: output = model(input) (fix_train.py:693) i.e. IntModel.forward, int_op_only
  * branch.  x_dev: device input in x_layout; logits_dev: float32 [n, num_classes] holding the
  * exact int32 logits (fix_resnet.py:383).  chunk: images per pass through the layer list
  * (<= the batch the workspace was sized for; 0 = n). */
-int f8_plan_run(f8_plan *plan, const void *x_dev, int x_layout, int n, float *logits_dev,
+F8_API int f8_plan_run(f8_plan *plan, const void *x_dev, int x_layout, int n, float *logits_dev,
                 void *workspace_dev, size_t workspace_bytes, int chunk, void *stream);
 
 /* Same, with HOST buffers (pinned or pageable): copies x host->device, runs, copies the
- * logits back, all on `stream`, then synchronises the stream.  x_stage_dev must hold the
- * input (n * 3*H*W*4 bytes for NCHW_I32, n * H*W*4 for NHWC4_8).  This is the entry the
- * reference-facing call surface uses for CPU tensors. */
-int f8_plan_run_host(f8_plan *plan, const void *x_host, int x_layout, int n, float *logits_host,
+ * logits back, all on `stream`, then (sync != 0) synchronises the stream.  x_stage_dev must hold the
+ * input (n * 3*H*W*4 bytes for NCHW_I32, n * H*W*4 for NHWC4_8).  sync = 0 leaves the stream
+ * unsynchronised (x_host / logits_host must then be pinned and stay alive) so that a caller
+ * can overlap the copies of one batch with the compute of another on a second stream.  This
+ * is the entry the reference-facing call surface uses for CPU tensors. */
+F8_API int f8_plan_run_host(f8_plan *plan, const void *x_host, int x_layout, int n, float *logits_host,
                      void *x_stage_dev, float *logits_dev, void *workspace_dev,
-                     size_t workspace_bytes, int chunk, void *stream);
+                     size_t workspace_bytes, int chunk, int sync, void *stream);
 
-/* Number of kernel launches one f8_plan_run(n, chunk) enqueues. */
-int f8_plan_launch_count(const f8_plan *plan, int n, int chunk);
+/* Measurement aid (the reference's only timing device is a wall-clock decorator,
+ * fix_train.py:41-53): one f8_plan_run with a CUDA event pair around every launch on
+ * `stream`; synchronises, then op_ms[i] = device time of op i summed over the passes. */
+F8_API int f8_plan_profile(f8_plan *plan, const void *x_dev, int x_layout, int n, float *logits_dev,
+                    void *workspace_dev, size_t workspace_bytes, int chunk, void *stream,
+                    float *op_ms, int n_ops);
+
+/* Number of kernel launches one f8_plan_run(x_layout, n, chunk) enqueues. */
+F8_API int f8_plan_launch_count(const f8_plan *plan, int x_layout, int n, int chunk);
 /* Which dense-conv backend the plan uses: 0 = mma.sync (legacy IMMA), 1 = tcgen05 (UMMA+TMA) */
-int f8_plan_set_backend(f8_plan *plan, int backend);
+F8_API int f8_plan_set_backend(f8_plan *plan, int backend);
 
 /* ------------------------------------------------------------------------------------
  * Per-kernel entry points (layer-level parity tests; same kernels the plan launches).
@@ -173,35 +188,35 @@ typedef struct f8_conv_args {
 
 /* Bytes of the packed weight image for a layer and the packing itself (host -> host).
  * kind: F8_OP_CONV_DENSE or F8_OP_CONV_DW.  weight: reference layout int32. */
-size_t f8_pack_weights_bytes(int kind, int cin, int cout, int cin_pad, int cout_pad, int kh,
+F8_API size_t f8_pack_weights_bytes(int kind, int cin, int cout, int cin_pad, int cout_pad, int kh,
                              int kw);
-int f8_pack_weights(int kind, const int32_t *weight, int cin, int cout, int cin_pad,
+F8_API int f8_pack_weights(int kind, const int32_t *weight, int cin, int cout, int cin_pad,
                     int cout_pad, int kh, int kw, void *dst_host);
 
 /* Replaces: int nn.Conv2d.__call__ (groups == 1) / nn.Linear.__call__ + the consumer-side
  * int_op_only_fix_quant, ReLU and residual add around it (fix_resnet.py:28-77). */
-int f8_conv_dense(const f8_conv_args *a, int backend, void *stream);
+F8_API int f8_conv_dense(const f8_conv_args *a, int backend, void *stream);
 /* Replaces: int nn.Conv2d.__call__ with groups == in_channels (fix_mobilenet_v1.py:33,
  * fix_mobilenet_v2.py:28) + consumer-side requant / ReLU. */
-int f8_conv_dw3x3(const f8_conv_args *a, void *stream);
+F8_API int f8_conv_dw3x3(const f8_conv_args *a, void *stream);
 /* Replaces: self.head[-1](x.float()).int()  (fix_resnet.py:358-359). in = int32 NHWC. */
-int f8_maxpool3x3s2(const f8_conv_args *a, void *stream);
+F8_API int f8_maxpool3x3s2(const f8_conv_args *a, void *stream);
 /* Replaces: FXQAvgPool2d.forward int branch + int_op_only_fix_quant for the classifier
  * (fix_quant_ops.py:126-134, fix_resnet.py:367-374). in = int32 NHWC [n,h,w,c_pad],
  * out[0] = 8-bit [n,c_pad]. */
-int f8_pool_requant(const f8_conv_args *a, void *stream);
+F8_API int f8_pool_requant(const f8_conv_args *a, void *stream);
 /* Replaces: the int32 NCHW tensor hand-over at model(x): repack to NHWC4 8 bit.
  * x int32 [n,3,h,w] -> out 8-bit [n,h,w,4]. */
-int f8_convert_input(const int32_t *x, void *out, int n, int h, int w, void *stream);
+F8_API int f8_convert_input(const int32_t *x, void *out, int n, int h, int w, void *stream);
 /* Replaces: int_op_only_fix_quant as a standalone op (fix_quant_ops.py:90-114):
  * y[i] = requant(x[i], input_fl - fl, is_signed), int32 in / int32 out. */
-int f8_requant_i32(const int32_t *x, int32_t *y, size_t count, int fl, int input_fl,
+F8_API int f8_requant_i32(const int32_t *x, int32_t *y, size_t count, int fl, int input_fl,
                    int is_signed, void *stream);
 
-const char *f8_last_error(void);
-int f8_abi_version(void);
+F8_API const char *f8_last_error(void);
+F8_API int f8_abi_version(void);
 /* 1 when the library was built with the tcgen05 path and the device is sm_100 */
-int f8_has_umma(int device);
+F8_API int f8_has_umma(int device);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,140 @@
+"""The C-ABI boundary without a GPU: the library loads, exports every symbol the header
+declares, the ctypes mirrors of the structs have the C compiler's layout, and the host-only
+weight packer produces the documented images.  No compute call is made here."""
+import ctypes
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from f8net_b200 import _capi as C
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "f8b200.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"F8_API\s+[\w\s\*]+?\b(f8_\w+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported_and_bound(f8lib):
+    names = _declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(f8lib, n), f"{n} declared in include/f8b200.h but not exported"
+        assert n in C.SYMBOLS, f"{n} has no ctypes prototype in f8net_b200/_capi.py"
+    assert sorted(C.SYMBOLS) == names
+    assert f8lib.f8_abi_version() == C.F8_ABI_VERSION
+
+
+def test_struct_layouts_match_the_c_compiler():
+    prog = r"""
+#include <stdio.h>
+#include <stddef.h>
+#include "f8b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu ", sizeof(f8_op), sizeof(f8_buffer), sizeof(f8_model_desc), sizeof(f8_conv_args));
+  printf("%zu %zu %zu %zu ", offsetof(f8_op, weight), offsetof(f8_op, carry_in_buf), offsetof(f8_op, out_buf), offsetof(f8_op, out_f32));
+  printf("%zu %zu %zu %zu %zu\n", offsetof(f8_conv_args, in), offsetof(f8_conv_args, carry_shift), offsetof(f8_conv_args, carry_out), offsetof(f8_conv_args, out_f32), offsetof(f8_model_desc, workspace_per_image));
+  return 0; }
+"""
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "t.c")
+        open(c, "w").write(prog)
+        exe = os.path.join(td, "t")
+        subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        got = [int(v) for v in subprocess.check_output([exe]).split()]
+    want = [ctypes.sizeof(C.f8_op), ctypes.sizeof(C.f8_buffer), ctypes.sizeof(C.f8_model_desc),
+            ctypes.sizeof(C.f8_conv_args),
+            C.f8_op.weight.offset, C.f8_op.carry_in_buf.offset, C.f8_op.out_buf.offset,
+            C.f8_op.out_f32.offset,
+            C.f8_conv_args.in_.offset, C.f8_conv_args.carry_shift.offset,
+            C.f8_conv_args.carry_out.offset, C.f8_conv_args.out_f32.offset,
+            C.f8_model_desc.workspace_per_image.offset]
+    assert got == want
+
+
+def _pack(f8lib, kind, w, cin_pad, cout_pad):
+    cout, cin_g, kh, kw = w.shape
+    cin = cout if kind == C.F8_OP_CONV_DW else cin_g
+    n = f8lib.f8_pack_weights_bytes(kind, cin, cout, cin_pad, cout_pad, kh, kw)
+    dst = np.full(n, 0x5A, dtype=np.uint8)
+    w = np.ascontiguousarray(w, dtype=np.int32)
+    rc = f8lib.f8_pack_weights(kind, w.ctypes.data, cin, cout, cin_pad, cout_pad, kh, kw,
+                               dst.ctypes.data)
+    return rc, dst
+
+
+def test_pack_dense_generic_layout(f8lib):
+    rng = np.random.default_rng(1)
+    w = rng.integers(-127, 128, (24, 20, 3, 3)).astype(np.int32)
+    rc, img = _pack(f8lib, C.F8_OP_CONV_DENSE, w, 32, 32)
+    assert rc == 0
+    K = 3 * 3 * 32
+    kp = (K + 63) // 64 * 64
+    img = img.view(np.int8).reshape(128, kp)
+    want = np.zeros((128, kp), np.int8)
+    # k = (r*kw + s)*cin_pad + c
+    want[:24, :K].reshape(24, 3, 3, 32)[..., :20] = np.transpose(w, (0, 2, 3, 1))
+    assert np.array_equal(img, want)
+
+
+def test_pack_dense_small_c_row_window(f8lib):
+    rng = np.random.default_rng(2)
+    for k in (7, 3):
+        w = rng.integers(-127, 128, (32, 3, k, k)).astype(np.int32)
+        rc, img = _pack(f8lib, C.F8_OP_CONV_DENSE, w, 4, 32)
+        assert rc == 0
+        px = (k + 1 + 1) // 2 * 2            # window pixels: one extra on the left, even count
+        K = k * px * 4
+        kp = (K + 63) // 64 * 64
+        img = img.view(np.int8).reshape(128, kp)
+        want = np.zeros((128, kp), np.int8)
+        v = want[:32, :K].reshape(32, k, px, 4)
+        v[:, :, 1:1 + k, :3] = np.transpose(w, (0, 2, 3, 1))
+        assert np.array_equal(img, want)
+
+
+def test_pack_depthwise_dp4a_operands(f8lib):
+    rng = np.random.default_rng(3)
+    w = rng.integers(-127, 128, (24, 1, 3, 3)).astype(np.int32)
+    rc, img = _pack(f8lib, C.F8_OP_CONV_DW, w, 32, 32)
+    assert rc == 0
+    img = img.view(np.uint32).reshape(12, 8)
+    for ch in range(24):
+        taps = w[ch, 0].reshape(9)
+        for k in range(3):
+            word = int(img[(ch % 4) * 3 + k, ch // 4])
+            for byte in range(4):
+                t = 4 * k + byte
+                want = int(taps[t]) & 0xFF if t < 9 else 0
+                assert (word >> (8 * byte)) & 0xFF == want
+    assert not img[:, 6:].any()              # padded channels stay zero
+
+
+def test_pack_rejects_weights_outside_8_bits(f8lib):
+    w = np.zeros((16, 16, 1, 1), np.int32)
+    w[3, 2, 0, 0] = 200
+    rc, _ = _pack(f8lib, C.F8_OP_CONV_DENSE, w, 16, 16)
+    assert rc == C.F8_ERR_UNSUPPORTED
+    assert b"8-bit" in f8lib.f8_last_error()
+
+
+def test_plan_create_rejects_bad_descriptors(f8lib):
+    h = ctypes.c_void_p()
+    assert f8lib.f8_plan_create(None, 0, ctypes.byref(h)) == C.F8_ERR_ARG
+    d = C.f8_model_desc()
+    d.abi_version = 99
+    assert f8lib.f8_plan_create(ctypes.byref(d), 0, ctypes.byref(h)) == C.F8_ERR_ARG
+    assert b"ABI" in f8lib.f8_last_error()
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(C, "_lib", None)
+    monkeypatch.setattr(C, "LIB_PATH", "/nonexistent/libf8b200.so")
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        C.lib()

@@ -1,0 +1,134 @@
+"""Whole-network parity on the GPU through the reference-facing call surface
+(f8net_b200.compile(...)(x) == IntModel.forward(x)):
+
+ * against the committed golden logits produced by the UNMODIFIED reference
+   (tests/golden/*.npz, N=2, calibrated + adversarial fixtures);
+ * against the CPU oracle on fresh seeded inputs (ragged batches / chunks);
+ * at BASELINE.json's full batch (256 per GPU) through size-independent properties:
+   chunking invariance, batch-permutation equivariance, determinism, and agreement of the
+   engine-native NHWC u8 input with the reference's int32 NCHW input.
+
+Integer path => bit-exact equality everywhere (logits are float32 holding exact int32s)."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+import f8net_b200  # noqa: E402
+from f8net_b200 import synth  # noqa: E402
+from oracle import nets  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ARCHS = list(synth.HEAD_SIGNED)
+
+
+def _engine(arch, sd, **kw):
+    return f8net_b200.compile(sd, arch=arch, head_signed=synth.HEAD_SIGNED[arch], **kw)
+
+
+def _nhwc4(x, signed):
+    n, _, h, w = x.shape
+    out = np.zeros((n, h, w, 4), dtype=np.int8 if signed else np.uint8)
+    out[..., :3] = x.transpose(0, 2, 3, 1)
+    return out
+
+
+@pytest.mark.parametrize("family", ["calibrated", "edge"])
+@pytest.mark.parametrize("arch", ARCHS)
+def test_golden_logits_from_the_reference(cuda, f8lib, arch, family):
+    hs = synth.HEAD_SIGNED[arch]
+    if family == "calibrated":
+        sd, x = synth.make_state_dict(arch, hs), synth.make_input(arch, 2, hs)
+        gold = np.load(os.path.join(GOLD, f"{arch}_n2.npz"))
+    else:
+        sd, x = synth.make_edge_state_dict(arch, hs), synth.make_input(arch, 2, hs, seed=777)
+        gold = np.load(os.path.join(GOLD, f"edge_{arch}_n2.npz"))
+    eng = _engine(arch, sd)
+    # the reference's own call: CPU int32 NCHW tensor in, float32 logits out
+    xt = torch.from_numpy(x)
+    xt.output_fraclen = 8
+    y = eng(xt)
+    assert y.dtype == torch.float32 and tuple(y.shape) == (2, 1000) and not y.is_cuda
+    assert np.array_equal(y.numpy().astype(np.int64), gold["logits"].astype(np.int64))
+    # same through device tensors, and through the engine-native NHWC 8-bit input
+    y2 = eng(xt.cuda())
+    assert torch.equal(y2.cpu(), y)
+    y3 = eng.run_device(torch.from_numpy(_nhwc4(x, hs)).cuda())
+    assert torch.equal(y3.cpu(), y)
+
+
+@pytest.mark.parametrize("arch", ARCHS)
+def test_oracle_parity_ragged_batch_and_chunks(cuda, f8lib, arch):
+    hs = synth.HEAD_SIGNED[arch]
+    sd = synth.make_state_dict(arch, hs)
+    x = synth.make_input(arch, 7, hs, seed=4242)
+    want = nets.forward(arch, sd, x, hs)
+    xt = torch.from_numpy(x).cuda()
+    for chunk in (7, 3, 1):
+        eng = _engine(arch, sd, chunk=chunk)
+        y = eng(xt).cpu().numpy()
+        assert np.array_equal(y, want), (arch, chunk)
+        assert eng.launches(7) == len(eng.plan.ops) * -(-7 // chunk)
+
+
+@pytest.mark.parametrize("arch", ARCHS)
+def test_full_batch_properties(cuda, f8lib, arch):
+    """BASELINE.json batch (256 images on one GPU): properties that do not need the oracle
+    at full size, plus an oracle spot check of 4 images scattered through the batch."""
+    hs = synth.HEAD_SIGNED[arch]
+    n = 256
+    sd = synth.make_state_dict(arch, hs)
+    x = synth.make_input(arch, n, hs)
+    xt = torch.from_numpy(x).cuda()
+    eng = _engine(arch, sd, chunk=32)
+    y = eng(xt)
+    torch.cuda.synchronize()
+    # determinism
+    assert torch.equal(eng(xt), y)
+    # chunking invariance (ragged last chunk)
+    assert torch.equal(_engine(arch, sd, chunk=n)(xt), y)
+    assert torch.equal(_engine(arch, sd, chunk=48)(xt), y)
+    # images are independent: permuting the batch permutes the logits
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(1)).cuda()
+    assert torch.equal(eng(xt[perm].contiguous()), y[perm])
+    # engine-native layout agrees with the reference layout
+    assert torch.equal(eng.run_device(torch.from_numpy(_nhwc4(x, hs)).cuda()), y)
+    # logits are exact integers and not degenerate
+    yc = y.cpu().numpy()
+    assert np.array_equal(yc, np.rint(yc)) and np.unique(yc.argmax(1)).size > 1
+    idx = [0, 97, 200, 255]
+    want = nets.forward(arch, sd, x[idx], hs)
+    assert np.array_equal(yc[idx], want)
+
+
+def test_compile_from_module_like_object_and_bound_method(cuda, f8lib):
+    """compile() accepts the state_dict, or the bound method the reference pickles
+    (fix_train.py:946 saves {'model': model_wrapper.state_dict} without calling it)."""
+    sd = synth.make_state_dict("mobilenet_v1")
+    tsd = synth.to_torch_state_dict(sd)
+
+    class Holder:
+        def state_dict(self):
+            return tsd
+
+    x = torch.from_numpy(synth.make_input("mobilenet_v1", 2))
+    a = f8net_b200.compile(tsd)(x)                       # arch inferred from the keys
+    b = f8net_b200.compile(Holder().state_dict)(x)       # bound method
+    assert torch.equal(a, b)
+    want = nets.forward("mobilenet_v1", sd, x.numpy())
+    assert np.array_equal(a.numpy(), want)
+
+
+def test_input_validation(cuda, f8lib):
+    eng = _engine("mobilenet_v1", synth.make_state_dict("mobilenet_v1"))
+    with pytest.raises(TypeError):
+        eng(torch.zeros((1, 3, 224, 224), dtype=torch.float32).cuda())
+    with pytest.raises(TypeError):
+        eng.run_device(torch.zeros((1, 224, 224, 4), dtype=torch.int8).cuda())   # head is unsigned
+    bad = torch.full((1, 3, 224, 224), 300, dtype=torch.int32)
+    with pytest.raises(ValueError, match="outside"):
+        eng(bad, strict=True)
