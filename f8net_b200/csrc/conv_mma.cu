@@ -14,7 +14,8 @@
 // GEMM view:  M = n*hout*wout output pixels, N = cout_pad, K = kh*kw*cin_pad.
 // CTA tile 128 x BN x 64, 8 warps (4 along M x 2 along N), 4-stage cp.async pipeline,
 // A gathered on the fly from the NHWC activation (zero-fill for padding), B from the
-// packed K-major weight image.  Integer accumulation is associative mod 2^32, so the
+// packed weight image (16-byte K chunks, chunk-major: [K_pad/16][rows][16], the layout the
+// tcgen05 kernel's bulk copies want; both backends share one image).  Integer accumulation is associative mod 2^32, so the
 // tiling order cannot change the result.
 #include "f8_common.cuh"
 
@@ -66,7 +67,8 @@ __device__ __forceinline__ void mma_i8(int32_t (&c)[4], const uint32_t (&a)[4], 
 
 struct ConvGeom {
     const uint8_t *in;
-    const uint8_t *wpack;  // [rows][K_pad]
+    const uint8_t *wpack;  // [K_pad/16][wrows][16]  (chunk-major, see dense_pack_geometry)
+    int wrows;
     int M;                 // n*hout*wout
     int hin, win, cin_pad;
     int hout, wout;
@@ -137,8 +139,8 @@ conv_mma_kernel(const ConvGeom g, const f8::Epilogue ep) {
     }
     // B rows handled by this thread
     constexpr int B_ROWS = BN / 64;
-    const int b_chunk = tid & 3;
-    const int b_row0 = tid >> 2;
+    const int b_chunk = tid >> 6;
+    const int b_row0 = tid & 63;
 
     auto load_stage = [&](int stage, int kt) {
         const uint32_t sa = smem_base + stage * STAGE;
@@ -169,7 +171,7 @@ conv_mma_kernel(const ConvGeom g, const f8::Epilogue ep) {
 #pragma unroll
         for (int i = 0; i < B_ROWS; ++i) {
             const int row = b_row0 + i * 64;
-            const uint8_t *src = g.wpack + (size_t)(n0 + row) * g.K_pad + kt * BK + b_chunk * 16;
+            const uint8_t *src = g.wpack + ((size_t)(kt * 4 + b_chunk) * g.wrows + n0 + row) * 16;
             cp_async16(sb + tile_off(row, b_chunk), src, true);
         }
         // ---- advance K decomposition by one tile (64 bytes) ----
@@ -342,7 +344,7 @@ DensePack dense_pack_geometry(int cin_pad, int cout_pad, int kh, int kw) {
         p.K = kh * kw * cin_pad;
     }
     p.K_pad = (p.K + 63) / 64 * 64;
-    p.rows = (cout_pad + 127) / 128 * 128;
+    p.rows = (cout_pad + 255) / 256 * 256;
     return p;
 }
 
@@ -373,6 +375,7 @@ int launch_conv_mma(const f8_conv_args &a, cudaStream_t s) {
     g.hout = a.hout; g.wout = a.wout;
     g.kh = a.kh; g.kw = a.kw; g.stride = a.stride; g.pad = a.pad;
     g.K_pad = pk.K_pad;
+    g.wrows = pk.rows;
     g.ktiles = pk.K_pad / BK;
     g.row_bytes = pk.row_bytes;
     g.shift_px = pk.shift_px;

@@ -106,8 +106,9 @@ struct DensePack {
     int row_bytes;   // mode 1: bytes of one filter row window
     int shift_px;    // mode 1: extra pixels on the left of the window
     int K;           // logical K in bytes
-    int K_pad;       // multiple of 128
-    int rows;        // cout_pad rounded up to 128
+    int K_pad;       // multiple of 64
+    int rows;        // cout_pad rounded up to 256
+    // image: int8 [K_pad/16][rows][16] -- byte k of output row o at ((k/16)*rows + o)*16 + k%16
 };
 DensePack dense_pack_geometry(int cin_pad, int cout_pad, int kh, int kw);
 }  // namespace f8host

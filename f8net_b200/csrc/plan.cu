@@ -123,7 +123,7 @@ extern "C" int f8_pack_weights(int kind, const int32_t *weight, int cin, int cou
                     const size_t k = p.mode == 1
                                          ? (size_t)r * p.row_bytes + (size_t)(s + p.shift_px) * 4 + c
                                          : ((size_t)r * kw + s) * cin_pad + c;
-                    dst[(size_t)o * p.K_pad + k] = (int8_t)w;
+                    dst[((k >> 4) * (size_t)p.rows + o) * 16 + (k & 15)] = (int8_t)w;
                 }
     return F8_OK;
 }

@@ -76,8 +76,9 @@ def test_pack_dense_generic_layout(f8lib):
     assert rc == 0
     K = 3 * 3 * 32
     kp = (K + 63) // 64 * 64
-    img = img.view(np.int8).reshape(128, kp)
-    want = np.zeros((128, kp), np.int8)
+    # image is [K_pad/16][256][16]; un-chunk it to [rows][K_pad]
+    img = img.view(np.int8).reshape(kp // 16, 256, 16).transpose(1, 0, 2).reshape(256, kp)
+    want = np.zeros((256, kp), np.int8)
     # k = (r*kw + s)*cin_pad + c
     want[:24, :K].reshape(24, 3, 3, 32)[..., :20] = np.transpose(w, (0, 2, 3, 1))
     assert np.array_equal(img, want)
@@ -92,8 +93,8 @@ def test_pack_dense_small_c_row_window(f8lib):
         px = (k + 1 + 1) // 2 * 2            # window pixels: one extra on the left, even count
         K = k * px * 4
         kp = (K + 63) // 64 * 64
-        img = img.view(np.int8).reshape(128, kp)
-        want = np.zeros((128, kp), np.int8)
+        img = img.view(np.int8).reshape(kp // 16, 256, 16).transpose(1, 0, 2).reshape(256, kp)
+        want = np.zeros((256, kp), np.int8)
         v = want[:32, :K].reshape(32, k, px, 4)
         v[:, :, 1:1 + k, :3] = np.transpose(w, (0, 2, 3, 1))
         assert np.array_equal(img, want)

@@ -69,22 +69,28 @@ DENSE_SHAPES = [
 ]
 
 
+BACKENDS = [pytest.param(0, id="imma"), pytest.param(1, id="tcgen05")]
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("shape", DENSE_SHAPES, ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("signed", [False, True])
-def test_conv_dense_plain(G, f8lib, shape, signed):
+def test_conv_dense_plain(G, f8lib, shape, signed, backend):
     cin, cout, k, st, pd, h = shape
     rng = np.random.default_rng(hash(shape) % 2 ** 31)
     lo, hi, w, b = _rand_layer(rng, cin, cout, k, signed)
     x = rng.integers(lo, hi, (3, cin, h, h)).astype(np.int32)
     outs = ((9, False), (7, True))
-    v, q, _ = G.run_conv(f8lib, x, w, b, st, pd, in_signed=signed, relu=True, outs=outs)
+    v, q, _ = G.run_conv(f8lib, x, w, b, st, pd, in_signed=signed, relu=True, outs=outs,
+                         backend=backend)
     ev, eq = G.expect_conv(x, w, b, st, pd, relu=True, outs=outs)
     assert np.array_equal(v, ev)
     assert np.array_equal(q[0], eq[0]) and np.array_equal(q[1], eq[1])
 
 
+@pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("carry_shift", [-3, 0, 2, 29])
-def test_conv_dense_residual_epilogue(G, f8lib, carry_shift):
+def test_conv_dense_residual_epilogue(G, f8lib, carry_shift, backend):
     """IntBlock shift-align / wrapping add / clamp / ReLU (fix_resnet.py:40-77) including
     accumulators at the int32 limits (huge biases) and left-shift requants."""
     rng = np.random.default_rng(10 + carry_shift)
@@ -96,14 +102,15 @@ def test_conv_dense_residual_epilogue(G, f8lib, carry_shift):
     for relu in (True, False):
         outs = ((11, False), (-2, True))
         v, q, _ = G.run_conv(f8lib, x, w, b, 1, 1, relu=relu, carry=carry,
-                             carry_shift=carry_shift, outs=outs)
+                             carry_shift=carry_shift, outs=outs, backend=backend)
         ev, eq = G.expect_conv(x, w, b, 1, 1, relu=relu, carry=carry, carry_shift=carry_shift,
                                outs=outs)
         assert np.array_equal(v, ev)
         assert np.array_equal(q[0], eq[0]) and np.array_equal(q[1], eq[1])
 
 
-def test_conv_dense_ties_round_half_even(G, f8lib):
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_conv_dense_ties_round_half_even(G, f8lib, backend):
     """Even weights + odd-half biases make every accumulator an exact tie of the shift."""
     rng = np.random.default_rng(5)
     cin, cout, h = 32, 32, 8
@@ -111,13 +118,14 @@ def test_conv_dense_ties_round_half_even(G, f8lib):
     x = (rng.integers(0, 64, (2, cin, h, h)) * 4).astype(np.int32)      # acc multiple of 8
     b = np.full(cout, 4, np.int32)                                        # + 4 -> tie for n=3
     outs = ((3, True), (3, False))
-    v, q, _ = G.run_conv(f8lib, x, w, b, 1, 0, outs=outs)
+    v, q, _ = G.run_conv(f8lib, x, w, b, 1, 0, outs=outs, backend=backend)
     ev, eq = G.expect_conv(x, w, b, 1, 0, outs=outs)
     assert (ev % 8 == 4).all()
     assert np.array_equal(v, ev) and np.array_equal(q[0], eq[0]) and np.array_equal(q[1], eq[1])
 
 
-def test_linear_float_logits(G, f8lib):
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_linear_float_logits(G, f8lib, backend):
     """nn.Linear + .float() (fix_quant_ops.py:1165-1195, fix_resnet.py:383) as a 1x1 conv on
     a 1x1 image; ragged batch, 1000 classes (cout_pad 1008)."""
     rng = np.random.default_rng(6)
@@ -125,7 +133,7 @@ def test_linear_float_logits(G, f8lib):
         w = rng.integers(-127, 128, (1000, k, 1, 1)).astype(np.int32)
         b = rng.integers(-2 ** 20, 2 ** 20, (1000,)).astype(np.int32)
         q8 = rng.integers(0, 256, (n, k, 1, 1)).astype(np.int32)
-        v, _, f = G.run_conv(f8lib, q8, w, b, 1, 0, outs=(), want_f32=True)
+        v, _, f = G.run_conv(f8lib, q8, w, b, 1, 0, outs=(), want_f32=True, backend=backend)
         yi, yf = O.linear(q8.reshape(n, k), w.reshape(1000, k), b)
         assert np.array_equal(v.reshape(n, 1000), yi)
         assert np.array_equal(f.reshape(n, 1000), yf)
@@ -133,7 +141,7 @@ def test_linear_float_logits(G, f8lib):
     w = np.full((1000, 512, 1, 1), 127, np.int32)
     q8 = np.full((2, 512, 1, 1), 255, np.int32)
     b = np.arange(1000, dtype=np.int32) * 3 + 2 ** 24
-    _, _, f = G.run_conv(f8lib, q8, w, b, 1, 0, outs=(), want_f32=True)
+    _, _, f = G.run_conv(f8lib, q8, w, b, 1, 0, outs=(), want_f32=True, backend=backend)
     _, yf = O.linear(q8.reshape(2, 512), w.reshape(1000, 512), b)
     assert np.array_equal(f.reshape(2, 1000), yf)
 
