@@ -1,0 +1,376 @@
+// conv3x3_umma.cu -- dense 3x3 / stride 1 / pad 1 int8 convolution on tcgen05 with the input
+// patch RESIDENT in shared memory: every input byte is fetched once per output tile and the
+// nine filter taps are nine shifted views of the same patch, expressed purely through the
+// start address of the tcgen05 shared-memory descriptor.
+//
+// Replaces, per launch: the 3x3 int nn.Conv2d of BasicBlock / Bottleneck bodies built by
+// int_conv() (/root/reference/models/fix_quant_ops.py:680-714) and the tensor-op chain around
+// it in IntBlock.forward (/root/reference/models/fix_resnet.py:28-77).
+//
+// Padded linear pixel space.  Stack the images of the batch into one tall image with ONE zero
+// row above every image and ONE zero column before every row; with pitch PW = W+1 the zero
+// column also serves as the right halo of the previous row, the zero row as the bottom halo of
+// the previous image:
+//     input  slot   pi(img, y, x) = (img*(H+1) + y + 1)*PW + x + 1
+//     output index  m (img, y, x) = (img*(H+1) + y    )*PW + x
+// so the input needed by output m for tap (r, s) is slot  m + r*PW + s  -- one constant offset
+// per tap for ALL pixels.  A tile is any 512 consecutive output indices (four M=128 MMA
+// segments); its patch is the slot range [m0, m0 + 512 + 2*PW + 2).  Output indices that fall
+// on the zero column / zero row are computed and dropped (W/(W+1) * H/(H+1) of the MMA rows are
+// real pixels: 96 % at 56x56, 77 % at 7x7).
+//
+// Shared-memory operand layout (K-major, SWIZZLE_NONE): [16-byte channel chunk][slot][16 B],
+// i.e. core matrices of 8 consecutive slots x 16 B, SBO = 128 B, LBO = slots*16 B.  A tap shift
+// of d slots is "start address += 16*d".  K order: for each 64-channel group, for each tap:
+// two K=32 MMAs per M segment.  The 64-column weight tile of a (channel group, tap) is
+// fetched once (4 bulk copies of 1 KB) and used by all four M segments.
+//
+// Persistent CTA, 1 per SM, 512 TMEM columns = 2 (double buffer) x 4 segments x 64 columns:
+//   warps 0-3 epilogue | warps 4-7 patch loaders (cp.async, zero fill) | warp 8 lane 0 MMA
+//   | warp 9 lane 0 weight-tile loader (cp.async.bulk).
+#include "umma_common.cuh"
+
+namespace {
+
+using namespace f8u;
+
+constexpr int BN = 64;                 // output channels per tile
+constexpr int MB = 4;                  // M segments of 128 rows per tile
+constexpr int TM = 128 * MB;           // output indices per tile
+constexpr int SA = 2;                  // patch ring (one stage = 64 channels of the patch)
+constexpr int SB = 12;                 // weight-tile ring (one stage = 64 cout x 64 K bytes)
+constexpr int B_TILE = BN * 64;
+constexpr int EPI_THREADS = 128;
+constexpr int LOADERS = 128;
+constexpr int LOADER_WARP0 = 4;
+constexpr int MMA_WARP = 8;
+constexpr int WLOAD_WARP = 9;
+constexpr int THREADS = 320;
+constexpr int MAX_SLOT_ITERS = 6;      // ceil((TM + 2*PW + 2) / 128) for PW <= 120
+
+struct PGeom {
+    const uint8_t *in;
+    const uint8_t *wpack;   // [K_pad/16][wrows][16], k = (r*3+s)*C + c
+    int wrows;
+    int N, H, W, C;         // C = cin_pad (multiple of 64)
+    int PW;                 // W + 1
+    int slots;              // TM + 2*PW + 2
+    int slots_pad;          // slots rounded up to 8
+    int n_super;            // tiles along the padded linear space
+    int ntiles_n;           // cout_pad / 64 (rounded up)
+};
+
+template <bool A_SIGNED>
+__global__ void __launch_bounds__(THREADS, 1)
+conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int a_stage = g.slots_pad * 64;                 // bytes of one patch stage
+    const uint32_t lbo_a = (uint32_t)g.slots_pad * 16;
+    const uint32_t smem_base = f8::smem_u32(smem);
+    const uint32_t sb_base = smem_base + SA * a_stage;
+    const uint32_t bar_base = sb_base + SB * B_TILE;
+    // a_full[SA] a_empty[SA] b_full[SB] b_empty[SB] acc_full[2] acc_empty[2]
+    auto a_full = [&](int s) { return bar_base + (uint32_t)s * 8; };
+    auto a_empty = [&](int s) { return bar_base + (uint32_t)(SA + s) * 8; };
+    auto b_full = [&](int s) { return bar_base + (uint32_t)(2 * SA + s) * 8; };
+    auto b_empty = [&](int s) { return bar_base + (uint32_t)(2 * SA + SB + s) * 8; };
+    auto acc_full = [&](int b) { return bar_base + (uint32_t)(2 * SA + 2 * SB + b) * 8; };
+    auto acc_empty = [&](int b) { return bar_base + (uint32_t)(2 * SA + 2 * SB + 2 + b) * 8; };
+    constexpr int NBARS = 2 * SA + 2 * SB + 4;
+    uint8_t *after = smem + SA * a_stage + SB * B_TILE + NBARS * 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(after);
+    int32_t *sbias = reinterpret_cast<int32_t *>(after + 16);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int total_items = g.n_super * g.ntiles_n;
+    const int ncg = g.C >> 6;
+    const int HP = g.H + 1;
+
+    if (warp == MMA_WARP) {
+        if (lane == 0) {
+            for (int s = 0; s < SA; ++s) { mbar_init(a_full(s), LOADERS); mbar_init(a_empty(s), 1); }
+            for (int s = 0; s < SB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+            for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), EPI_THREADS); }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(f8::smem_u32(tmem_slot), 512);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= LOADER_WARP0 && warp < MMA_WARP) {
+        // =========================== patch loaders ================================
+        const int lt = tid - LOADER_WARP0 * 32;
+        int slot = 0, phase = 0, aslot = 0, issued = 0;
+        for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+            const int st = it / g.ntiles_n;
+            const long long pi0 = (long long)st * TM;
+            // decode this thread's slots once per tile: global byte offset of the pixel or -1
+            long long off[MAX_SLOT_ITERS];
+#pragma unroll
+            for (int k = 0; k < MAX_SLOT_ITERS; ++k) {
+                const int pl = lt + k * LOADERS;
+                off[k] = -1;
+                if (pl < g.slots) {
+                    const long long pi = pi0 + pl;
+                    const int Yp = (int)(pi / g.PW);
+                    const int xs = (int)(pi - (long long)Yp * g.PW);
+                    const int img = Yp / HP;
+                    const int yy = Yp - img * HP;
+                    if (xs >= 1 && yy >= 1 && img < g.N)
+                        off[k] = ((long long)(img * g.H + (yy - 1)) * g.W + (xs - 1)) * g.C;
+                }
+            }
+            for (int cg = 0; cg < ncg; ++cg) {
+                mbar_wait(a_empty(slot), phase ^ 1);
+                const uint32_t sa = smem_base + slot * a_stage;
+#pragma unroll
+                for (int k = 0; k < MAX_SLOT_ITERS; ++k) {
+                    const int pl = lt + k * LOADERS;
+                    if (pl < g.slots) {
+                        const bool ok = off[k] >= 0;
+                        const uint8_t *src = ok ? g.in + off[k] + cg * 64 : g.in;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            cp_async16(sa + j * lbo_a + pl * 16, src + j * 16, ok);
+                    }
+                }
+                cp_async_commit();
+                if (++slot == SA) { slot = 0; phase ^= 1; }
+                if (++issued == SA) {
+                    cp_async_wait<SA - 1>();
+                    fence_proxy_async();
+                    mbar_arrive(a_full(aslot));
+                    if (++aslot == SA) aslot = 0;
+                    --issued;
+                }
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        for (; issued > 0; --issued) {
+            mbar_arrive(a_full(aslot));
+            if (++aslot == SA) aslot = 0;
+        }
+    } else if (warp == WLOAD_WARP) {
+        // =========================== weight-tile loader ===========================
+        if (lane == 0) {
+            int slot = 0, phase = 0;
+            for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+                const int st = it / g.ntiles_n;
+                const int n0 = (it - st * g.ntiles_n) * BN;
+                for (int cg = 0; cg < ncg; ++cg)
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(b_empty(slot), phase ^ 1);
+                        const uint32_t sb = sb_base + slot * B_TILE;
+                        mbar_expect_tx(b_full(slot), B_TILE);
+                        mbar_arrive(b_full(slot));
+                        const size_t kc = (size_t)(tap * g.C + cg * 64) >> 4;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            bulk_g2s(sb + j * (BN * 16), g.wpack + ((kc + j) * g.wrows + n0) * 16,
+                                     BN * 16, b_full(slot));
+                        if (++slot == SB) { slot = 0; phase ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // =========================== MMA issuer ===================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc(A_SIGNED, BN);
+            int aslot = 0, aphase = 0, bslot = 0, bphase = 0, buf = 0, acc_phase = 0;
+            for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+                mbar_wait(acc_empty(buf), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * MB * BN);
+                for (int cg = 0; cg < ncg; ++cg) {
+                    mbar_wait(a_full(aslot), aphase);
+                    const uint32_t sa = smem_base + aslot * a_stage;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(b_full(bslot), bphase);
+                        tc_fence_after();
+                        const uint32_t sb = sb_base + bslot * B_TILE;
+                        const int r = tap / 3, s = tap - r * 3;
+                        const uint32_t shift = (uint32_t)(r * g.PW + s) * 16;
+#pragma unroll
+                        for (int i = 0; i < MB; ++i) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint64_t ad = smem_desc(sa + (2 * h) * lbo_a + shift + i * 2048, lbo_a, 128);
+                                const uint64_t bd = smem_desc(sb + (2 * h) * (BN * 16), BN * 16, 128);
+                                umma_i8(tacc + (uint32_t)(i * BN), ad, bd, idesc,
+                                        (uint32_t)((cg | tap | h) != 0));
+                            }
+                        }
+                        umma_commit(b_empty(bslot));
+                        if (++bslot == SB) { bslot = 0; bphase ^= 1; }
+                    }
+                    umma_commit(a_empty(aslot));
+                    if (++aslot == SA) { aslot = 0; aphase ^= 1; }
+                }
+                umma_commit(acc_full(buf));
+                if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // =========================== epilogue (warps 0-3) =========================
+        const int row = tid;
+        const bool has_carry = ep.carry_in != nullptr;
+        int buf = 0, acc_phase = 0;
+        for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+            const int st = it / g.ntiles_n;
+            const int n0 = (it - st * g.ntiles_n) * BN;
+            int ncols = ep.cout_pad - n0;
+            if (ncols > BN) ncols = BN;
+            int32_t *bias_s = sbias + buf * BN;
+            if (row < ncols) bias_s[row] = __ldg(ep.bias + n0 + row);
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+            mbar_wait(acc_full(buf), acc_phase);
+            tc_fence_after();
+            for (int i = 0; i < MB; ++i) {
+                const long long m = (long long)st * TM + i * 128 + row;
+                const int Yo = (int)(m / g.PW);
+                const int xo = (int)(m - (long long)Yo * g.PW);
+                const int img = Yo / HP;
+                const int y = Yo - img * HP;
+                const bool valid = xo < g.W && y < g.H && img < g.N;
+                const size_t opix = ((size_t)(img * g.H + y) * g.W + xo);
+                const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) +
+                                      (uint32_t)((buf * MB + i) * BN);
+                for (int c0 = 0; c0 < ncols; c0 += 16) {
+                    int32_t v[16];
+                    tmem_ld16(trow + (uint32_t)c0, v);
+                    tmem_ld_wait();
+                    if (i == MB - 1 && c0 + 16 >= ncols) {
+                        tc_fence_before();
+                        mbar_arrive(acc_empty(buf));     // whole accumulator buffer drained
+                    }
+                    if (valid) {
+                        const int gc = n0 + c0;
+                        const size_t o = opix * ep.cout_pad + gc;
+#pragma unroll
+                        for (int q = 0; q < 16; q += 4) {
+                            const int4 b = *reinterpret_cast<const int4 *>(bias_s + c0 + q);
+                            v[q + 0] = (int32_t)((uint32_t)v[q + 0] + (uint32_t)b.x);
+                            v[q + 1] = (int32_t)((uint32_t)v[q + 1] + (uint32_t)b.y);
+                            v[q + 2] = (int32_t)((uint32_t)v[q + 2] + (uint32_t)b.z);
+                            v[q + 3] = (int32_t)((uint32_t)v[q + 3] + (uint32_t)b.w);
+                            int4 c = make_int4(0, 0, 0, 0);
+                            if (has_carry) c = ld_stream_int4(ep.carry_in + o + q);
+                            v[q + 0] = f8::residual_relu(v[q + 0], has_carry, c.x, ep.carry_shift, ep.relu);
+                            v[q + 1] = f8::residual_relu(v[q + 1], has_carry, c.y, ep.carry_shift, ep.relu);
+                            v[q + 2] = f8::residual_relu(v[q + 2], has_carry, c.z, ep.carry_shift, ep.relu);
+                            v[q + 3] = f8::residual_relu(v[q + 3], has_carry, c.w, ep.carry_shift, ep.relu);
+                            if (ep.carry_out)
+                                *reinterpret_cast<int4 *>(ep.carry_out + o + q) =
+                                    make_int4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+                        }
+                        if (ep.out0) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                w[q] = 0;
+#pragma unroll
+                                for (int b = 0; b < 4; ++b)
+                                    w[q] |= ((uint32_t)f8::requant(v[q * 4 + b], ep.shift0, ep.signed0) & 0xffu)
+                                            << (8 * b);
+                            }
+                            *reinterpret_cast<uint4 *>(ep.out0 + o) = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                        if (ep.out1) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                w[q] = 0;
+#pragma unroll
+                                for (int b = 0; b < 4; ++b)
+                                    w[q] |= ((uint32_t)f8::requant(v[q * 4 + b], ep.shift1, ep.signed1) & 0xffu)
+                                            << (8 * b);
+                            }
+                            *reinterpret_cast<uint4 *>(ep.out1 + o) = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    }
+                }
+            }
+            if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace
+
+namespace f8host {
+
+// F8_ERR_UNSUPPORTED => the caller falls back to the gather kernel (conv_umma.cu)
+int launch_conv3x3_umma(const f8_conv_args &a, cudaStream_t s) {
+    if (a.kh != 3 || a.kw != 3 || a.stride != 1 || a.pad != 1 || a.cin_pad % 64 != 0 ||
+        a.cout_pad % 16 != 0 || a.hin != a.hout || a.win != a.wout || a.out_f32 != nullptr)
+        return F8_ERR_UNSUPPORTED;
+    const int PW = a.win + 1;
+    const int slots = TM + 2 * PW + 2;
+    if ((slots + LOADERS - 1) / LOADERS > MAX_SLOT_ITERS) return F8_ERR_UNSUPPORTED;
+    const int slots_pad = (slots + 7) / 8 * 8;
+    const size_t smem_bytes = (size_t)SA * slots_pad * 64 + (size_t)SB * B_TILE +
+                              (2 * SA + 2 * SB + 4) * 8 + 16 + 2 * BN * 4;
+    if (smem_bytes > 220 * 1024) return F8_ERR_UNSUPPORTED;
+    // the kernel owns all 512 TMEM columns: keep a second CTA off the SM
+    const size_t smem_launch = smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes;
+    const long long lin = (long long)a.n * (a.hin + 1) * PW;     // padded linear output space
+    if (lin > 0x7fffffffLL - TM) return F8_ERR_UNSUPPORTED;
+    const DensePack pk = dense_pack_geometry(a.cin_pad, a.cout_pad, 3, 3);
+    PGeom g{};
+    g.in = static_cast<const uint8_t *>(a.in);
+    g.wpack = static_cast<const uint8_t *>(a.wpack);
+    g.wrows = pk.rows;
+    g.N = a.n; g.H = a.hin; g.W = a.win; g.C = a.cin_pad;
+    g.PW = PW;
+    g.slots = slots;
+    g.slots_pad = slots_pad;
+    g.n_super = (int)((lin + TM - 1) / TM);
+    g.ntiles_n = (a.cout_pad + BN - 1) / BN;
+    f8::Epilogue ep{};
+    ep.bias = a.bias;
+    ep.carry_in = a.carry_in;
+    ep.carry_out = a.carry_out;
+    ep.out0 = static_cast<uint8_t *>(a.out[0]);
+    ep.out1 = static_cast<uint8_t *>(a.out[1]);
+    ep.carry_shift = a.carry_shift;
+    ep.relu = a.relu;
+    ep.shift0 = a.out_shift[0]; ep.signed0 = a.out_signed[0];
+    ep.shift1 = a.out_shift[1]; ep.signed1 = a.out_signed[1];
+    ep.cout = a.cout;
+    ep.cout_pad = a.cout_pad;
+    static bool attr_done = false;
+    static int num_sms = 0;
+    if (!attr_done) {
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        int dev = 0;
+        F8_CUDA(cudaGetDevice(&dev));
+        F8_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        attr_done = true;
+    }
+    long long grid = (long long)g.n_super * g.ntiles_n;
+    if (grid > num_sms) grid = num_sms;
+    if (a.in_signed)
+        conv3x3_umma_kernel<true><<<(unsigned)grid, THREADS, smem_launch, s>>>(g, ep);
+    else
+        conv3x3_umma_kernel<false><<<(unsigned)grid, THREADS, smem_launch, s>>>(g, ep);
+    F8_CUDA(cudaGetLastError());
+    return F8_OK;
+}
+
+}  // namespace f8host

@@ -9,30 +9,37 @@
 // bias, residual shift-add-clamp, ReLU, consumer-side int_op_only_fix_quant, .float().
 //
 // GEMM view: M = n*hout*wout output pixels, N = cout_pad, K = kh*kw*cin_pad bytes.
-// CTA tile 128 x BN (BN = 64 | 128 | 256 TMEM columns), K step 64 bytes per pipeline stage
-// (two K=32 MMAs).  Warp roles:
-//   warps 0-3  producers, then epilogue.  Thread t owns output pixel m0+t: it gathers the
+// Tile 128 x BN (BN = 64 | 128 | 256), K step 64 bytes per pipeline stage (two K=32 MMAs).
+// PERSISTENT kernel, one or two CTAs per SM, each looping over its tiles with one operand
+// ring and two TMEM accumulators, so the loads of tile i+1 and the epilogue of tile i-1
+// overlap the MMAs of tile i.  Warp roles:
+//   warps 4-7  producers.  Thread r owns tile row r (one output pixel): it gathers the
 //              pixel's K bytes from the NHWC activation with 16-byte cp.async (zero fill for
 //              the padding halo) into the canonical K-major no-swizzle operand layout
 //              [K/16][128 rows][16 B] (core matrix = 8 rows x 16 B contiguous, SBO = 128 B,
 //              LBO = 2048 B), fences the generic->async proxy and arrives on the stage's
-//              "full" mbarrier.  Thread 0 also posts the stage's weight bytes: 4 bulk copies
-//              of BN*16 contiguous bytes from the chunk-major weight image.
-//   warp 4     lane 0 issues the MMAs (tcgen05.mma is a single-thread instruction) and
-//              commits each stage to its "empty" mbarrier; the last commit signals the
-//              epilogue.  Warp 4 also owns the TMEM allocation.
-// After the K loop each producer thread reads its own accumulator row (TMEM lane = tile row)
-// 16 columns at a time and runs the integer epilogue of f8_common.cuh.
+//              "full" mbarrier.  Its thread 0 also posts the stage's weight bytes: 4 bulk
+//              copies of BN*16 contiguous bytes from the chunk-major weight image.
+//   warp 8     lane 0 issues the MMAs (tcgen05.mma is a single-thread instruction), commits
+//              each stage to its "empty" mbarrier and each finished accumulator to
+//              "acc_full".  Warp 8 also owns the TMEM allocation (2 x BN columns).
+//   warps 0-3  epilogue: thread t reads accumulator row t (TMEM lane = tile row) 16 columns
+//              at a time, releases the accumulator ("acc_empty") as soon as the last column
+//              is in registers, and runs the integer epilogue of f8_common.cuh.
 // Integer accumulation is associative mod 2^32: tiling and MMA order cannot change results.
-#include "f8_common.cuh"
+#include "umma_common.cuh"
 
 namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
+constexpr int EPI_THREADS = 128;      // warps 0-3: epilogue (warp % 4 == TMEM lane group)
+constexpr int PRODUCER_WARP0 = 4;     // warps 4-7: A gather (+ thread 0 of them: B bulk copies)
 constexpr int PRODUCERS = 128;
-constexpr int THREADS = 160;
+constexpr int MMA_WARP = 8;           // warp 8: TMEM alloc, lane 0 issues tcgen05.mma
+constexpr int THREADS = 288;
+// ring depth per tile width: ~96-120 KB of operand bytes in flight per CTA
+__host__ __device__ constexpr int stages_for(int bn) { return bn <= 64 ? 8 : (bn <= 128 ? 6 : 5); }
 constexpr int A_STAGE = BM * BK;          // 8192 B: [4 chunks][128 rows][16 B]
 constexpr int A_CHUNK = BM * 16;          // 2048 B between K chunks (LBO of A)
 
@@ -49,325 +56,275 @@ struct UGeom {
     int shift_px;          // small-C mode
 };
 
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void fence_barrier_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool pred) {
-    const int sz = pred ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src, bool pred) {
-    const int sz = pred ? 8 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(sz)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() {
-    asm volatile("cp.async.commit_group;" ::: "memory");
-}
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem),
-                 "r"(cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
-                 : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-                 : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], int8 operands, int32 accumulate, no saturation
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                        uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-          "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() {
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
+using namespace f8u;
 
-// shared-memory matrix descriptor, K-major, SWIZZLE_NONE (layout_type 0), version 1:
-// start address [0,14), leading byte offset [16,30), stride byte offset [32,46), all >> 4
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo >> 4) << 16) |
-           ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
-}
-// instruction descriptor for kind::i8: c_format S32 (2) at [4,6), a_format at [7,10)
-// (0 = u8, 1 = s8), b_format s8 at [10,13), K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t instr_desc(bool a_signed, int n) {
-    return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) |
-           ((uint32_t)(BM >> 4) << 24);
-}
-
+// Persistent, warp-specialised kernel.  Static tile schedule: CTA b runs tiles b, b+grid, ...
+// with the N tile fastest, so CTAs that are co-resident read the same activation rows.
 template <int BN, bool A_SIGNED, bool SMALL_C>
 __global__ void __launch_bounds__(THREADS)
-conv_umma_kernel(const UGeom g, const f8::Epilogue ep) {
+conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const int ntiles_n) {
     extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int S = stages_for(BN);
     constexpr int B_STAGE = BN * BK;
     constexpr int B_CHUNK = BN * 16;
     constexpr int STAGE = A_STAGE + B_STAGE;
     const uint32_t smem_base = f8::smem_u32(smem);
-    const uint32_t bar_base = smem_base + STAGES * STAGE;       // full[S] empty[S] accum
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + STAGES * STAGE + (2 * STAGES + 1) * 8);
+    // after the ring: full[S] empty[S] acc_full[2] acc_empty[2] | tmem slot | bias[2][BN]
+    const uint32_t bar_base = smem_base + S * STAGE;
     auto full_bar = [&](int s) { return bar_base + (uint32_t)s * 8; };
-    auto empty_bar = [&](int s) { return bar_base + (uint32_t)(STAGES + s) * 8; };
-    const uint32_t accum_bar = bar_base + 2 * STAGES * 8;
+    auto empty_bar = [&](int s) { return bar_base + (uint32_t)(S + s) * 8; };
+    auto acc_full_bar = [&](int b) { return bar_base + (uint32_t)(2 * S + b) * 8; };
+    auto acc_empty_bar = [&](int b) { return bar_base + (uint32_t)(2 * S + 2 + b) * 8; };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S * STAGE + (2 * S + 4) * 8);
+    int32_t *sbias = reinterpret_cast<int32_t *>(smem + S * STAGE + (2 * S + 4) * 8 + 16);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.x * BM;
-    const int n0 = blockIdx.y * BN;
+    const int total_tiles = mtiles * ntiles_n;
 
-    if (warp == 4) {
+    if (warp == MMA_WARP) {
         if (lane == 0) {
-            for (int s = 0; s < STAGES; ++s) {
+            for (int s = 0; s < S; ++s) {
                 mbar_init(full_bar(s), PRODUCERS);
                 mbar_init(empty_bar(s), 1);
             }
-            mbar_init(accum_bar, 1);
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(acc_full_bar(b), 1);
+                mbar_init(acc_empty_bar(b), EPI_THREADS);
+            }
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc(f8::smem_u32(tmem_slot), BN);
+        tmem_alloc(f8::smem_u32(tmem_slot), 2 * BN);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
-        // =========================== producer: A gather + B bulk copies ===========
-        const int row = tid;
-        const int m = m0 + row;
-        const bool valid = m < g.M;
+    if (warp >= PRODUCER_WARP0 && warp < MMA_WARP) {
+        // =========================== producers: A gather + B bulk copies ==========
+        const int row = tid - PRODUCER_WARP0 * 32;
         const int HW = g.hout * g.wout;
-        const int mm = valid ? m : 0;
-        const int img = mm / HW;
-        const int rem = mm - img * HW;
-        const int p = rem / g.wout, q = rem - p * g.wout;
-        const int ih0 = p * g.stride - g.pad;
-        const int iw0 = q * g.stride - g.pad - (SMALL_C ? g.shift_px : 0);
-        const uint8_t *base = g.in + (size_t)img * g.hin * g.win * g.cin_pad;
-        int k_r = 0, k_s = 0, k_c = 0;
-
-        for (int kt = 0; kt < g.ktiles; ++kt) {
-            const int slot = kt % STAGES;
-            if (kt >= STAGES) mbar_wait(empty_bar(slot), ((kt / STAGES) - 1) & 1);
-            const uint32_t sa = smem_base + slot * STAGE;
-            if (tid == 0) {
-                const uint32_t sb = sa + A_STAGE;
-                mbar_expect_tx(full_bar(slot), B_STAGE);
+        int slot = 0, phase = 0;       // ring position of the stage being issued
+        int aslot = 0;                 // ring position of the next stage to signal
+        int issued = 0;                // stages issued and not yet signalled
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int mt = t / ntiles_n;
+            const int n0 = (t - mt * ntiles_n) * BN;
+            const int m = mt * BM + row;
+            const bool valid = m < g.M;
+            const int mm = valid ? m : 0;
+            const int img = mm / HW;
+            const int rem = mm - img * HW;
+            const int p = rem / g.wout, q = rem - p * g.wout;
+            const int ih0 = p * g.stride - g.pad;
+            const int iw0 = q * g.stride - g.pad - (SMALL_C ? g.shift_px : 0);
+            const uint8_t *base = g.in + (size_t)img * g.hin * g.win * g.cin_pad;
+            int k_r = 0, k_s = 0, k_c = 0;
+            for (int kt = 0; kt < g.ktiles; ++kt) {
+                mbar_wait(empty_bar(slot), phase ^ 1);
+                const uint32_t sa = smem_base + slot * STAGE;
+                if (row == 0) {
+                    const uint32_t sb = sa + A_STAGE;
+                    mbar_expect_tx(full_bar(slot), B_STAGE);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    bulk_g2s(sb + j * B_CHUNK,
-                             g.wpack + ((size_t)(kt * 4 + j) * g.wrows + n0) * 16, B_CHUNK,
-                             full_bar(slot));
-            }
-            if constexpr (SMALL_C) {
-#pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) {
-                    const int ih = ih0 + k_r;
-                    const int iw = iw0 + (k_c >> 2);
-                    const bool ok = valid && k_r < g.kh && (unsigned)ih < (unsigned)g.hin &&
-                                    (unsigned)iw < (unsigned)g.win;
-                    const uint8_t *src = ok ? base + ((size_t)ih * g.win + iw) * 4 : g.in;
-                    cp_async8(sa + (c8 >> 1) * A_CHUNK + row * 16 + (c8 & 1) * 8, src, ok);
-                    k_c += 8;
-                    if (k_c >= g.row_bytes) { k_c = 0; ++k_r; }
+                    for (int j = 0; j < 4; ++j)
+                        bulk_g2s(sb + j * B_CHUNK,
+                                 g.wpack + ((size_t)(kt * 4 + j) * g.wrows + n0) * 16, B_CHUNK,
+                                 full_bar(slot));
                 }
-            } else {
+                if constexpr (SMALL_C) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int ih = ih0 + k_r;
-                    const int iw = iw0 + k_s;
-                    const bool ok = valid && k_r < g.kh && (unsigned)ih < (unsigned)g.hin &&
-                                    (unsigned)iw < (unsigned)g.win;
-                    const uint8_t *src =
-                        ok ? base + ((size_t)ih * g.win + iw) * g.cin_pad + k_c : g.in;
-                    cp_async16(sa + j * A_CHUNK + row * 16, src, ok);
-                    k_c += 16;
-                    if (k_c >= g.cin_pad) {
-                        k_c = 0;
-                        if (++k_s == g.kw) { k_s = 0; ++k_r; }
+                    for (int c8 = 0; c8 < 8; ++c8) {
+                        const int ih = ih0 + k_r;
+                        const int iw = iw0 + (k_c >> 2);
+                        const bool ok = valid && k_r < g.kh && (unsigned)ih < (unsigned)g.hin &&
+                                        (unsigned)iw < (unsigned)g.win;
+                        const uint8_t *src = ok ? base + ((size_t)ih * g.win + iw) * 4 : g.in;
+                        cp_async8(sa + (c8 >> 1) * A_CHUNK + row * 16 + (c8 & 1) * 8, src, ok);
+                        k_c += 8;
+                        if (k_c >= g.row_bytes) { k_c = 0; ++k_r; }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int ih = ih0 + k_r;
+                        const int iw = iw0 + k_s;
+                        const bool ok = valid && k_r < g.kh && (unsigned)ih < (unsigned)g.hin &&
+                                        (unsigned)iw < (unsigned)g.win;
+                        const uint8_t *src =
+                            ok ? base + ((size_t)ih * g.win + iw) * g.cin_pad + k_c : g.in;
+                        cp_async16(sa + j * A_CHUNK + row * 16, src, ok);
+                        k_c += 16;
+                        if (k_c >= g.cin_pad) {
+                            k_c = 0;
+                            if (++k_s == g.kw) { k_s = 0; ++k_r; }
+                        }
                     }
                 }
-            }
-            cp_async_commit();
-            if (kt >= STAGES - 1) {
-                cp_async_wait<STAGES - 1>();      // stage kt-(STAGES-1) has landed
-                fence_proxy_async();              // generic-proxy writes -> visible to the MMA
-                mbar_arrive(full_bar((kt - (STAGES - 1)) % STAGES));
+                cp_async_commit();
+                if (++slot == S) { slot = 0; phase ^= 1; }
+                if (++issued == S) {
+                    cp_async_wait<S - 1>();       // the oldest unsignalled stage has landed
+                    fence_proxy_async();          // generic-proxy writes -> visible to the MMA
+                    mbar_arrive(full_bar(aslot));
+                    if (++aslot == S) aslot = 0;
+                    --issued;
+                }
             }
         }
         cp_async_wait<0>();
         fence_proxy_async();
-        {
-            int first = g.ktiles - (STAGES - 1);
-            if (first < 0) first = 0;
-            for (int i = first; i < g.ktiles; ++i) mbar_arrive(full_bar(i % STAGES));
+        for (; issued > 0; --issued) {
+            mbar_arrive(full_bar(aslot));
+            if (++aslot == S) aslot = 0;
         }
-
-        // =========================== epilogue ====================================
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
-        const bool has_carry = ep.carry_in != nullptr;
-        int ncols = ep.cout_pad - n0;
-        if (ncols > BN) ncols = BN;
-        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-        for (int c0 = 0; c0 < ncols; c0 += 16) {
-            int32_t v[16];
-            tmem_ld16(trow + (uint32_t)c0, v);
-            tmem_ld_wait();
-            if (valid) {
-                const int gc = n0 + c0;
-                const size_t o = (size_t)m * ep.cout_pad + gc;
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    const int4 b = __ldg(reinterpret_cast<const int4 *>(ep.bias + gc + i));
-                    v[i + 0] = (int32_t)((uint32_t)v[i + 0] + (uint32_t)b.x);
-                    v[i + 1] = (int32_t)((uint32_t)v[i + 1] + (uint32_t)b.y);
-                    v[i + 2] = (int32_t)((uint32_t)v[i + 2] + (uint32_t)b.z);
-                    v[i + 3] = (int32_t)((uint32_t)v[i + 3] + (uint32_t)b.w);
-                    int4 c = make_int4(0, 0, 0, 0);
-                    if (has_carry) c = *reinterpret_cast<const int4 *>(ep.carry_in + o + i);
-                    v[i + 0] = f8::residual_relu(v[i + 0], has_carry, c.x, ep.carry_shift, ep.relu);
-                    v[i + 1] = f8::residual_relu(v[i + 1], has_carry, c.y, ep.carry_shift, ep.relu);
-                    v[i + 2] = f8::residual_relu(v[i + 2], has_carry, c.z, ep.carry_shift, ep.relu);
-                    v[i + 3] = f8::residual_relu(v[i + 3], has_carry, c.w, ep.carry_shift, ep.relu);
-                    if (ep.carry_out)
-                        *reinterpret_cast<int4 *>(ep.carry_out + o + i) =
-                            make_int4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                }
-                if (ep.out0) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        w[i] = 0;
-#pragma unroll
-                        for (int b = 0; b < 4; ++b)
-                            w[i] |= ((uint32_t)f8::requant(v[i * 4 + b], ep.shift0, ep.signed0) & 0xffu)
-                                    << (8 * b);
-                    }
-                    *reinterpret_cast<uint4 *>(ep.out0 + o) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-                if (ep.out1) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        w[i] = 0;
-#pragma unroll
-                        for (int b = 0; b < 4; ++b)
-                            w[i] |= ((uint32_t)f8::requant(v[i * 4 + b], ep.shift1, ep.signed1) & 0xffu)
-                                    << (8 * b);
-                    }
-                    *reinterpret_cast<uint4 *>(ep.out1 + o) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-                if (ep.out_f32) {
-                    float *f = ep.out_f32 + (size_t)m * ep.out_f32_ld + gc;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (gc + i < ep.cout) f[i] = (float)v[i];
-                }
-            }
-        }
-    } else if (lane == 0) {
+    } else if (warp == MMA_WARP) {
         // =========================== MMA issuer ==================================
-        constexpr uint32_t idesc = instr_desc(A_SIGNED, BN);
-        for (int kt = 0; kt < g.ktiles; ++kt) {
-            const int slot = kt % STAGES;
-            mbar_wait(full_bar(slot), (kt / STAGES) & 1);
-            tc_fence_after();
-            const uint32_t sa = smem_base + slot * STAGE;
-            const uint32_t sb = sa + A_STAGE;
+        if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc(A_SIGNED, BN);
+            int slot = 0, phase = 0;
+            int buf = 0, acc_phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                mbar_wait(acc_empty_bar(buf), acc_phase ^ 1);   // epilogue drained this buffer
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+                for (int kt = 0; kt < g.ktiles; ++kt) {
+                    mbar_wait(full_bar(slot), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + slot * STAGE;
+                    const uint32_t sb = sa + A_STAGE;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const uint64_t ad = smem_desc(sa + i * 2 * A_CHUNK, A_CHUNK, 128);
-                const uint64_t bd = smem_desc(sb + i * 2 * B_CHUNK, B_CHUNK, 128);
-                umma_i8(tmem_base, ad, bd, idesc, (uint32_t)((kt | i) != 0));
+                    for (int i = 0; i < 2; ++i) {
+                        const uint64_t ad = smem_desc(sa + i * 2 * A_CHUNK, A_CHUNK, 128);
+                        const uint64_t bd = smem_desc(sb + i * 2 * B_CHUNK, B_CHUNK, 128);
+                        umma_i8(tacc, ad, bd, idesc, (uint32_t)((kt | i) != 0));
+                    }
+                    umma_commit(empty_bar(slot));   // frees the stage once these MMAs have read it
+                    if (++slot == S) { slot = 0; phase ^= 1; }
+                }
+                umma_commit(acc_full_bar(buf));     // accumulator complete -> epilogue
+                if (++buf == 2) { buf = 0; acc_phase ^= 1; }
             }
-            umma_commit(empty_bar(slot));     // frees the stage when these MMAs have read it
         }
-        umma_commit(accum_bar);               // accumulator complete -> epilogue
+    } else {
+        // =========================== epilogue (warps 0-3) =========================
+        const int row = tid;                         // TMEM lane == tile row
+        const bool has_carry = ep.carry_in != nullptr;
+        int buf = 0, acc_phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int mt = t / ntiles_n;
+            const int n0 = (t - mt * ntiles_n) * BN;
+            const int m = mt * BM + row;
+            const bool valid = m < g.M;
+            int ncols = ep.cout_pad - n0;
+            if (ncols > BN) ncols = BN;
+            int32_t *bias_s = sbias + buf * BN;
+            for (int i = row; i < ncols; i += EPI_THREADS) bias_s[i] = __ldg(ep.bias + n0 + i);
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+            mbar_wait(acc_full_bar(buf), acc_phase);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN);
+            for (int c0 = 0; c0 < ncols; c0 += 16) {
+                int32_t v[16];
+                tmem_ld16(trow + (uint32_t)c0, v);
+                tmem_ld_wait();
+                if (c0 + 16 >= ncols) {
+                    // every accumulator column of this tile is now in registers
+                    tc_fence_before();
+                    mbar_arrive(acc_empty_bar(buf));
+                }
+                if (valid) {
+                    const int gc = n0 + c0;
+                    const size_t o = (size_t)m * ep.cout_pad + gc;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        const int4 b = *reinterpret_cast<const int4 *>(bias_s + c0 + i);
+                        v[i + 0] = (int32_t)((uint32_t)v[i + 0] + (uint32_t)b.x);
+                        v[i + 1] = (int32_t)((uint32_t)v[i + 1] + (uint32_t)b.y);
+                        v[i + 2] = (int32_t)((uint32_t)v[i + 2] + (uint32_t)b.z);
+                        v[i + 3] = (int32_t)((uint32_t)v[i + 3] + (uint32_t)b.w);
+                        int4 c = make_int4(0, 0, 0, 0);
+                        if (has_carry) c = ld_stream_int4(ep.carry_in + o + i);
+                        v[i + 0] = f8::residual_relu(v[i + 0], has_carry, c.x, ep.carry_shift, ep.relu);
+                        v[i + 1] = f8::residual_relu(v[i + 1], has_carry, c.y, ep.carry_shift, ep.relu);
+                        v[i + 2] = f8::residual_relu(v[i + 2], has_carry, c.z, ep.carry_shift, ep.relu);
+                        v[i + 3] = f8::residual_relu(v[i + 3], has_carry, c.w, ep.carry_shift, ep.relu);
+                        if (ep.carry_out)
+                            *reinterpret_cast<int4 *>(ep.carry_out + o + i) =
+                                make_int4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    }
+                    if (ep.out0) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            w[i] = 0;
+#pragma unroll
+                            for (int b = 0; b < 4; ++b)
+                                w[i] |= ((uint32_t)f8::requant(v[i * 4 + b], ep.shift0, ep.signed0) & 0xffu)
+                                        << (8 * b);
+                        }
+                        *reinterpret_cast<uint4 *>(ep.out0 + o) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                    if (ep.out1) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            w[i] = 0;
+#pragma unroll
+                            for (int b = 0; b < 4; ++b)
+                                w[i] |= ((uint32_t)f8::requant(v[i * 4 + b], ep.shift1, ep.signed1) & 0xffu)
+                                        << (8 * b);
+                        }
+                        *reinterpret_cast<uint4 *>(ep.out1 + o) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                    if (ep.out_f32) {
+                        float *f = ep.out_f32 + (size_t)m * ep.out_f32_ld + gc;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (gc + i < ep.cout) f[i] = (float)v[i];
+                    }
+                }
+            }
+            if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+        }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == MMA_WARP) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, BN);
+        tmem_dealloc(tmem_base, 2 * BN);
     }
+}
+
+template <int BN>
+constexpr int smem_bytes_for() {
+    return stages_for(BN) * (A_STAGE + BN * BK) + (2 * stages_for(BN) + 4) * 8 + 16 + 2 * BN * 4;
 }
 
 template <int BN, bool A_SIGNED, bool SMALL_C>
 int launch_t(const UGeom &g, const f8::Epilogue &ep, cudaStream_t s) {
-    constexpr int smem_bytes = STAGES * (A_STAGE + BN * BK) + (2 * STAGES + 1) * 8 + 16;
+    constexpr int smem_bytes = smem_bytes_for<BN>();
     auto kern = conv_umma_kernel<BN, A_SIGNED, SMALL_C>;
     static bool attr_done = false;
+    static int num_sms = 0;
     if (!attr_done) {
         F8_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        int dev = 0;
+        F8_CUDA(cudaGetDevice(&dev));
+        F8_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         attr_done = true;
     }
-    dim3 grid((g.M + BM - 1) / BM, (ep.cout_pad + BN - 1) / BN);
-    kern<<<grid, THREADS, smem_bytes, s>>>(g, ep);
+    const int mtiles = (g.M + BM - 1) / BM;
+    const int ntn = (ep.cout_pad + BN - 1) / BN;
+    const long long total = (long long)mtiles * ntn;
+    // 2 x BN TMEM columns and the smem ring per CTA: two co-resident CTAs for BN <= 128
+    const int per_sm = (BN <= 128) ? 2 : 1;
+    long long grid = (long long)num_sms * per_sm;
+    if (grid > total) grid = total;
+    kern<<<(unsigned)grid, THREADS, smem_bytes, s>>>(g, ep, mtiles, ntn);
     F8_CUDA(cudaGetLastError());
     return F8_OK;
 }

@@ -243,8 +243,8 @@ extern "C" int f8_plan_workspace_bytes(const f8_plan *plan, int max_batch, size_
 }
 
 extern "C" int f8_plan_set_backend(f8_plan *plan, int backend) {
-    if (!plan || backend < 0 || backend > 1) { set_error("set_backend: bad arguments"); return F8_ERR_ARG; }
-    if (backend == 1 && !f8_has_umma(plan->device)) {
+    if (!plan || backend < 0 || backend > 2) { set_error("set_backend: bad arguments"); return F8_ERR_ARG; }
+    if (backend >= 1 && !f8_has_umma(plan->device)) {
         set_error("set_backend: tcgen05 backend not available on device %d", plan->device);
         return F8_ERR_UNSUPPORTED;
     }
@@ -437,9 +437,15 @@ extern "C" int f8_conv_dense(const f8_conv_args *a, int backend, void *stream) {
     if (rc) return rc;
     if (!a->wpack || !a->bias) { set_error("conv_dense: no weights / bias"); return F8_ERR_ARG; }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (backend == 1) {
+    if (backend >= 1) {
+        // backend 1: resident-patch kernel for 3x3 s1, gather kernel for the rest;
+        // backend 2: gather kernel only (A/B comparisons)
+        if (backend == 1) {
+            rc = f8host::launch_conv3x3_umma(*a, s);
+            if (rc != F8_ERR_UNSUPPORTED) return rc;
+        }
         rc = f8host::launch_conv_umma(*a, s);
-        if (rc != F8_ERR_UNSUPPORTED) return rc;   // shapes outside the tcgen05 kernel: IMMA path
+        if (rc != F8_ERR_UNSUPPORTED) return rc;   // shapes outside the tcgen05 kernels: IMMA path
     }
     return f8host::launch_conv_mma(*a, s);
 }
@@ -498,5 +504,6 @@ extern "C" int f8_has_umma(int device) {
 #ifndef F8_WITH_UMMA
 namespace f8host {
 int launch_conv_umma(const f8_conv_args &, cudaStream_t) { return F8_ERR_UNSUPPORTED; }
+int launch_conv3x3_umma(const f8_conv_args &, cudaStream_t) { return F8_ERR_UNSUPPORTED; }
 }  // namespace f8host
 #endif

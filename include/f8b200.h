@@ -159,7 +159,8 @@ F8_API int f8_plan_profile(f8_plan *plan, const void *x_dev, int x_layout, int n
 
 /* Number of kernel launches one f8_plan_run(x_layout, n, chunk) enqueues. */
 F8_API int f8_plan_launch_count(const f8_plan *plan, int x_layout, int n, int chunk);
-/* Which dense-conv backend the plan uses: 0 = mma.sync (legacy IMMA), 1 = tcgen05 (UMMA+TMA) */
+/* Which dense-conv backend the plan uses: 0 = mma.sync (legacy IMMA); 1 = tcgen05 (resident-
+ * patch kernel for 3x3 stride 1, gather kernel otherwise); 2 = tcgen05 gather kernel only */
 F8_API int f8_plan_set_backend(f8_plan *plan, int backend);
 
 /* ------------------------------------------------------------------------------------

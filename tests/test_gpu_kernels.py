@@ -66,6 +66,9 @@ DENSE_SHAPES = [
     (144, 24, 1, 1, 0, 9),     # K = 144 (not a multiple of 64)
     (160, 960, 1, 1, 0, 7),
     (512, 512, 3, 1, 1, 7),    # K = 4608
+    (64, 64, 3, 1, 1, 56),     # resident-patch kernel: 2 rows per M segment
+    (128, 192, 3, 1, 1, 28),   # 2 channel groups, 3 N tiles
+    (256, 256, 3, 1, 1, 14),
 ]
 
 
