@@ -26,27 +26,34 @@
 // fetched once (4 bulk copies of 1 KB) and used by all four M segments.
 //
 // Persistent CTA, 1 per SM, 512 TMEM columns = 2 (double buffer) x 4 segments x 64 columns:
-//   warps 0-3 epilogue | warps 4-7 patch loaders (cp.async, zero fill) | warp 8 lane 0 MMA
-//   | warp 9 lane 0 weight-tile loader (cp.async.bulk).
+//   warps 0-15 epilogue (the exact integer requantisation is instruction-bound: 16 warps)
+//   | warps 16-19 patch loaders (cp.async, zero fill) | warp 20: one elected lane issues the MMAs
+//   | warp 21 lane 0 weight-tile loader (cp.async.bulk).
+#include <cstdio>
+#include <cstdlib>
+
 #include "umma_common.cuh"
 
 namespace {
 
 using namespace f8u;
 
-constexpr int BN = 64;                 // output channels per tile
-constexpr int MB = 4;                  // M segments of 128 rows per tile
-constexpr int TM = 128 * MB;           // output indices per tile
-constexpr int SA = 2;                  // patch ring (one stage = 64 channels of the patch)
-constexpr int SB = 12;                 // weight-tile ring (one stage = 64 cout x 64 K bytes)
-constexpr int B_TILE = BN * 64;
-constexpr int EPI_THREADS = 128;
+// Tile = MB segments of 128 output indices x BN output channels, MB * BN = 256 so that two
+// accumulator sets fill the 512 TMEM columns.  BN = 128 (MB = 2) balances the tensor pipe
+// against operand fetch from shared memory (per K=32 MMA: 4 KB of A + 4 KB of B in 64 tensor
+// cycles); BN = 64 (MB = 4) serves the 64-channel layers.
+__host__ __device__ constexpr int mb_for(int bn) { return 256 / bn; }
+__host__ __device__ constexpr int sb_for(int bn) { return bn == 64 ? 12 : 8; }   // weight-tile ring
+constexpr int SA = 3;                  // patch ring (one stage = 64 channels of the patch)
+constexpr int A_LAG = 1;               // a stage is signalled once A_LAG younger stages are issued
+constexpr int EPI_WARPS = 16;          // warp w: TMEM lane group w % 4, 16-column slice w / 4
+constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int LOADERS = 128;
-constexpr int LOADER_WARP0 = 4;
-constexpr int MMA_WARP = 8;
-constexpr int WLOAD_WARP = 9;
-constexpr int THREADS = 320;
-constexpr int MAX_SLOT_ITERS = 6;      // ceil((TM + 2*PW + 2) / 128) for PW <= 120
+constexpr int LOADER_WARP0 = EPI_WARPS;
+constexpr int MMA_WARP = EPI_WARPS + 4;
+constexpr int WLOAD_WARP = EPI_WARPS + 5;
+constexpr int THREADS = (EPI_WARPS + 6) * 32;
+constexpr int MAX_SLOT_ITERS = 6;      // ceil((TM + 2*PW + 2) / 128) for TM = 512, PW <= 120
 
 struct PGeom {
     const uint8_t *in;
@@ -54,16 +61,34 @@ struct PGeom {
     int wrows;
     int N, H, W, C;         // C = cin_pad (multiple of 64)
     int PW;                 // W + 1
-    int slots;              // TM + 2*PW + 2
+    int tm;                 // 128 * MB
+    int slots;              // tm + 2*PW + 2
     int slots_pad;          // slots rounded up to 8
     int n_super;            // tiles along the padded linear space
-    int ntiles_n;           // cout_pad / 64 (rounded up)
+    int ntiles_n;           // cout_pad / BN (rounded up)
+    long long *stats;       // debug (F8_STATS=1): per-CTA wait-cycle counters, else nullptr
 };
 
-template <bool A_SIGNED>
+#define F8_TIMED_WAIT(acc, stmt)                 \
+    do {                                         \
+        if (g.stats) {                           \
+            const long long _t0 = clock64();     \
+            stmt;                                \
+            acc += clock64() - _t0;              \
+        } else {                                 \
+            stmt;                                \
+        }                                        \
+    } while (0)
+
+template <int BN, bool A_SIGNED, bool PLAIN_U8>
 __global__ void __launch_bounds__(THREADS, 1)
 conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
     extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int MB = mb_for(BN);
+    constexpr int TM = 128 * MB;
+    constexpr int SB = sb_for(BN);
+    constexpr int B_TILE = BN * 64;
+    constexpr int CW = BN / 4;                             // columns per epilogue warp slice
     const int a_stage = g.slots_pad * 64;                 // bytes of one patch stage
     const uint32_t lbo_a = (uint32_t)g.slots_pad * 16;
     const uint32_t smem_base = f8::smem_u32(smem);
@@ -106,9 +131,11 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
         // =========================== patch loaders ================================
         const int lt = tid - LOADER_WARP0 * 32;
         int slot = 0, phase = 0, aslot = 0, issued = 0;
+        long long w_empty = 0, w_cp = 0;
+        const long long t_begin = clock64();
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
             const int st = it / g.ntiles_n;
-            const long long pi0 = (long long)st * TM;
+            const int pi0 = st * TM;
             // decode this thread's slots once per tile: global byte offset of the pixel or -1
             long long off[MAX_SLOT_ITERS];
 #pragma unroll
@@ -116,9 +143,9 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
                 const int pl = lt + k * LOADERS;
                 off[k] = -1;
                 if (pl < g.slots) {
-                    const long long pi = pi0 + pl;
-                    const int Yp = (int)(pi / g.PW);
-                    const int xs = (int)(pi - (long long)Yp * g.PW);
+                    const int pi = pi0 + pl;
+                    const int Yp = pi / g.PW;
+                    const int xs = pi - Yp * g.PW;
                     const int img = Yp / HP;
                     const int yy = Yp - img * HP;
                     if (xs >= 1 && yy >= 1 && img < g.N)
@@ -126,7 +153,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
                 }
             }
             for (int cg = 0; cg < ncg; ++cg) {
-                mbar_wait(a_empty(slot), phase ^ 1);
+                F8_TIMED_WAIT(w_empty, mbar_wait(a_empty(slot), phase ^ 1));
                 const uint32_t sa = smem_base + slot * a_stage;
 #pragma unroll
                 for (int k = 0; k < MAX_SLOT_ITERS; ++k) {
@@ -141,8 +168,10 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
                 }
                 cp_async_commit();
                 if (++slot == SA) { slot = 0; phase ^= 1; }
-                if (++issued == SA) {
-                    cp_async_wait<SA - 1>();
+                // signal a stage as soon as its bytes have landed, WITHOUT first needing a free
+                // slot for a much younger stage (that would chain MMA(k) behind MMA(k-1))
+                if (++issued > A_LAG) {
+                    F8_TIMED_WAIT(w_cp, cp_async_wait<A_LAG>());
                     fence_proxy_async();
                     mbar_arrive(a_full(aslot));
                     if (++aslot == SA) aslot = 0;
@@ -156,16 +185,23 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
             mbar_arrive(a_full(aslot));
             if (++aslot == SA) aslot = 0;
         }
+        if (g.stats && lt == 0) {
+            g.stats[blockIdx.x * 16 + 0] = clock64() - t_begin;
+            g.stats[blockIdx.x * 16 + 1] = w_empty;
+            g.stats[blockIdx.x * 16 + 2] = w_cp;
+        }
     } else if (warp == WLOAD_WARP) {
         // =========================== weight-tile loader ===========================
         if (lane == 0) {
             int slot = 0, phase = 0;
+            long long w_bempty = 0;
+            const long long t_begin = clock64();
             for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
                 const int st = it / g.ntiles_n;
                 const int n0 = (it - st * g.ntiles_n) * BN;
                 for (int cg = 0; cg < ncg; ++cg)
                     for (int tap = 0; tap < 9; ++tap) {
-                        mbar_wait(b_empty(slot), phase ^ 1);
+                        F8_TIMED_WAIT(w_bempty, mbar_wait(b_empty(slot), phase ^ 1));
                         const uint32_t sb = sb_base + slot * B_TILE;
                         mbar_expect_tx(b_full(slot), B_TILE);
                         mbar_arrive(b_full(slot));
@@ -177,126 +213,123 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
                         if (++slot == SB) { slot = 0; phase ^= 1; }
                     }
             }
+            if (g.stats) {
+                g.stats[blockIdx.x * 16 + 3] = clock64() - t_begin;
+                g.stats[blockIdx.x * 16 + 4] = w_bempty;
+            }
         }
     } else if (warp == MMA_WARP) {
         // =========================== MMA issuer ===================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = instr_desc(A_SIGNED, BN);
-            int aslot = 0, aphase = 0, bslot = 0, bphase = 0, buf = 0, acc_phase = 0;
-            for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
-                mbar_wait(acc_empty(buf), acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t tacc = tmem_base + (uint32_t)(buf * MB * BN);
-                for (int cg = 0; cg < ncg; ++cg) {
-                    mbar_wait(a_full(aslot), aphase);
-                    const uint32_t sa = smem_base + aslot * a_stage;
-                    for (int tap = 0; tap < 9; ++tap) {
-                        mbar_wait(b_full(bslot), bphase);
-                        tc_fence_after();
-                        const uint32_t sb = sb_base + bslot * B_TILE;
-                        const int r = tap / 3, s = tap - r * 3;
-                        const uint32_t shift = (uint32_t)(r * g.PW + s) * 16;
+        // The whole warp runs the loop (uniform control flow); one elected lane issues.
+        // Descriptor high words are loop constants, low words advance by 32-bit adds.
+        constexpr uint32_t idesc = instr_desc(A_SIGNED, BN);
+        constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);          // SBO = 128 B, version 1
+        const uint32_t a_lbo_field = (lbo_a >> 4) << 16;
+        constexpr uint32_t b_lbo_field = ((uint32_t)(BN * 16) >> 4) << 16;
+        int aslot = 0, aphase = 0, bslot = 0, bphase = 0, buf = 0, acc_phase = 0;
+        long long w_acc = 0, w_a = 0, w_b = 0;
+        const long long t_begin = clock64();
+        for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+            F8_TIMED_WAIT(w_acc, mbar_wait(acc_empty(buf), acc_phase ^ 1));
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + (uint32_t)(buf * MB * BN);
+            for (int cg = 0; cg < ncg; ++cg) {
+                F8_TIMED_WAIT(w_a, mbar_wait(a_full(aslot), aphase));
+                const uint32_t sa = smem_base + aslot * a_stage;
+                for (int tap = 0; tap < 9; ++tap) {
+                    F8_TIMED_WAIT(w_b, mbar_wait(b_full(bslot), bphase));
+                    tc_fence_after();
+                    const uint32_t sb = sb_base + bslot * B_TILE;
+                    const int r = tap / 3, s = tap - r * 3;
+                    const uint32_t a_lo0 = (((sa + (uint32_t)(r * g.PW + s) * 16) & 0x3ffffu) >> 4) | a_lbo_field;
+                    const uint32_t b_lo0 = ((sb & 0x3ffffu) >> 4) | b_lbo_field;
+                    const uint32_t first = (uint32_t)((cg | tap) != 0);
+                    if (elect_one()) {
 #pragma unroll
                         for (int i = 0; i < MB; ++i) {
 #pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const uint64_t ad = smem_desc(sa + (2 * h) * lbo_a + shift + i * 2048, lbo_a, 128);
-                                const uint64_t bd = smem_desc(sb + (2 * h) * (BN * 16), BN * 16, 128);
-                                umma_i8(tacc + (uint32_t)(i * BN), ad, bd, idesc,
-                                        (uint32_t)((cg | tap | h) != 0));
-                            }
+                            for (int h = 0; h < 2; ++h)
+                                umma_i8_lohi(tacc + (uint32_t)(i * BN),
+                                             a_lo0 + (uint32_t)((i * 2048) >> 4) + (uint32_t)h * ((2 * lbo_a) >> 4),
+                                             desc_hi,
+                                             b_lo0 + (uint32_t)h * ((2 * BN * 16) >> 4), desc_hi, idesc,
+                                             h ? 1u : first);
                         }
                         umma_commit(b_empty(bslot));
-                        if (++bslot == SB) { bslot = 0; bphase ^= 1; }
                     }
-                    umma_commit(a_empty(aslot));
-                    if (++aslot == SA) { aslot = 0; aphase ^= 1; }
+                    __syncwarp();
+                    if (++bslot == SB) { bslot = 0; bphase ^= 1; }
                 }
-                umma_commit(acc_full(buf));
-                if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+                if (elect_one()) umma_commit(a_empty(aslot));
+                __syncwarp();
+                if (++aslot == SA) { aslot = 0; aphase ^= 1; }
             }
+            if (elect_one()) umma_commit(acc_full(buf));
+            __syncwarp();
+            if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+        }
+        if (g.stats && lane == 0) {
+            g.stats[blockIdx.x * 16 + 5] = clock64() - t_begin;
+            g.stats[blockIdx.x * 16 + 6] = w_acc;
+            g.stats[blockIdx.x * 16 + 7] = w_a;
+            g.stats[blockIdx.x * 16 + 8] = w_b;
         }
     } else {
-        // =========================== epilogue (warps 0-3) =========================
-        const int row = tid;
-        const bool has_carry = ep.carry_in != nullptr;
+        // =========================== epilogue (warps 0-15) ========================
+        const int lg = warp & 3;                       // TMEM lane group of this warp
+        const int cw0 = (warp >> 2) * CW;              // this warp's column slice of the tile
+        const int row = lg * 32 + lane;
         int buf = 0, acc_phase = 0;
+        long long w_full = 0;
+        const long long t_begin = clock64();
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
             const int st = it / g.ntiles_n;
             const int n0 = (it - st * g.ntiles_n) * BN;
             int ncols = ep.cout_pad - n0;
             if (ncols > BN) ncols = BN;
             int32_t *bias_s = sbias + buf * BN;
-            if (row < ncols) bias_s[row] = __ldg(ep.bias + n0 + row);
+            if (tid < ncols) {
+                int32_t b = __ldg(ep.bias + n0 + tid);
+                if (PLAIN_U8) b = (int32_t)((uint32_t)b + (1u << (ep.shift0 - 1)));   // bias + half
+                bias_s[tid] = b;
+            }
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-            mbar_wait(acc_full(buf), acc_phase);
+            F8_TIMED_WAIT(w_full, mbar_wait(acc_full(buf), acc_phase));
             tc_fence_after();
-            for (int i = 0; i < MB; ++i) {
-                const long long m = (long long)st * TM + i * 128 + row;
-                const int Yo = (int)(m / g.PW);
-                const int xo = (int)(m - (long long)Yo * g.PW);
-                const int img = Yo / HP;
-                const int y = Yo - img * HP;
-                const bool valid = xo < g.W && y < g.H && img < g.N;
-                const size_t opix = ((size_t)(img * g.H + y) * g.W + xo);
-                const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) +
-                                      (uint32_t)((buf * MB + i) * BN);
-                for (int c0 = 0; c0 < ncols; c0 += 16) {
-                    int32_t v[16];
-                    tmem_ld16(trow + (uint32_t)c0, v);
-                    tmem_ld_wait();
-                    if (i == MB - 1 && c0 + 16 >= ncols) {
-                        tc_fence_before();
-                        mbar_arrive(acc_empty(buf));     // whole accumulator buffer drained
-                    }
-                    if (valid) {
-                        const int gc = n0 + c0;
-                        const size_t o = opix * ep.cout_pad + gc;
+            if (cw0 < ncols) {
+                for (int i = 0; i < MB; ++i) {
+                    const int m = st * TM + i * 128 + row;
+                    const int Yo = m / g.PW;
+                    const int xo = m - Yo * g.PW;
+                    const int img = Yo / HP;
+                    const int y = Yo - img * HP;
+                    const bool valid = xo < g.W && y < g.H && img < g.N;
+                    const size_t opix = ((size_t)(img * g.H + y) * g.W + xo);
+                    const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) +
+                                          (uint32_t)((buf * MB + i) * BN);
 #pragma unroll
-                        for (int q = 0; q < 16; q += 4) {
-                            const int4 b = *reinterpret_cast<const int4 *>(bias_s + c0 + q);
-                            v[q + 0] = (int32_t)((uint32_t)v[q + 0] + (uint32_t)b.x);
-                            v[q + 1] = (int32_t)((uint32_t)v[q + 1] + (uint32_t)b.y);
-                            v[q + 2] = (int32_t)((uint32_t)v[q + 2] + (uint32_t)b.z);
-                            v[q + 3] = (int32_t)((uint32_t)v[q + 3] + (uint32_t)b.w);
-                            int4 c = make_int4(0, 0, 0, 0);
-                            if (has_carry) c = ld_stream_int4(ep.carry_in + o + q);
-                            v[q + 0] = f8::residual_relu(v[q + 0], has_carry, c.x, ep.carry_shift, ep.relu);
-                            v[q + 1] = f8::residual_relu(v[q + 1], has_carry, c.y, ep.carry_shift, ep.relu);
-                            v[q + 2] = f8::residual_relu(v[q + 2], has_carry, c.z, ep.carry_shift, ep.relu);
-                            v[q + 3] = f8::residual_relu(v[q + 3], has_carry, c.w, ep.carry_shift, ep.relu);
-                            if (ep.carry_out)
-                                *reinterpret_cast<int4 *>(ep.carry_out + o + q) =
-                                    make_int4(v[q], v[q + 1], v[q + 2], v[q + 3]);
-                        }
-                        if (ep.out0) {
-                            uint32_t w[4];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                w[q] = 0;
-#pragma unroll
-                                for (int b = 0; b < 4; ++b)
-                                    w[q] |= ((uint32_t)f8::requant(v[q * 4 + b], ep.shift0, ep.signed0) & 0xffu)
-                                            << (8 * b);
+                    for (int c0 = cw0; c0 < cw0 + CW; c0 += 16) {
+                        if (c0 < ncols) {
+                            int32_t v[16];
+                            tmem_ld16(trow + (uint32_t)c0, v);
+                            tmem_ld_wait();
+                            if (valid) {
+                                const size_t o = opix * ep.cout_pad + n0 + c0;
+                                if (PLAIN_U8) f8::epilogue16_plain_u8(v, bias_s + c0, ep.out0 + o, ep.shift0);
+                                else f8::epilogue16(v, bias_s + c0, ep, o, n0 + c0, opix);
                             }
-                            *reinterpret_cast<uint4 *>(ep.out0 + o) = make_uint4(w[0], w[1], w[2], w[3]);
-                        }
-                        if (ep.out1) {
-                            uint32_t w[4];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                w[q] = 0;
-#pragma unroll
-                                for (int b = 0; b < 4; ++b)
-                                    w[q] |= ((uint32_t)f8::requant(v[q * 4 + b], ep.shift1, ep.signed1) & 0xffu)
-                                            << (8 * b);
-                            }
-                            *reinterpret_cast<uint4 *>(ep.out1 + o) = make_uint4(w[0], w[1], w[2], w[3]);
                         }
                     }
                 }
             }
+            // every accumulator column this thread owns is in registers (or consumed)
+            tc_fence_before();
+            mbar_arrive(acc_empty(buf));
             if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+        }
+        if (g.stats && tid == 0) {
+            g.stats[blockIdx.x * 16 + 9] = clock64() - t_begin;
+            g.stats[blockIdx.x * 16 + 10] = w_full;
         }
     }
 
@@ -310,13 +343,14 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
 
 }  // namespace
 
-namespace f8host {
+namespace {
 
-// F8_ERR_UNSUPPORTED => the caller falls back to the gather kernel (conv_umma.cu)
-int launch_conv3x3_umma(const f8_conv_args &a, cudaStream_t s) {
-    if (a.kh != 3 || a.kw != 3 || a.stride != 1 || a.pad != 1 || a.cin_pad % 64 != 0 ||
-        a.cout_pad % 16 != 0 || a.hin != a.hout || a.win != a.wout || a.out_f32 != nullptr)
-        return F8_ERR_UNSUPPORTED;
+template <int BN>
+int launch_bn(const f8_conv_args &a, cudaStream_t s) {
+    constexpr int MB = mb_for(BN);
+    constexpr int TM = 128 * MB;
+    constexpr int SB = sb_for(BN);
+    constexpr int B_TILE = BN * 64;
     const int PW = a.win + 1;
     const int slots = TM + 2 * PW + 2;
     if ((slots + LOADERS - 1) / LOADERS > MAX_SLOT_ITERS) return F8_ERR_UNSUPPORTED;
@@ -328,13 +362,14 @@ int launch_conv3x3_umma(const f8_conv_args &a, cudaStream_t s) {
     const size_t smem_launch = smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes;
     const long long lin = (long long)a.n * (a.hin + 1) * PW;     // padded linear output space
     if (lin > 0x7fffffffLL - TM) return F8_ERR_UNSUPPORTED;
-    const DensePack pk = dense_pack_geometry(a.cin_pad, a.cout_pad, 3, 3);
+    const f8host::DensePack pk = f8host::dense_pack_geometry(a.cin_pad, a.cout_pad, 3, 3);
     PGeom g{};
     g.in = static_cast<const uint8_t *>(a.in);
     g.wpack = static_cast<const uint8_t *>(a.wpack);
     g.wrows = pk.rows;
     g.N = a.n; g.H = a.hin; g.W = a.win; g.C = a.cin_pad;
     g.PW = PW;
+    g.tm = TM;
     g.slots = slots;
     g.slots_pad = slots_pad;
     g.n_super = (int)((lin + TM - 1) / TM);
@@ -354,10 +389,10 @@ int launch_conv3x3_umma(const f8_conv_args &a, cudaStream_t s) {
     static bool attr_done = false;
     static int num_sms = 0;
     if (!attr_done) {
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<false>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<true>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         int dev = 0;
         F8_CUDA(cudaGetDevice(&dev));
         F8_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -365,12 +400,52 @@ int launch_conv3x3_umma(const f8_conv_args &a, cudaStream_t s) {
     }
     long long grid = (long long)g.n_super * g.ntiles_n;
     if (grid > num_sms) grid = num_sms;
-    if (a.in_signed)
-        conv3x3_umma_kernel<true><<<(unsigned)grid, THREADS, smem_launch, s>>>(g, ep);
-    else
-        conv3x3_umma_kernel<false><<<(unsigned)grid, THREADS, smem_launch, s>>>(g, ep);
+    static const bool want_stats = getenv("F8_STATS") != nullptr;
+    static long long *stats_dev = nullptr;
+    if (want_stats) {
+        if (!stats_dev) F8_CUDA(cudaMalloc(&stats_dev, 16 * 1024 * sizeof(long long)));
+        F8_CUDA(cudaMemsetAsync(stats_dev, 0, 16 * 1024 * sizeof(long long), s));
+        g.stats = stats_dev;
+    }
+    const bool plain = f8::epilogue_is_plain_u8(ep);
+    const unsigned gr = (unsigned)grid;
+    if (a.in_signed) {
+        if (plain) conv3x3_umma_kernel<BN, true, true><<<gr, THREADS, smem_launch, s>>>(g, ep);
+        else conv3x3_umma_kernel<BN, true, false><<<gr, THREADS, smem_launch, s>>>(g, ep);
+    } else {
+        if (plain) conv3x3_umma_kernel<BN, false, true><<<gr, THREADS, smem_launch, s>>>(g, ep);
+        else conv3x3_umma_kernel<BN, false, false><<<gr, THREADS, smem_launch, s>>>(g, ep);
+    }
     F8_CUDA(cudaGetLastError());
+    if (want_stats) {
+        static long long host[16 * 1024];
+        F8_CUDA(cudaStreamSynchronize(s));
+        F8_CUDA(cudaMemcpy(host, stats_dev, sizeof(host), cudaMemcpyDeviceToHost));
+        double acc[16] = {0};
+        for (long long b = 0; b < grid; ++b)
+            for (int k = 0; k < 16; ++k) acc[k] += (double)host[b * 16 + k] / (double)grid;
+        const long long items = (long long)g.n_super * g.ntiles_n;
+        fprintf(stderr,
+                "[f8 stats] conv3x3 BN=%d C=%d cout=%d HxW=%dx%d items=%lld/cta=%.1f | loader total %.0f wait_empty %.0f "
+                "wait_cp %.0f | wload total %.0f wait_bempty %.0f | mma total %.0f wait_acc %.0f wait_a %.0f "
+                "wait_b %.0f | epi total %.0f wait_full %.0f (cycles, mean per CTA)\n",
+                BN, g.C, a.cout, g.H, g.W, items, (double)items / (double)grid, acc[0], acc[1], acc[2], acc[3],
+                acc[4], acc[5], acc[6], acc[7], acc[8], acc[9], acc[10]);
+    }
     return F8_OK;
+}
+
+}  // namespace
+
+namespace f8host {
+
+// F8_ERR_UNSUPPORTED => the caller falls back to the gather kernel (conv_umma.cu)
+int launch_conv3x3_umma(const f8_conv_args &a, cudaStream_t s) {
+    if (a.kh != 3 || a.kw != 3 || a.stride != 1 || a.pad != 1 || a.cin_pad % 64 != 0 ||
+        a.cout_pad % 16 != 0 || a.hin != a.hout || a.win != a.wout || a.out_f32 != nullptr)
+        return F8_ERR_UNSUPPORTED;
+    if (a.cout_pad > 64) return launch_bn<128>(a, s);
+    return launch_bn<64>(a, s);
 }
 
 }  // namespace f8host

@@ -13,19 +13,20 @@
 // PERSISTENT kernel, one or two CTAs per SM, each looping over its tiles with one operand
 // ring and two TMEM accumulators, so the loads of tile i+1 and the epilogue of tile i-1
 // overlap the MMAs of tile i.  Warp roles:
-//   warps 4-7  producers.  Thread r owns tile row r (one output pixel): it gathers the
+//   warps 8-11 producers.  Thread r owns tile row r (one output pixel): it gathers the
 //              pixel's K bytes from the NHWC activation with 16-byte cp.async (zero fill for
 //              the padding halo) into the canonical K-major no-swizzle operand layout
 //              [K/16][128 rows][16 B] (core matrix = 8 rows x 16 B contiguous, SBO = 128 B,
 //              LBO = 2048 B), fences the generic->async proxy and arrives on the stage's
 //              "full" mbarrier.  Its thread 0 also posts the stage's weight bytes: 4 bulk
 //              copies of BN*16 contiguous bytes from the chunk-major weight image.
-//   warp 8     lane 0 issues the MMAs (tcgen05.mma is a single-thread instruction), commits
+//   warp 12    lane 0 issues the MMAs (tcgen05.mma is a single-thread instruction), commits
 //              each stage to its "empty" mbarrier and each finished accumulator to
-//              "acc_full".  Warp 8 also owns the TMEM allocation (2 x BN columns).
-//   warps 0-3  epilogue: thread t reads accumulator row t (TMEM lane = tile row) 16 columns
-//              at a time, releases the accumulator ("acc_empty") as soon as the last column
-//              is in registers, and runs the integer epilogue of f8_common.cuh.
+//              "acc_full".  Warp 12 also owns the TMEM allocation (2 x BN columns).
+//   warps 0-7  epilogue: warp w reads TMEM lane group w % 4 (lane = tile row), column half
+//              w / 4, 16 columns at a time, runs the integer epilogue of f8_common.cuh and
+//              releases the accumulator ("acc_empty").  Eight warps because the exact integer
+//              requantisation costs ~8 instructions per element.
 // Integer accumulation is associative mod 2^32: tiling and MMA order cannot change results.
 #include "umma_common.cuh"
 
@@ -33,11 +34,12 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int EPI_THREADS = 128;      // warps 0-3: epilogue (warp % 4 == TMEM lane group)
-constexpr int PRODUCER_WARP0 = 4;     // warps 4-7: A gather (+ thread 0 of them: B bulk copies)
+constexpr int EPI_WARPS = 8;          // warps 0-7: epilogue (lane group w % 4, column half w / 4)
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int PRODUCER_WARP0 = 8;     // warps 8-11: A gather (+ thread 0 of them: B bulk copies)
 constexpr int PRODUCERS = 128;
-constexpr int MMA_WARP = 8;           // warp 8: TMEM alloc, lane 0 issues tcgen05.mma
-constexpr int THREADS = 288;
+constexpr int MMA_WARP = 12;          // warp 12: TMEM alloc, lane 0 issues tcgen05.mma
+constexpr int THREADS = 416;
 // ring depth per tile width: ~96-120 KB of operand bytes in flight per CTA
 __host__ __device__ constexpr int stages_for(int bn) { return bn <= 64 ? 8 : (bn <= 128 ? 6 : 5); }
 constexpr int A_STAGE = BM * BK;          // 8192 B: [4 chunks][128 rows][16 B]
@@ -61,7 +63,7 @@ using namespace f8u;
 // Persistent, warp-specialised kernel.  Static tile schedule: CTA b runs tiles b, b+grid, ...
 // with the N tile fastest, so CTAs that are co-resident read the same activation rows.
 template <int BN, bool A_SIGNED, bool SMALL_C>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, (BN <= 128) ? 2 : 1)
 conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const int ntiles_n) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int S = stages_for(BN);
@@ -165,8 +167,10 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
                 }
                 cp_async_commit();
                 if (++slot == S) { slot = 0; phase ^= 1; }
-                if (++issued == S) {
-                    cp_async_wait<S - 1>();       // the oldest unsignalled stage has landed
+                // signal with a lag of S/2 stages: deep enough to cover the load latency, and
+                // never waiting for a slot the MMA of the immediately preceding stage holds
+                if (++issued > S / 2) {
+                    cp_async_wait<S / 2>();       // the oldest unsignalled stage has landed
                     fence_proxy_async();          // generic-proxy writes -> visible to the MMA
                     mbar_arrive(full_bar(aslot));
                     if (++aslot == S) aslot = 0;
@@ -182,36 +186,42 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
         }
     } else if (warp == MMA_WARP) {
         // =========================== MMA issuer ==================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = instr_desc(A_SIGNED, BN);
-            int slot = 0, phase = 0;
-            int buf = 0, acc_phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                mbar_wait(acc_empty_bar(buf), acc_phase ^ 1);   // epilogue drained this buffer
+        // whole warp in the loop (uniform control flow), one elected lane issues; descriptor
+        // high words are constants, low words advance by 32-bit adds
+        constexpr uint32_t idesc = instr_desc(A_SIGNED, BN);
+        constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);          // SBO = 128 B, version 1
+        constexpr uint32_t a_lbo_field = ((uint32_t)A_CHUNK >> 4) << 16;
+        constexpr uint32_t b_lbo_field = ((uint32_t)B_CHUNK >> 4) << 16;
+        int slot = 0, phase = 0;
+        int buf = 0, acc_phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            mbar_wait(acc_empty_bar(buf), acc_phase ^ 1);   // epilogue drained this buffer
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+            for (int kt = 0; kt < g.ktiles; ++kt) {
+                mbar_wait(full_bar(slot), phase);
                 tc_fence_after();
-                const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
-                for (int kt = 0; kt < g.ktiles; ++kt) {
-                    mbar_wait(full_bar(slot), phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem_base + slot * STAGE;
-                    const uint32_t sb = sa + A_STAGE;
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const uint64_t ad = smem_desc(sa + i * 2 * A_CHUNK, A_CHUNK, 128);
-                        const uint64_t bd = smem_desc(sb + i * 2 * B_CHUNK, B_CHUNK, 128);
-                        umma_i8(tacc, ad, bd, idesc, (uint32_t)((kt | i) != 0));
-                    }
+                const uint32_t sa = smem_base + slot * STAGE;
+                const uint32_t a_lo = ((sa & 0x3ffffu) >> 4) | a_lbo_field;
+                const uint32_t b_lo = (((sa + A_STAGE) & 0x3ffffu) >> 4) | b_lbo_field;
+                if (elect_one()) {
+                    umma_i8_lohi(tacc, a_lo, desc_hi, b_lo, desc_hi, idesc, (uint32_t)(kt != 0));
+                    umma_i8_lohi(tacc, a_lo + ((2 * A_CHUNK) >> 4), desc_hi, b_lo + ((2 * B_CHUNK) >> 4),
+                                 desc_hi, idesc, 1u);
                     umma_commit(empty_bar(slot));   // frees the stage once these MMAs have read it
-                    if (++slot == S) { slot = 0; phase ^= 1; }
                 }
-                umma_commit(acc_full_bar(buf));     // accumulator complete -> epilogue
-                if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++slot == S) { slot = 0; phase ^= 1; }
             }
+            if (elect_one()) umma_commit(acc_full_bar(buf));     // accumulator complete -> epilogue
+            __syncwarp();
+            if (++buf == 2) { buf = 0; acc_phase ^= 1; }
         }
     } else {
-        // =========================== epilogue (warps 0-3) =========================
-        const int row = tid;                         // TMEM lane == tile row
-        const bool has_carry = ep.carry_in != nullptr;
+        // =========================== epilogue (warps 0-7) =========================
+        const int lg = warp & 3;                       // TMEM lane group of this warp
+        const int ch = warp >> 2;                      // column half
+        const int row = lg * 32 + lane;                // TMEM lane == tile row
         int buf = 0, acc_phase = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int mt = t / ntiles_n;
@@ -221,72 +231,24 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
             int ncols = ep.cout_pad - n0;
             if (ncols > BN) ncols = BN;
             int32_t *bias_s = sbias + buf * BN;
-            for (int i = row; i < ncols; i += EPI_THREADS) bias_s[i] = __ldg(ep.bias + n0 + i);
+            for (int i = tid; i < ncols; i += EPI_THREADS) bias_s[i] = __ldg(ep.bias + n0 + i);
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
             mbar_wait(acc_full_bar(buf), acc_phase);
             tc_fence_after();
-            const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN);
-            for (int c0 = 0; c0 < ncols; c0 += 16) {
+            const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * BN);
+            const int c_lo = ch * (BN / 2);
+            int c_hi = c_lo + BN / 2;
+            if (c_hi > ncols) c_hi = ncols;
+            for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
                 int32_t v[16];
                 tmem_ld16(trow + (uint32_t)c0, v);
                 tmem_ld_wait();
-                if (c0 + 16 >= ncols) {
-                    // every accumulator column of this tile is now in registers
-                    tc_fence_before();
-                    mbar_arrive(acc_empty_bar(buf));
-                }
-                if (valid) {
-                    const int gc = n0 + c0;
-                    const size_t o = (size_t)m * ep.cout_pad + gc;
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        const int4 b = *reinterpret_cast<const int4 *>(bias_s + c0 + i);
-                        v[i + 0] = (int32_t)((uint32_t)v[i + 0] + (uint32_t)b.x);
-                        v[i + 1] = (int32_t)((uint32_t)v[i + 1] + (uint32_t)b.y);
-                        v[i + 2] = (int32_t)((uint32_t)v[i + 2] + (uint32_t)b.z);
-                        v[i + 3] = (int32_t)((uint32_t)v[i + 3] + (uint32_t)b.w);
-                        int4 c = make_int4(0, 0, 0, 0);
-                        if (has_carry) c = ld_stream_int4(ep.carry_in + o + i);
-                        v[i + 0] = f8::residual_relu(v[i + 0], has_carry, c.x, ep.carry_shift, ep.relu);
-                        v[i + 1] = f8::residual_relu(v[i + 1], has_carry, c.y, ep.carry_shift, ep.relu);
-                        v[i + 2] = f8::residual_relu(v[i + 2], has_carry, c.z, ep.carry_shift, ep.relu);
-                        v[i + 3] = f8::residual_relu(v[i + 3], has_carry, c.w, ep.carry_shift, ep.relu);
-                        if (ep.carry_out)
-                            *reinterpret_cast<int4 *>(ep.carry_out + o + i) =
-                                make_int4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                    }
-                    if (ep.out0) {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            w[i] = 0;
-#pragma unroll
-                            for (int b = 0; b < 4; ++b)
-                                w[i] |= ((uint32_t)f8::requant(v[i * 4 + b], ep.shift0, ep.signed0) & 0xffu)
-                                        << (8 * b);
-                        }
-                        *reinterpret_cast<uint4 *>(ep.out0 + o) = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
-                    if (ep.out1) {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            w[i] = 0;
-#pragma unroll
-                            for (int b = 0; b < 4; ++b)
-                                w[i] |= ((uint32_t)f8::requant(v[i * 4 + b], ep.shift1, ep.signed1) & 0xffu)
-                                        << (8 * b);
-                        }
-                        *reinterpret_cast<uint4 *>(ep.out1 + o) = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
-                    if (ep.out_f32) {
-                        float *f = ep.out_f32 + (size_t)m * ep.out_f32_ld + gc;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (gc + i < ep.cout) f[i] = (float)v[i];
-                    }
-                }
+                if (valid)
+                    f8::epilogue16(v, bias_s + c0, ep, (size_t)m * ep.cout_pad + n0 + c0, n0 + c0,
+                                   (size_t)m);
             }
+            tc_fence_before();
+            mbar_arrive(acc_empty_bar(buf));       // this thread's columns are drained
             if (++buf == 2) { buf = 0; acc_phase ^= 1; }
         }
     }

@@ -33,6 +33,38 @@ __device__ __forceinline__ int32_t requant(int32_t x, int n, int is_signed) {
     return max(lo, min(hi, r));
 }
 
+// requant() without the final clamp: the saturating byte pack below supplies it.
+//   tie <=> (x mod 2^n) == 2^(n-1) <=> the low n bits of t = x + 2^(n-1) are all zero
+__device__ __forceinline__ int32_t requant_shift(int32_t x, int n) {
+    if (n > 0) {
+        const uint32_t half = 1u << (n - 1);
+        const uint32_t mask = (half << 1) - 1u;
+        const uint32_t t = (uint32_t)x + half;
+        int32_t r = (int32_t)t >> n;
+        if ((t & mask) == 0u) r &= ~1;
+        return r;
+    }
+    return (int32_t)((uint32_t)x << (-n));
+}
+
+// four requantised values -> four saturated bytes (a in the low byte).  cvt.pack.sat clamps to
+// [0,255] (u8) or [-128,127] (s8); the reference's signed range is [-127,127], hence the max.
+__device__ __forceinline__ uint32_t requant_pack4(int32_t a, int32_t b, int32_t c, int32_t d, int n,
+                                                  int is_signed) {
+    a = requant_shift(a, n); b = requant_shift(b, n);
+    c = requant_shift(c, n); d = requant_shift(d, n);
+    uint32_t hi, out;
+    if (is_signed) {
+        a = max(a, -127); b = max(b, -127); c = max(c, -127); d = max(d, -127);
+        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
+        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(b), "r"(a), "r"(hi));
+    } else {
+        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
+        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(b), "r"(a), "r"(hi));
+    }
+    return out;
+}
+
 // Epilogue parameters, identical for every producing kernel (see f8_op in f8b200.h).
 struct Epilogue {
     const int32_t *bias;      // [cout_pad]
@@ -61,6 +93,99 @@ __device__ __forceinline__ int32_t residual_relu(int32_t v, bool has_carry, int3
     }
     if (relu) v = max(v, 0);
     return v;
+}
+
+// streaming 16-byte load of a residual carry (read once: keep it out of L1)
+__device__ __forceinline__ int4 ld_stream_int4(const int32_t *p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// The fused epilogue for 16 consecutive output channels of ONE output pixel held by one
+// thread (tcgen05 kernels: TMEM lane = pixel).  v: raw accumulators; bias16: 16 ints (shared
+// memory); o = pixel * cout_pad + first channel; gc = first channel.
+__device__ __forceinline__ void epilogue16(int32_t (&v)[16], const int32_t *bias16,
+                                           const Epilogue &ep, size_t o, int gc, size_t pixel) {
+    const bool has_carry = ep.carry_in != nullptr;
+#pragma unroll
+    for (int q = 0; q < 16; q += 4) {
+        const int4 b = *reinterpret_cast<const int4 *>(bias16 + q);
+        v[q + 0] = (int32_t)((uint32_t)v[q + 0] + (uint32_t)b.x);
+        v[q + 1] = (int32_t)((uint32_t)v[q + 1] + (uint32_t)b.y);
+        v[q + 2] = (int32_t)((uint32_t)v[q + 2] + (uint32_t)b.z);
+        v[q + 3] = (int32_t)((uint32_t)v[q + 3] + (uint32_t)b.w);
+        if (has_carry) {
+            const int4 c = ld_stream_int4(ep.carry_in + o + q);
+            v[q + 0] = residual_relu(v[q + 0], true, c.x, ep.carry_shift, ep.relu);
+            v[q + 1] = residual_relu(v[q + 1], true, c.y, ep.carry_shift, ep.relu);
+            v[q + 2] = residual_relu(v[q + 2], true, c.z, ep.carry_shift, ep.relu);
+            v[q + 3] = residual_relu(v[q + 3], true, c.w, ep.carry_shift, ep.relu);
+        } else if (ep.relu) {
+            v[q + 0] = max(v[q + 0], 0); v[q + 1] = max(v[q + 1], 0);
+            v[q + 2] = max(v[q + 2], 0); v[q + 3] = max(v[q + 3], 0);
+        }
+        if (ep.carry_out)
+            *reinterpret_cast<int4 *>(ep.carry_out + o + q) =
+                make_int4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+    }
+    if (ep.out0) {
+        uint4 w;
+        w.x = requant_pack4(v[0], v[1], v[2], v[3], ep.shift0, ep.signed0);
+        w.y = requant_pack4(v[4], v[5], v[6], v[7], ep.shift0, ep.signed0);
+        w.z = requant_pack4(v[8], v[9], v[10], v[11], ep.shift0, ep.signed0);
+        w.w = requant_pack4(v[12], v[13], v[14], v[15], ep.shift0, ep.signed0);
+        *reinterpret_cast<uint4 *>(ep.out0 + o) = w;
+    }
+    if (ep.out1) {
+        uint4 w;
+        w.x = requant_pack4(v[0], v[1], v[2], v[3], ep.shift1, ep.signed1);
+        w.y = requant_pack4(v[4], v[5], v[6], v[7], ep.shift1, ep.signed1);
+        w.z = requant_pack4(v[8], v[9], v[10], v[11], ep.shift1, ep.signed1);
+        w.w = requant_pack4(v[12], v[13], v[14], v[15], ep.shift1, ep.signed1);
+        *reinterpret_cast<uint4 *>(ep.out1 + o) = w;
+    }
+    if (ep.out_f32) {
+        float *f = ep.out_f32 + pixel * ep.out_f32_ld + gc;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (gc + i < ep.cout) f[i] = (float)v[i];
+    }
+}
+
+// Fast path of the same epilogue for the most common launch: no residual, no int32 carry
+// out, ONE unsigned 8-bit consumer reached by a right shift (n > 0).  ReLU is then absorbed
+// by the unsigned clamp (requant(relu(v)) == requant(v) for n > 0, SURVEY.md "exactness
+// traps"), and bias + 2^(n-1) is one pre-merged addend (wrapping adds associate), so an
+// element costs add, tie test, shift, tie mask and half a saturating pack.
+// bh16: 16 ints in shared memory holding bias + half.
+__host__ __device__ inline bool epilogue_is_plain_u8(const Epilogue &ep) {
+    return ep.carry_in == nullptr && ep.carry_out == nullptr && ep.out1 == nullptr &&
+           ep.out_f32 == nullptr && ep.out0 != nullptr && ep.shift0 > 0 && !ep.signed0;
+}
+__device__ __forceinline__ void epilogue16_plain_u8(const int32_t (&v)[16], const int32_t *bh16,
+                                                    uint8_t *dst, int n) {
+    const uint32_t mask = (1u << n) - 1u;
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int4 b = *reinterpret_cast<const int4 *>(bh16 + 4 * q);
+        int32_t r[4];
+        const uint32_t t0 = (uint32_t)v[4 * q + 0] + (uint32_t)b.x;
+        const uint32_t t1 = (uint32_t)v[4 * q + 1] + (uint32_t)b.y;
+        const uint32_t t2 = (uint32_t)v[4 * q + 2] + (uint32_t)b.z;
+        const uint32_t t3 = (uint32_t)v[4 * q + 3] + (uint32_t)b.w;
+        r[0] = (int32_t)t0 >> n; if ((t0 & mask) == 0u) r[0] &= ~1;
+        r[1] = (int32_t)t1 >> n; if ((t1 & mask) == 0u) r[1] &= ~1;
+        r[2] = (int32_t)t2 >> n; if ((t2 & mask) == 0u) r[2] &= ~1;
+        r[3] = (int32_t)t3 >> n; if ((t3 & mask) == 0u) r[3] &= ~1;
+        uint32_t hi;
+        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(r[3]), "r"(r[2]), "r"(0));
+        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w[q]) : "r"(r[1]), "r"(r[0]), "r"(hi));
+    }
+    *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // float32 -> int32 as the reference's x86 CPU path does (.int()): truncate, and the x86
