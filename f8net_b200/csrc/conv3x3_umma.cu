@@ -46,13 +46,11 @@ __host__ __device__ constexpr int mb_for(int bn) { return 256 / bn; }
 __host__ __device__ constexpr int sb_for(int bn) { return bn == 64 ? 12 : 8; }   // weight-tile ring
 constexpr int SA = 3;                  // patch ring (one stage = 64 channels of the patch)
 constexpr int A_LAG = 1;               // a stage is signalled once A_LAG younger stages are issued
-constexpr int EPI_WARPS = 16;          // warp w: TMEM lane group w % 4, 16-column slice w / 4
-constexpr int EPI_THREADS = EPI_WARPS * 32;
+// epilogue warps: warp w reads TMEM lane group w % 4, column slice w / 4.  The plain-u8
+// epilogue is instruction-bound (16 warps); the generic one (residual carries) is bound by
+// memory latency and needs registers for its carry prefetch instead (8 warps).
+__host__ __device__ constexpr int epi_warps_for(bool plain) { return plain ? 16 : 8; }
 constexpr int LOADERS = 128;
-constexpr int LOADER_WARP0 = EPI_WARPS;
-constexpr int MMA_WARP = EPI_WARPS + 4;
-constexpr int WLOAD_WARP = EPI_WARPS + 5;
-constexpr int THREADS = (EPI_WARPS + 6) * 32;
 constexpr int MAX_SLOT_ITERS = 6;      // ceil((TM + 2*PW + 2) / 128) for TM = 512, PW <= 120
 
 struct PGeom {
@@ -81,14 +79,19 @@ struct PGeom {
     } while (0)
 
 template <int BN, bool A_SIGNED, bool PLAIN_U8>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__((epi_warps_for(PLAIN_U8) + 6) * 32, 1)
 conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
     extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int EPI_WARPS = epi_warps_for(PLAIN_U8);
+    constexpr int EPI_THREADS = EPI_WARPS * 32;
+    constexpr int LOADER_WARP0 = EPI_WARPS;
+    constexpr int MMA_WARP = EPI_WARPS + 4;
+    constexpr int WLOAD_WARP = EPI_WARPS + 5;
     constexpr int MB = mb_for(BN);
     constexpr int TM = 128 * MB;
     constexpr int SB = sb_for(BN);
     constexpr int B_TILE = BN * 64;
-    constexpr int CW = BN / 4;                             // columns per epilogue warp slice
+    constexpr int CW = BN / (EPI_WARPS / 4);               // columns per epilogue warp slice
     const int a_stage = g.slots_pad * 64;                 // bytes of one patch stage
     const uint32_t lbo_a = (uint32_t)g.slots_pad * 16;
     const uint32_t smem_base = f8::smem_u32(smem);
@@ -294,30 +297,80 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
                 bias_s[tid] = b;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-            F8_TIMED_WAIT(w_full, mbar_wait(acc_full(buf), acc_phase));
-            tc_fence_after();
-            if (cw0 < ncols) {
-                for (int i = 0; i < MB; ++i) {
+            if (PLAIN_U8) {
+                F8_TIMED_WAIT(w_full, mbar_wait(acc_full(buf), acc_phase));
+                tc_fence_after();
+                if (cw0 < ncols) {
+#pragma unroll
+                    for (int i = 0; i < MB; ++i) {
+                        const int m = st * TM + i * 128 + row;
+                        const int Yo = m / g.PW;
+                        const int xo = m - Yo * g.PW;
+                        const int img = Yo / HP;
+                        const int y = Yo - img * HP;
+                        const bool valid = xo < g.W && y < g.H && img < g.N;
+                        const size_t opix = ((size_t)(img * g.H + y) * g.W + xo);
+                        const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) +
+                                              (uint32_t)((buf * MB + i) * BN);
+#pragma unroll
+                        for (int c0 = cw0; c0 < cw0 + CW; c0 += 16) {
+                            if (c0 < ncols) {
+                                int32_t v[16];
+                                tmem_ld16(trow + (uint32_t)c0, v);
+                                tmem_ld_wait();
+                                if (valid)
+                                    f8::epilogue16_plain_u8(v, bias_s + c0,
+                                                            ep.out0 + opix * ep.cout_pad + n0 + c0, ep.shift0);
+                            }
+                        }
+                    }
+                }
+            } else {
+                // units of 32 columns; the residual carry of unit u+1 is requested while unit u
+                // is computed, and unit 0's before the accumulator is even complete
+                constexpr int UPS = CW / 32;                 // units per segment
+                constexpr int UNITS = MB * UPS;
+                const bool has_carry = ep.carry_in != nullptr;
+                int4 cb[2][8];
+                auto unit = [&](int u, bool &valid, size_t &opix, uint32_t &trow, int &c0) {
+                    const int i = u / UPS;
+                    c0 = cw0 + (u - i * UPS) * 32;
                     const int m = st * TM + i * 128 + row;
                     const int Yo = m / g.PW;
                     const int xo = m - Yo * g.PW;
                     const int img = Yo / HP;
                     const int y = Yo - img * HP;
-                    const bool valid = xo < g.W && y < g.H && img < g.N;
-                    const size_t opix = ((size_t)(img * g.H + y) * g.W + xo);
-                    const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) +
-                                          (uint32_t)((buf * MB + i) * BN);
+                    valid = xo < g.W && y < g.H && img < g.N && c0 < ncols;
+                    opix = ((size_t)(img * g.H + y) * g.W + xo);
+                    trow = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((buf * MB + i) * BN);
+                };
+                auto prefetch = [&](int u, int4 (&dst)[8]) {
+                    bool valid; size_t opix; uint32_t trow; int c0;
+                    unit(u, valid, opix, trow, c0);
+                    if (has_carry && valid) {
+                        const int32_t *src = ep.carry_in + opix * ep.cout_pad + n0 + c0;
 #pragma unroll
-                    for (int c0 = cw0; c0 < cw0 + CW; c0 += 16) {
-                        if (c0 < ncols) {
+                        for (int q = 0; q < 8; ++q) dst[q] = f8::ld_carry_int4(src + 4 * q);
+                    }
+                };
+                prefetch(0, cb[0]);
+                F8_TIMED_WAIT(w_full, mbar_wait(acc_full(buf), acc_phase));
+                tc_fence_after();
+#pragma unroll
+                for (int u = 0; u < UNITS; ++u) {
+                    if (u + 1 < UNITS) prefetch(u + 1, cb[(u + 1) & 1]);
+                    bool valid; size_t opix; uint32_t trow; int c0;
+                    unit(u, valid, opix, trow, c0);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (c0 + 16 * h < ncols) {          // warp-uniform
                             int32_t v[16];
-                            tmem_ld16(trow + (uint32_t)c0, v);
+                            tmem_ld16(trow + (uint32_t)(c0 + 16 * h), v);
                             tmem_ld_wait();
-                            if (valid) {
-                                const size_t o = opix * ep.cout_pad + n0 + c0;
-                                if (PLAIN_U8) f8::epilogue16_plain_u8(v, bias_s + c0, ep.out0 + o, ep.shift0);
-                                else f8::epilogue16(v, bias_s + c0, ep, o, n0 + c0, opix);
-                            }
+                            if (valid)
+                                f8::epilogue16_t<true>(v, bias_s + c0 + 16 * h, ep,
+                                                       opix * ep.cout_pad + n0 + c0 + 16 * h,
+                                                       n0 + c0 + 16 * h, opix, &cb[u & 1][4 * h]);
                         }
                     }
                 }
@@ -410,11 +463,11 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     const bool plain = f8::epilogue_is_plain_u8(ep);
     const unsigned gr = (unsigned)grid;
     if (a.in_signed) {
-        if (plain) conv3x3_umma_kernel<BN, true, true><<<gr, THREADS, smem_launch, s>>>(g, ep);
-        else conv3x3_umma_kernel<BN, true, false><<<gr, THREADS, smem_launch, s>>>(g, ep);
+        if (plain) conv3x3_umma_kernel<BN, true, true><<<gr, (epi_warps_for(true) + 6) * 32, smem_launch, s>>>(g, ep);
+        else conv3x3_umma_kernel<BN, true, false><<<gr, (epi_warps_for(false) + 6) * 32, smem_launch, s>>>(g, ep);
     } else {
-        if (plain) conv3x3_umma_kernel<BN, false, true><<<gr, THREADS, smem_launch, s>>>(g, ep);
-        else conv3x3_umma_kernel<BN, false, false><<<gr, THREADS, smem_launch, s>>>(g, ep);
+        if (plain) conv3x3_umma_kernel<BN, false, true><<<gr, (epi_warps_for(true) + 6) * 32, smem_launch, s>>>(g, ep);
+        else conv3x3_umma_kernel<BN, false, false><<<gr, (epi_warps_for(false) + 6) * 32, smem_launch, s>>>(g, ep);
     }
     F8_CUDA(cudaGetLastError());
     if (want_stats) {

@@ -104,11 +104,20 @@ __device__ __forceinline__ int4 ld_stream_int4(const int32_t *p) {
     return r;
 }
 
+// 16-byte read-only load of a residual carry through L1 (adjacent 16-byte pieces of a sector
+// are requested by the same thread back to back)
+__device__ __forceinline__ int4 ld_carry_int4(const int32_t *p) {
+    return __ldg(reinterpret_cast<const int4 *>(p));
+}
+
 // The fused epilogue for 16 consecutive output channels of ONE output pixel held by one
 // thread (tcgen05 kernels: TMEM lane = pixel).  v: raw accumulators; bias16: 16 ints (shared
-// memory); o = pixel * cout_pad + first channel; gc = first channel.
-__device__ __forceinline__ void epilogue16(int32_t (&v)[16], const int32_t *bias16,
-                                           const Epilogue &ep, size_t o, int gc, size_t pixel) {
+// memory); o = pixel * cout_pad + first channel; gc = first channel.  carry16: the 16 residual
+// carry values, loaded by the caller ahead of time (software prefetch) when PRELOADED.
+template <bool PRELOADED>
+__device__ __forceinline__ void epilogue16_t(int32_t (&v)[16], const int32_t *bias16,
+                                             const Epilogue &ep, size_t o, int gc, size_t pixel,
+                                             const int4 *carry16) {
     const bool has_carry = ep.carry_in != nullptr;
 #pragma unroll
     for (int q = 0; q < 16; q += 4) {
@@ -118,7 +127,9 @@ __device__ __forceinline__ void epilogue16(int32_t (&v)[16], const int32_t *bias
         v[q + 2] = (int32_t)((uint32_t)v[q + 2] + (uint32_t)b.z);
         v[q + 3] = (int32_t)((uint32_t)v[q + 3] + (uint32_t)b.w);
         if (has_carry) {
-            const int4 c = ld_stream_int4(ep.carry_in + o + q);
+            int4 c;
+            if (PRELOADED) c = carry16[q >> 2];
+            else c = ld_stream_int4(ep.carry_in + o + q);
             v[q + 0] = residual_relu(v[q + 0], true, c.x, ep.carry_shift, ep.relu);
             v[q + 1] = residual_relu(v[q + 1], true, c.y, ep.carry_shift, ep.relu);
             v[q + 2] = residual_relu(v[q + 2], true, c.z, ep.carry_shift, ep.relu);
@@ -153,6 +164,10 @@ __device__ __forceinline__ void epilogue16(int32_t (&v)[16], const int32_t *bias
         for (int i = 0; i < 16; ++i)
             if (gc + i < ep.cout) f[i] = (float)v[i];
     }
+}
+__device__ __forceinline__ void epilogue16(int32_t (&v)[16], const int32_t *bias16,
+                                           const Epilogue &ep, size_t o, int gc, size_t pixel) {
+    epilogue16_t<false>(v, bias16, ep, o, gc, pixel, nullptr);
 }
 
 // Fast path of the same epilogue for the most common launch: no residual, no int32 carry
