@@ -343,7 +343,7 @@ def gpu_arm(args):
         d = fam[dom_kind]
         kind_names = {C.F8_OP_CONVERT_INPUT: "convert_input", C.F8_OP_CONV_DENSE: "conv_dense",
                       C.F8_OP_CONV_DW: "conv_dw3x3", C.F8_OP_MAXPOOL: "maxpool",
-                      C.F8_OP_POOL_REQUANT: "pool_requant"}
+                      C.F8_OP_POOL_REQUANT: "pool_requant", C.F8_OP_HEAD_POOL: "head_conv_pool"}
         achieved = d["bytes"] / (d["ms"] / 1e3) / 1e9 if d["ms"] > 0 else 0.0
         roofline = {
             "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

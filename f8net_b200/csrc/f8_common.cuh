@@ -233,6 +233,7 @@ namespace f8host {
 int launch_conv_mma(const f8_conv_args &a, cudaStream_t s);
 int launch_conv_umma(const f8_conv_args &a, cudaStream_t s);
 int launch_conv3x3_umma(const f8_conv_args &a, cudaStream_t s);
+int launch_head_pool(const f8_conv_args &a, cudaStream_t s);
 int launch_dw3x3(const f8_conv_args &a, cudaStream_t s);
 int launch_maxpool(const f8_conv_args &a, cudaStream_t s);
 int launch_pool_requant(const f8_conv_args &a, cudaStream_t s);

@@ -184,14 +184,15 @@ extern "C" int f8_plan_create(const f8_model_desc *desc, int device, f8_plan **o
         if (!rc) rc = check_shift(o.carry_shift, "residual");
         if (!rc) rc = check_shift(o.out_shift[0], "requant");
         if (!rc) rc = check_shift(o.out_shift[1], "requant");
-        if (!rc && (o.kind == F8_OP_CONV_DENSE || o.kind == F8_OP_CONV_DW)) {
+        if (!rc && (o.kind == F8_OP_CONV_DENSE || o.kind == F8_OP_CONV_DW || o.kind == F8_OP_HEAD_POOL)) {
             if (!o.weight || !o.bias) {
                 set_error("plan_create: op %d has no weight / bias", i);
                 rc = F8_ERR_ARG;
             } else {
                 po.w_off = blob;
-                blob += align_up(f8_pack_weights_bytes(o.kind, o.cin, o.cout, o.cin_pad,
-                                                       o.cout_pad, o.kh, o.kw), kAlign);
+                blob += align_up(f8_pack_weights_bytes(o.kind == F8_OP_HEAD_POOL ? F8_OP_CONV_DENSE : o.kind,
+                                                       o.cin, o.cout, o.cin_pad, o.cout_pad, o.kh, o.kw),
+                                 kAlign);
                 po.b_off = blob;
                 blob += align_up((size_t)o.cout_pad * sizeof(int32_t), kAlign);
             }
@@ -209,9 +210,9 @@ extern "C" int f8_plan_create(const f8_model_desc *desc, int device, f8_plan **o
     std::vector<uint8_t> host(blob ? blob : 1, 0);
     for (PlanOp &po : p->ops) {
         const f8_op &o = po.op;
-        if (o.kind != F8_OP_CONV_DENSE && o.kind != F8_OP_CONV_DW) continue;
-        int rc = f8_pack_weights(o.kind, o.weight, o.cin, o.cout, o.cin_pad, o.cout_pad, o.kh,
-                                 o.kw, host.data() + po.w_off);
+        if (o.kind != F8_OP_CONV_DENSE && o.kind != F8_OP_CONV_DW && o.kind != F8_OP_HEAD_POOL) continue;
+        int rc = f8_pack_weights(o.kind == F8_OP_HEAD_POOL ? F8_OP_CONV_DENSE : o.kind, o.weight, o.cin,
+                                 o.cout, o.cin_pad, o.cout_pad, o.kh, o.kw, host.data() + po.w_off);
         if (rc) { delete p; return rc; }
         std::memcpy(host.data() + po.b_off, o.bias, (size_t)o.cout * sizeof(int32_t));
         po.op.weight = nullptr;   // host pointers are not kept: the caller owns them
@@ -300,6 +301,16 @@ static int run_op(const f8_plan *p, const PlanOp &po, int n, const uint8_t *x, b
         case F8_OP_CONV_DW: return f8host::launch_dw3x3(a, s);
         case F8_OP_MAXPOOL: return f8host::launch_maxpool(a, s);
         case F8_OP_POOL_REQUANT: return f8host::launch_pool_requant(a, s);
+        case F8_OP_HEAD_POOL: {
+            if (p->backend != 1) {
+                set_error("plan_run: the plan fuses head conv + max-pool (tcgen05 backend); rebuild it "
+                          "for backend %d", p->backend);
+                return F8_ERR_UNSUPPORTED;
+            }
+            int rc = f8host::launch_head_pool(a, s);
+            if (rc == F8_ERR_UNSUPPORTED) set_error("plan_run: fused head geometry not supported");
+            return rc;
+        }
         default: set_error("plan_run: unknown op kind %d", o.kind); return F8_ERR_ARG;
     }
 }
@@ -463,6 +474,15 @@ extern "C" int f8_maxpool3x3s2(const f8_conv_args *a, void *stream) {
     return f8host::launch_maxpool(*a, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int f8_head_pool(const f8_conv_args *a, void *stream) {
+    int rc = check_args(a, "head_pool");
+    if (rc) return rc;
+    if (!a->wpack || !a->bias) { set_error("head_pool: no weights / bias"); return F8_ERR_ARG; }
+    rc = f8host::launch_head_pool(*a, static_cast<cudaStream_t>(stream));
+    if (rc == F8_ERR_UNSUPPORTED) set_error("head_pool: only the 224x224 7x7 s2 p3 3->64 head on sm_100");
+    return rc;
+}
+
 extern "C" int f8_pool_requant(const f8_conv_args *a, void *stream) {
     int rc = check_args(a, "pool_requant");
     if (rc) return rc;
@@ -505,5 +525,6 @@ extern "C" int f8_has_umma(int device) {
 namespace f8host {
 int launch_conv_umma(const f8_conv_args &, cudaStream_t) { return F8_ERR_UNSUPPORTED; }
 int launch_conv3x3_umma(const f8_conv_args &, cudaStream_t) { return F8_ERR_UNSUPPORTED; }
+int launch_head_pool(const f8_conv_args &, cudaStream_t) { return F8_ERR_UNSUPPORTED; }
 }  // namespace f8host
 #endif

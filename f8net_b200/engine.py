@@ -57,7 +57,10 @@ class Engine:
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None
                                    else torch.device(device).index or 0)
         self.net = net
-        self.plan: Plan = build_plan(net, _to_numpy_sd(state_dict))
+        if backend is None:
+            backend = 1 if self.lib.f8_has_umma(self.device.index) else 0
+        # the fused head conv + max-pool launch exists on the tcgen05 backend only
+        self.plan: Plan = build_plan(net, _to_numpy_sd(state_dict), fuse_head=(int(backend) == 1))
         self.chunk = int(chunk)
         desc, keep = self.plan.to_desc()
         handle = ctypes.c_void_p()
@@ -66,8 +69,6 @@ class Engine:
                                             ctypes.byref(handle)))
         del keep
         self._h = handle
-        if backend is None:
-            backend = 1 if self.lib.f8_has_umma(self.device.index) else 0
         self.set_backend(backend)
         self._ws = None
         self._stage = None

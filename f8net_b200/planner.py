@@ -216,9 +216,10 @@ def _out_hw(h, k, s, p):
     return (h + 2 * p - k) // s + 1
 
 
-def build_plan(net: NetSpec, sd: Dict[str, np.ndarray]) -> Plan:
+def build_plan(net: NetSpec, sd: Dict[str, np.ndarray], fuse_head: bool = False) -> Plan:
     """Lower the integer graph to fused launches.  ``sd`` maps the reference state_dict keys
-    to integer arrays (numpy or anything np.asarray accepts)."""
+    to integer arrays (numpy or anything np.asarray accepts).  ``fuse_head``: emit the ResNet
+    head conv + ReLU + max-pool as one F8_OP_HEAD_POOL launch (tcgen05 backend)."""
     P = Plan(net)
     S = net.image_size
 
@@ -246,15 +247,25 @@ def build_plan(net: NetSpec, sd: Dict[str, np.ndarray]) -> Plan:
     conv_in.outs.append((x8, 0, int(net.head.sym)))
     head = conv_op(net.head, conv_in, 0, True, S, requant=False)
     head.in_buf = x8
-    P.emit(head)
-    cur, fa, hw = head, head.fa, head.hout
-    if net.maxpool:
-        # x = self.head[-1](x.float()).int(), fix_resnet.py:358-359
-        mp = Op(C.F8_OP_MAXPOOL, "head.maxpool", cin=cur.cout, cout=cur.cout,
-                cin_pad=cur.cout_pad, cout_pad=cur.cout_pad, k=3, stride=2, pad=1, hin=hw, win=hw,
-                hout=_out_hw(hw, 3, 2, 1), wout=_out_hw(hw, 3, 2, 1), in_buf=P.carry(cur), fa=fa)
-        P.emit(mp)
-        cur, hw = mp, mp.hout
+    fused = (fuse_head and net.maxpool and S == 224 and net.head.k == 7 and net.head.stride == 2
+             and net.head.pad == 3 and net.head.cin == 3 and net.head.cout == 64)
+    if fused:
+        # x = self.head[:-1](x); x = self.head[-1](x.float()).int()  (fix_resnet.py:355-362)
+        head.kind = C.F8_OP_HEAD_POOL
+        head.name = "head.0+maxpool"
+        head.hout = head.wout = _out_hw(head.hout, 3, 2, 1)
+        P.emit(head)
+        cur, fa, hw = head, head.fa, head.hout
+    else:
+        P.emit(head)
+        cur, fa, hw = head, head.fa, head.hout
+        if net.maxpool:
+            # x = self.head[-1](x.float()).int(), fix_resnet.py:358-359
+            mp = Op(C.F8_OP_MAXPOOL, "head.maxpool", cin=cur.cout, cout=cur.cout,
+                    cin_pad=cur.cout_pad, cout_pad=cur.cout_pad, k=3, stride=2, pad=1, hin=hw, win=hw,
+                    hout=_out_hw(hw, 3, 2, 1), wout=_out_hw(hw, 3, 2, 1), in_buf=P.carry(cur), fa=fa)
+            P.emit(mp)
+            cur, hw = mp, mp.hout
 
     # ---- blocks ----
     for blk in net.blocks:

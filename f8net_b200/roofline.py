@@ -58,7 +58,12 @@ def op_work(plan):
     for op in plan.ops:
         el_in = op.hin * op.win * op.cin
         el_out = op.hout * op.wout * op.cout
-        if op.kind == C.F8_OP_CONV_DENSE:
+        if op.kind == C.F8_OP_HEAD_POOL:
+            # conv at the un-pooled resolution; only the pooled tensor is written
+            hc = _hw(op.hin, op.k, op.stride, op.pad)
+            macs = hc * hc * op.cout * op.cin * op.k * op.k
+            wb = op.cout * op.cin * op.k * op.k
+        elif op.kind == C.F8_OP_CONV_DENSE:
             macs = el_out * op.cin * op.k * op.k
             wb = op.cout * op.cin * op.k * op.k
         elif op.kind == C.F8_OP_CONV_DW:
@@ -67,7 +72,10 @@ def op_work(plan):
         else:
             macs = wb = 0
         b = 0
-        if op.kind in (C.F8_OP_CONV_DENSE, C.F8_OP_CONV_DW):
+        if op.kind == C.F8_OP_HEAD_POOL:
+            hc = _hw(op.hin, op.k, op.stride, op.pad)
+            b = el_in + hc * hc * op.cout       # SURVEY definition: conv in + conv out, pool excluded
+        elif op.kind in (C.F8_OP_CONV_DENSE, C.F8_OP_CONV_DW):
             b = el_in + el_out
             if op.carry_in_buf >= 0:
                 b += 4 * el_out

@@ -57,7 +57,9 @@ typedef enum f8_op_kind {
     F8_OP_CONV_DENSE = 1,     /* groups == 1 conv or nn.Linear, tensor cores, fused epilogue    */
     F8_OP_CONV_DW = 2,        /* depthwise 3x3, CUDA-core int MAC, fused epilogue               */
     F8_OP_MAXPOOL = 3,        /* ResNet head 3x3 s2 p1 max-pool with float32 round trip         */
-    F8_OP_POOL_REQUANT = 4    /* FXQAvgPool2d sum over HxW + requant for the classifier         */
+    F8_OP_POOL_REQUANT = 4,   /* FXQAvgPool2d sum over HxW + requant for the classifier         */
+    F8_OP_HEAD_POOL = 5       /* ResNet head fused: 7x7 s2 conv + ReLU + float round trip +
+                                 3x3 s2 max-pool (tcgen05 backend only); hout/wout = pooled size  */
 } f8_op_kind;
 
 /*
@@ -202,6 +204,11 @@ F8_API int f8_conv_dense(const f8_conv_args *a, int backend, void *stream);
 F8_API int f8_conv_dw3x3(const f8_conv_args *a, void *stream);
 /* Replaces: self.head[-1](x.float()).int()  (fix_resnet.py:358-359). in = int32 NHWC. */
 F8_API int f8_maxpool3x3s2(const f8_conv_args *a, void *stream);
+/* Replaces: x = self.head[:-1](x); x = self.head[-1](x.float()).int() in one launch
+ * (fix_resnet.py:355-362): 7x7 s2 p3 conv of the NHWC4 image + bias + ReLU + float32 round trip
+ * + 3x3 s2 p1 max-pool + consumer requant(s) / int32 carry.  a->hout/wout = 56 (pooled);
+ * sm_100 only; F8_ERR_UNSUPPORTED for any other geometry. */
+F8_API int f8_head_pool(const f8_conv_args *a, void *stream);
 /* Replaces: FXQAvgPool2d.forward int branch + int_op_only_fix_quant for the classifier
  * (fix_quant_ops.py:126-134, fix_resnet.py:367-374). in = int32 NHWC [n,h,w,c_pad],
  * out[0] = 8-bit [n,c_pad]. */

@@ -8,7 +8,7 @@ import torch
 from f8net_b200 import _capi as C
 from oracle import oracle as O
 
-from util import cpad, nchw_to_nhwc8, nchw_to_nhwc32, nhwc_to_nchw
+from util import cpad, nchw_to_nhwc8, nchw_to_nhwc32, nhwc_to_nchw  # noqa: F401 (re-exported)
 
 DEV = "cuda:0"
 

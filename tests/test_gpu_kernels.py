@@ -200,6 +200,45 @@ def test_maxpool_float_round_trip(G, f8lib):
     assert np.array_equal(nhwc_to_nchw(q0.cpu().numpy(), c), O.requant(want, 0, 15, False))
 
 
+@pytest.mark.parametrize("signed", [False, True])
+def test_head_conv_pool_fused(G, f8lib, signed):
+    """x = head[:-1](x); x = head[-1](x.float()).int() in one launch (fix_resnet.py:355-362),
+    incl. accumulators above 2^24 (float rounding) and at INT_MAX (x86 .int() indefinite)."""
+    if not f8lib.f8_has_umma(0):
+        pytest.skip("tcgen05 backend not available")
+    rng = np.random.default_rng(21 + signed)
+    n = 3
+    lo, hi, w, b = _rand_layer(rng, 3, 64, 7, signed)
+    b[5] = 2 ** 24 + 12345          # every value of the channel needs float32 rounding
+    b[9] = 2 ** 31 - 1000           # float(x) == 2^31 for most pixels -> INT_MIN after .int()
+    b[11] = -2 ** 31 + 5
+    x = rng.integers(lo, hi, (n, 3, 224, 224)).astype(np.int32)
+    acc = O.relu(O.conv2d(x, w, b, 2, 3, 1))
+    pooled = O.maxpool_float_rt(acc, 3, 2, 1)
+    outs = ((14, False), (13, True))
+    want_q = [O.requant(pooled, 0, s, g) for s, g in outs]
+    xd = G.dev(G.nchw_to_nhwc8(x, 4, signed))
+    wd = G.dev(G.pack(f8lib, C.F8_OP_CONV_DENSE, w, 4, 64))
+    bd = G.dev(b)
+    a = C.f8_conv_args()
+    a.n, a.cin, a.cout, a.cin_pad, a.cout_pad = n, 3, 64, 4, 64
+    a.kh, a.kw, a.stride, a.pad = 7, 7, 2, 3
+    a.hin, a.win, a.hout, a.wout = 224, 224, 56, 56
+    a.in_signed = int(signed)
+    a.in_, a.wpack, a.bias = xd.data_ptr(), wd.data_ptr(), bd.data_ptr()
+    co = torch.full((n, 56, 56, 64), -7, dtype=torch.int32, device="cuda:0")
+    q = [torch.full((n, 56, 56, 64), 0x77, dtype=torch.uint8, device="cuda:0") for _ in outs]
+    a.carry_out = co.data_ptr()
+    for j, (s_, g_) in enumerate(outs):
+        a.out[j] = q[j].data_ptr()
+        a.out_shift[j], a.out_signed[j] = s_, int(g_)
+    C.check(f8lib.f8_head_pool(ctypes.byref(a), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert np.array_equal(nhwc_to_nchw(co.cpu().numpy(), 64), pooled)
+    assert np.array_equal(nhwc_to_nchw(q[0].cpu().numpy(), 64), want_q[0])
+    assert np.array_equal(nhwc_to_nchw(q[1].cpu().numpy().view(np.int8), 64), want_q[1])
+
+
 def test_pool_requant(G, f8lib):
     """FXQAvgPool2d int branch + classifier requant (fix_quant_ops.py:126-134)."""
     rng = np.random.default_rng(9)
