@@ -21,6 +21,9 @@
 //             staging tile; then each of 224 threads max-pools one pooled pixel (float bit
 //             patterns of non-negative floats order like integers), converts back with the
 //             x86 cvttss2si semantics of .int(), and writes carry / 8-bit images.
+#include <cstdio>
+#include <cstdlib>
+
 #include "umma_common.cuh"
 
 namespace {
@@ -61,8 +64,19 @@ struct HGeom {
     const uint8_t *wpack;   // [16][wrows][16]
     int wrows;
     int N;
-    int wrows_bytes;
+    long long *stats;       // debug (F8_STATS=1)
 };
+
+#define F8_TIMED(acc, stmt)                      \
+    do {                                         \
+        if (g.stats) {                           \
+            const long long _t0 = clock64();     \
+            stmt;                                \
+            acc += clock64() - _t0;              \
+        } else {                                 \
+            stmt;                                \
+        }                                        \
+    } while (0)
 
 __device__ __forceinline__ uint32_t stage_off(int m, int chunk) {
     // 64-byte record per conv pixel, 16-byte chunks XOR-swizzled so that both the per-pixel
@@ -140,14 +154,15 @@ head_pool_kernel(const HGeom g, const f8::Epilogue ep) {
             cp_async_commit();
         };
         int slot = 0, phase = 0, pbuf = 0;
+        long long w_patch = 0, w_aempty = 0;
+        const long long t_begin = clock64();
         if ((int)blockIdx.x < total_tiles) load_patch(blockIdx.x, 0);
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            cp_async_wait<0>();
-            asm volatile("bar.sync 2, %0;" ::"n"(BUILDERS) : "memory");   // whole patch visible
+            F8_TIMED(w_patch, cp_async_wait<0>(); asm volatile("bar.sync 2, %0;" ::"n"(BUILDERS) : "memory"));   // whole patch visible
             if (t + (int)gridDim.x < total_tiles) load_patch(t + gridDim.x, pbuf ^ 1);
             const uint8_t *patch = smem + OFF_PATCH + pbuf * ((PATCH_BYTES + 127) / 128 * 128);
             for (int s = 0; s < SEGS; ++s) {
-                mbar_wait(a_empty(slot), phase ^ 1);
+                F8_TIMED(w_aempty, mbar_wait(a_empty(slot), phase ^ 1));
                 uint8_t *sa = smem + OFF_A + slot * A_STAGE;
                 const int m = s * 128 + bt;
                 if (m < CPIX) {
@@ -172,6 +187,11 @@ head_pool_kernel(const HGeom g, const f8::Epilogue ep) {
             pbuf ^= 1;
         }
         cp_async_wait<0>();
+        if (g.stats && bt == 0) {
+            g.stats[blockIdx.x * 16 + 0] = clock64() - t_begin;
+            g.stats[blockIdx.x * 16 + 1] = w_patch;
+            g.stats[blockIdx.x * 16 + 2] = w_aempty;
+        }
     } else if (warp == MMA_WARP) {
         // =========================== MMA issuer ===================================
         constexpr uint32_t idesc = instr_desc(A_SIGNED, COUT);
@@ -181,11 +201,13 @@ head_pool_kernel(const HGeom g, const f8::Epilogue ep) {
         mbar_wait(w_full, 0);
         const uint32_t b_lo0 = (((smem_base + OFF_W) & 0x3ffffu) >> 4) | b_lbo;
         int slot = 0, phase = 0, tphase = 0;
+        long long w_acc = 0, w_a = 0;
+        const long long t_begin = clock64();
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            mbar_wait(acc_empty, tphase ^ 1);            // epilogue has drained the previous tile
+            F8_TIMED(w_acc, mbar_wait(acc_empty, tphase ^ 1));            // epilogue has drained the previous tile
             tc_fence_after();
             for (int s = 0; s < SEGS; ++s) {
-                mbar_wait(a_full(slot), phase);
+                F8_TIMED(w_a, mbar_wait(a_full(slot), phase));
                 tc_fence_after();
                 const uint32_t a_lo0 = (((smem_base + OFF_A + slot * A_STAGE) & 0x3ffffu) >> 4) | a_lbo;
                 if (elect_one()) {
@@ -204,18 +226,26 @@ head_pool_kernel(const HGeom g, const f8::Epilogue ep) {
             __syncwarp();
             tphase ^= 1;
         }
+        if (g.stats && lane == 0) {
+            g.stats[blockIdx.x * 16 + 3] = clock64() - t_begin;
+            g.stats[blockIdx.x * 16 + 4] = w_acc;
+            g.stats[blockIdx.x * 16 + 5] = w_a;
+        }
     } else {
         // =========================== epilogue (warps 0-7) =========================
         const int lg = warp & 3;                 // TMEM lane group
         const int shalf = warp >> 2;             // segments 4*shalf .. 4*shalf+3
         uint8_t *stage = smem + OFF_STAGE;
         int tphase = 0;
+        long long w_full = 0, t_p1 = 0, t_p2 = 0;
+        const long long t_begin = clock64();
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int img = t / tiles_per_img;
             const int pr0 = (t - img * tiles_per_img) * TP;
-            mbar_wait(acc_full, tphase);
+            F8_TIMED(w_full, mbar_wait(acc_full, tphase));
             tc_fence_after();
             for (int grp = 0; grp < 4; ++grp) {
+                const long long tp0 = g.stats ? clock64() : 0;
                 // ---- phase 1: accumulators -> relu -> float bits -> staging tile ----
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -243,6 +273,8 @@ head_pool_kernel(const HGeom g, const f8::Epilogue ep) {
                     mbar_arrive(acc_empty);          // TMEM of this tile fully read
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                const long long tp1 = g.stats ? clock64() : 0;
+                t_p1 += tp1 - tp0;
                 // ---- phase 2: 3x3 s2 p1 max-pool, .int(), carry + requantised images ----
                 if (tid < TP * POOLED) {
                     const int pr = tid / POOLED, pq = tid - pr * POOLED;
@@ -300,8 +332,15 @@ head_pool_kernel(const HGeom g, const f8::Epilogue ep) {
                     }
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                if (g.stats) t_p2 += clock64() - tp1;
             }
             tphase ^= 1;
+        }
+        if (g.stats && tid == 0) {
+            g.stats[blockIdx.x * 16 + 6] = clock64() - t_begin;
+            g.stats[blockIdx.x * 16 + 7] = w_full;
+            g.stats[blockIdx.x * 16 + 8] = t_p1;
+            g.stats[blockIdx.x * 16 + 9] = t_p2;
         }
     }
 
@@ -352,9 +391,29 @@ int launch_head_pool(const f8_conv_args &a, cudaStream_t s) {
     }
     long long grid = (long long)a.n * (POOLED / TP);
     if (grid > num_sms) grid = num_sms;
+    static const bool want_stats = getenv("F8_STATS") != nullptr;
+    static long long *stats_dev = nullptr;
+    if (want_stats) {
+        if (!stats_dev) F8_CUDA(cudaMalloc(&stats_dev, 16 * 1024 * sizeof(long long)));
+        F8_CUDA(cudaMemsetAsync(stats_dev, 0, 16 * 1024 * sizeof(long long), s));
+        g.stats = stats_dev;
+    }
     if (a.in_signed) head_pool_kernel<true><<<(unsigned)grid, THREADS, SMEM_BYTES, s>>>(g, ep);
     else head_pool_kernel<false><<<(unsigned)grid, THREADS, SMEM_BYTES, s>>>(g, ep);
     F8_CUDA(cudaGetLastError());
+    if (want_stats) {
+        static long long host[16 * 1024];
+        F8_CUDA(cudaStreamSynchronize(s));
+        F8_CUDA(cudaMemcpy(host, stats_dev, sizeof(host), cudaMemcpyDeviceToHost));
+        double acc[16] = {0};
+        for (long long b = 0; b < grid; ++b)
+            for (int k = 0; k < 16; ++k) acc[k] += (double)host[b * 16 + k] / (double)grid;
+        fprintf(stderr,
+                "[f8 stats] head_pool tiles/cta=%.1f | build total %.0f wait_patch %.0f wait_aempty %.0f | mma total "
+                "%.0f wait_acc %.0f wait_a %.0f | epi total %.0f wait_full %.0f phase1 %.0f phase2 %.0f\n",
+                (double)a.n * (POOLED / TP) / (double)grid, acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], acc[6],
+                acc[7], acc[8], acc[9]);
+    }
     return F8_OK;
 }
 
