@@ -345,9 +345,17 @@ def gpu_arm(args):
                       C.F8_OP_CONV_DW: "conv_dw3x3", C.F8_OP_MAXPOOL: "maxpool",
                       C.F8_OP_POOL_REQUANT: "pool_requant", C.F8_OP_HEAD_POOL: "head_conv_pool"}
         achieved = d["bytes"] / (d["ms"] / 1e3) / 1e9 if d["ms"] > 0 else 0.0
+        # DRAM bytes per launch of this kernel family from the committed `ncu --set full` capture
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(arch, {})
+            if tr.get("batch") == B and kind_names[dom_kind] in tr:
+                traffic = tr[kind_names[dom_kind]]["dram_bytes_per_launch"]
+        except (OSError, ValueError):
+            pass
         roofline = {
             "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-            "frac": achieved / hbm_peak, "traffic": None,
+            "frac": achieved / hbm_peak, "traffic": traffic,
             "kernel": kind_names[dom_kind], "launches_per_step": d["launches"],
             "algorithmic_bytes_per_launch": d["bytes"] / d["launches"],
             "avg_launch_ms": d["ms"] / d["launches"],

@@ -48,7 +48,7 @@ class Engine:
     """One compiled plan on one GPU.  Stateless at inference like the reference's IntModel:
     the only mutable state is scratch memory, so use one Engine per stream."""
 
-    def __init__(self, net: NetSpec, state_dict, device=None, chunk: int = 32, backend=None):
+    def __init__(self, net: NetSpec, state_dict, device=None, chunk: int = 256, backend=None):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("f8net_b200 needs a CUDA device (sm_100a); there is no CPU path")
@@ -210,7 +210,7 @@ class Engine:
 
 
 def compile(model_or_state_dict, arch: Optional[str] = None, head_signed: Optional[bool] = None,
-            device=None, chunk: int = 32, backend=None) -> Engine:
+            device=None, chunk: int = 256, backend=None) -> Engine:
     """Build an Engine from a reference ``IntModel`` (module tree walked for stride / groups /
     input_symmetric), or from its ``state_dict()`` plus the architecture name -- the
     attributes the dict lacks are then re-derived from the architecture (SURVEY.md 8(b));
