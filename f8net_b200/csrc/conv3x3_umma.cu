@@ -43,9 +43,18 @@ using namespace f8u;
 // against operand fetch from shared memory (per K=32 MMA: 4 KB of A + 4 KB of B in 64 tensor
 // cycles); BN = 64 (MB = 4) serves the 64-channel layers.
 __host__ __device__ constexpr int mb_for(int bn) { return 256 / bn; }
-__host__ __device__ constexpr int sb_for(int bn) { return bn == 64 ? 12 : 8; }   // weight-tile ring
-constexpr int SA = 3;                  // patch ring (one stage = 64 channels of the patch)
-constexpr int A_LAG = 1;               // a stage is signalled once A_LAG younger stages are issued
+// Ring depths.  The generic (residual) epilogue needs ~96 KB of warp-private staging to make its
+// int32 carry traffic coalesced, so its operand rings are shallower.
+__host__ __device__ constexpr int sb_for(int bn, bool plain) { return plain ? (bn == 64 ? 12 : 8) : 6; }
+__host__ __device__ constexpr int sa_for(bool plain) { return plain ? 3 : 2; }   // patch ring
+// a patch stage is signalled once A_LAG younger stages are issued (never the whole ring)
+__host__ __device__ constexpr int a_lag_for(bool plain) { return plain ? 1 : 0; }
+// per-warp staging of the generic epilogue: 2 carry buffers of 32 rows x (128 + 16) B and
+// 2 output buffers of 32 rows x (32 + 16) B
+constexpr int CARRY_PITCH = 144, CARRY_BUF = 32 * CARRY_PITCH;
+constexpr int OUT_PITCH = 48, OUT_BUF = 32 * OUT_PITCH;
+constexpr int WARP_SCRATCH = 2 * CARRY_BUF + 2 * OUT_BUF;
+__host__ __device__ constexpr int scratch_for(bool plain) { return plain ? 0 : 8 * WARP_SCRATCH; }
 // epilogue warps: warp w reads TMEM lane group w % 4, column slice w / 4.  The plain-u8
 // epilogue is instruction-bound (16 warps); the generic one (residual carries) is bound by
 // memory latency and needs registers for its carry prefetch instead (8 warps).
@@ -89,9 +98,11 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
     constexpr int WLOAD_WARP = EPI_WARPS + 5;
     constexpr int MB = mb_for(BN);
     constexpr int TM = 128 * MB;
-    constexpr int SB = sb_for(BN);
+    constexpr int SB = sb_for(BN, PLAIN_U8);
+    constexpr int SA = sa_for(PLAIN_U8);
+    constexpr int A_LAG = a_lag_for(PLAIN_U8);
     constexpr int B_TILE = BN * 64;
-    constexpr int CW = BN / (EPI_WARPS / 4);               // columns per epilogue warp slice
+    constexpr int CW = BN / (EPI_WARPS / 4);               // columns per epilogue warp slice (plain path)
     const int a_stage = g.slots_pad * 64;                 // bytes of one patch stage
     const uint32_t lbo_a = (uint32_t)g.slots_pad * 16;
     const uint32_t smem_base = f8::smem_u32(smem);
@@ -108,6 +119,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
     uint8_t *after = smem + SA * a_stage + SB * B_TILE + NBARS * 8;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(after);
     int32_t *sbias = reinterpret_cast<int32_t *>(after + 16);
+    uint8_t *scratch = after + 16 + 2 * BN * 4;            // generic epilogue: warp-private staging
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -153,6 +165,21 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
                     const int yy = Yp - img * HP;
                     if (xs >= 1 && yy >= 1 && img < g.N)
                         off[k] = ((long long)(img * g.H + (yy - 1)) * g.W + (xs - 1)) * g.C;
+                }
+            }
+            if (!PLAIN_U8 && ep.carry_in != nullptr) {
+                // pull the residual carry of this tile's pixels into L2 now: the epilogue reads it
+                // one to three tiles later and then pays L2, not DRAM, latency per 16-byte load
+                const int n0 = (it - st * g.ntiles_n) * BN;
+#pragma unroll
+                for (int k = 0; k < MAX_SLOT_ITERS; ++k) {
+                    if (off[k] >= 0) {
+                        const char *cp = reinterpret_cast<const char *>(
+                            ep.carry_in + (size_t)(off[k] / g.C) * ep.cout_pad + n0);
+#pragma unroll
+                        for (int b = 0; b < BN * 4; b += 128)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + b));
+                    }
                 }
             }
             for (int cg = 0; cg < ncg; ++cg) {
@@ -283,6 +310,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
         const int cw0 = (warp >> 2) * CW;              // this warp's column slice of the tile
         const int row = lg * 32 + lane;
         int buf = 0, acc_phase = 0;
+        bool epi_primed = false;
         long long w_full = 0;
         const long long t_begin = clock64();
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
@@ -326,58 +354,146 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
                     }
                 }
             } else {
-                // units of 32 columns; the residual carry of unit u+1 is requested while unit u
-                // is computed, and unit 0's before the accumulator is even complete
-                constexpr int UPS = CW / 32;                 // units per segment
-                constexpr int UNITS = MB * UPS;
+                // ---- generic epilogue: residual carries, int32 carry out, dual / signed outputs ----
+                // Warp (lg, h) owns rows [32*lg, 32*lg+32) of the units u = h, h+2 (a unit = one M
+                // segment x 64 columns) and walks them in four half-units of 32 columns.  All global
+                // traffic is staged through a warp-private shared-memory tile so that each
+                // instruction moves whole 128-byte lines (lanes 8k..8k+7 -> one row): the carry of
+                // half-unit q+1 arrives by cp.async while q is computed.
+                constexpr int UPS = BN / 64;                 // units per segment
                 const bool has_carry = ep.carry_in != nullptr;
-                int4 cb[2][8];
-                auto unit = [&](int u, bool &valid, size_t &opix, uint32_t &trow, int &c0) {
-                    const int i = u / UPS;
-                    c0 = cw0 + (u - i * UPS) * 32;
-                    const int m = st * TM + i * 128 + row;
+                const f8::EpiConst kc = f8::epi_const(ep, has_carry);
+                const int h = warp >> 2;
+                uint8_t *ws = scratch + warp * WARP_SCRATCH;
+                const uint32_t ws_u32 = f8::smem_u32(ws);
+                auto half_unit = [&](int st_, int n0_, int q, int &pix, int &col0, uint32_t &tcol) {
+                    const int u = h + 2 * (q >> 1);
+                    const int seg = u / UPS;
+                    col0 = (u - seg * UPS) * 64 + (q & 1) * 32;         // first column inside the tile
+                    const int m = st_ * TM + seg * 128 + row;
                     const int Yo = m / g.PW;
                     const int xo = m - Yo * g.PW;
                     const int img = Yo / HP;
                     const int y = Yo - img * HP;
-                    valid = xo < g.W && y < g.H && img < g.N && c0 < ncols;
-                    opix = ((size_t)(img * g.H + y) * g.W + xo);
-                    trow = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((buf * MB + i) * BN);
+                    const bool valid = xo < g.W && y < g.H && img < g.N && n0_ + col0 < ep.cout_pad;
+                    pix = valid ? (img * g.H + y) * g.W + xo : -1;
+                    tcol = (uint32_t)(seg * BN + col0);
                 };
-                auto prefetch = [&](int u, int4 (&dst)[8]) {
-                    bool valid; size_t opix; uint32_t trow; int c0;
-                    unit(u, valid, opix, trow, c0);
-                    if (has_carry && valid) {
-                        const int32_t *src = ep.carry_in + opix * ep.cout_pad + n0 + c0;
+                auto issue_carry = [&](int st_, int n0_, int q, int bufi) {
+                    if (has_carry) {
+                        int pix, col0; uint32_t tcol;
+                        half_unit(st_, n0_, q, pix, col0, tcol);
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) dst[q] = f8::ld_carry_int4(src + 4 * q);
-                    }
-                };
-                prefetch(0, cb[0]);
-                F8_TIMED_WAIT(w_full, mbar_wait(acc_full(buf), acc_phase));
-                tc_fence_after();
-#pragma unroll
-                for (int u = 0; u < UNITS; ++u) {
-                    if (u + 1 < UNITS) prefetch(u + 1, cb[(u + 1) & 1]);
-                    bool valid; size_t opix; uint32_t trow; int c0;
-                    unit(u, valid, opix, trow, c0);
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (c0 + 16 * h < ncols) {          // warp-uniform
-                            int32_t v[16];
-                            tmem_ld16(trow + (uint32_t)(c0 + 16 * h), v);
-                            tmem_ld_wait();
-                            if (valid)
-                                f8::epilogue16_t<true>(v, bias_s + c0 + 16 * h, ep,
-                                                       opix * ep.cout_pad + n0 + c0 + 16 * h,
-                                                       n0 + c0 + 16 * h, opix, &cb[u & 1][4 * h]);
+                        for (int j = 0; j < 8; ++j) {
+                            const int r = 4 * j + (lane >> 3);
+                            const int p = __shfl_sync(0xffffffffu, pix, r);
+                            const int32_t *src = ep.carry_in + ((size_t)(p < 0 ? 0 : p) * ep.cout_pad + n0_ + col0) +
+                                                 (lane & 7) * 4;
+                            cp_async16(ws_u32 + bufi * CARRY_BUF + r * CARRY_PITCH + (lane & 7) * 16, src,
+                                       p >= 0 && n0_ + col0 + (lane & 7) * 4 < ep.cout_pad);
                         }
                     }
+                    cp_async_commit();
+                };
+                if (!epi_primed) {                // very first half-unit of this CTA
+                    issue_carry(st, n0, 0, 0);
+                    epi_primed = true;
+                }
+                F8_TIMED_WAIT(w_full, mbar_wait(acc_full(buf), acc_phase));
+                tc_fence_after();
+#pragma unroll 1
+                for (int q = 0; q < 4; ++q) {
+                    // request the next half-unit's carry (possibly the next tile's first one)
+                    if (q < 3) {
+                        issue_carry(st, n0, q + 1, (q + 1) & 1);
+                    } else {
+                        const int it2 = it + gridDim.x;
+                        if (it2 < total_items) {
+                            const int st2 = it2 / g.ntiles_n;
+                            issue_carry(st2, (it2 - st2 * g.ntiles_n) * BN, 0, 0);
+                        } else {
+                            cp_async_commit();
+                        }
+                    }
+                    cp_async_wait<1>();
+                    __syncwarp();
+                    int pix, col0; uint32_t tcol;
+                    half_unit(st, n0, q, pix, col0, tcol);
+                    uint8_t *cbuf = ws + (q & 1) * CARRY_BUF;
+                    uint8_t *obuf0 = ws + 2 * CARRY_BUF, *obuf1 = obuf0 + OUT_BUF;
+                    const bool cols_ok = n0 + col0 < ep.cout_pad;        // warp-uniform
+                    if (cols_ok) {
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            int32_t v[16];
+                            tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * MB * BN) + tcol + 16 * hh, v);
+                            tmem_ld_wait();
+                            int4 c[4];
+                            if (has_carry) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    c[k] = *reinterpret_cast<const int4 *>(cbuf + lane * CARRY_PITCH + hh * 64 + k * 16);
+                            }
+                            f8::epilogue16_math(v, bias_s + col0 + 16 * hh, kc, c, has_carry);
+                            if (ep.carry_out) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    *reinterpret_cast<int4 *>(cbuf + lane * CARRY_PITCH + hh * 64 + k * 16) =
+                                        make_int4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                            }
+                            if (ep.out0)
+                                *reinterpret_cast<uint4 *>(obuf0 + lane * OUT_PITCH + hh * 16) =
+                                    f8::requant_pack16(v, ep.shift0, ep.signed0);
+                            if (ep.out1)
+                                *reinterpret_cast<uint4 *>(obuf1 + lane * OUT_PITCH + hh * 16) =
+                                    f8::requant_pack16(v, ep.shift1, ep.signed1);
+                        }
+                    }
+                    if (q == 3) {
+                        tc_fence_before();
+                        mbar_arrive(acc_empty(buf));     // this thread's accumulator columns are drained
+                    }
+                    __syncwarp();
+                    if (cols_ok) {
+                        // cooperative, line-sized stores of the staged results
+                        if (ep.carry_out) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int r = 4 * j + (lane >> 3);
+                                const int p = __shfl_sync(0xffffffffu, pix, r);
+                                const int4 val = *reinterpret_cast<const int4 *>(cbuf + r * CARRY_PITCH + (lane & 7) * 16);
+                                if (p >= 0 && n0 + col0 + (lane & 7) * 4 < ep.cout_pad)
+                                    *reinterpret_cast<int4 *>(ep.carry_out + ((size_t)p * ep.cout_pad + n0 + col0) +
+                                                              (lane & 7) * 4) = val;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const int r = 16 * j + (lane >> 1);
+                            int p = __shfl_sync(0xffffffffu, pix, r);
+                            if (n0 + col0 + (lane & 1) * 16 >= ep.cout_pad) p = -1;   // partial last tile
+                            if (ep.out0) {
+                                const uint4 val = *reinterpret_cast<const uint4 *>(obuf0 + r * OUT_PITCH + (lane & 1) * 16);
+                                if (p >= 0)
+                                    *reinterpret_cast<uint4 *>(ep.out0 + ((size_t)p * ep.cout_pad + n0 + col0) +
+                                                               (lane & 1) * 16) = val;
+                            }
+                            if (ep.out1) {
+                                const uint4 val = *reinterpret_cast<const uint4 *>(obuf1 + r * OUT_PITCH + (lane & 1) * 16);
+                                if (p >= 0)
+                                    *reinterpret_cast<uint4 *>(ep.out1 + ((size_t)p * ep.cout_pad + n0 + col0) +
+                                                               (lane & 1) * 16) = val;
+                            }
+                        }
+                    }
+                    __syncwarp();       // staging tiles are free again
                 }
             }
-            // every accumulator column this thread owns is in registers (or consumed)
-            tc_fence_before();
-            mbar_arrive(acc_empty(buf));
+            if (PLAIN_U8) {
+                // every accumulator column this thread owns is in registers (or consumed)
+                tc_fence_before();
+                mbar_arrive(acc_empty(buf));
+            }
             if (++buf == 2) { buf = 0; acc_phase ^= 1; }
         }
         if (g.stats && tid == 0) {
@@ -402,15 +518,34 @@ template <int BN>
 int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     constexpr int MB = mb_for(BN);
     constexpr int TM = 128 * MB;
-    constexpr int SB = sb_for(BN);
     constexpr int B_TILE = BN * 64;
     const int PW = a.win + 1;
     const int slots = TM + 2 * PW + 2;
     if ((slots + LOADERS - 1) / LOADERS > MAX_SLOT_ITERS) return F8_ERR_UNSUPPORTED;
     const int slots_pad = (slots + 7) / 8 * 8;
+    f8::Epilogue ep{};
+    ep.bias = a.bias;
+    ep.carry_in = a.carry_in;
+    ep.carry_out = a.carry_out;
+    ep.out0 = static_cast<uint8_t *>(a.out[0]);
+    ep.out1 = static_cast<uint8_t *>(a.out[1]);
+    ep.carry_shift = a.carry_shift;
+    ep.relu = a.relu;
+    ep.shift0 = a.out_shift[0]; ep.signed0 = a.out_signed[0];
+    ep.shift1 = a.out_shift[1]; ep.signed1 = a.out_signed[1];
+    ep.cout = a.cout;
+    ep.cout_pad = a.cout_pad;
+    if (const char *probe = getenv("F8_PROBE")) {   // timing probes only: WRONG results
+        const int pv = atoi(probe);
+        if (pv & 1) ep.carry_in = nullptr;
+        if (pv & 2) ep.carry_out = nullptr;
+        if (pv & 4) ep.out0 = nullptr;
+    }
+    const bool plain = f8::epilogue_is_plain_u8(ep);
+    const int SA = sa_for(plain), SB = sb_for(BN, plain);
     const size_t smem_bytes = (size_t)SA * slots_pad * 64 + (size_t)SB * B_TILE +
-                              (2 * SA + 2 * SB + 4) * 8 + 16 + 2 * BN * 4;
-    if (smem_bytes > 220 * 1024) return F8_ERR_UNSUPPORTED;
+                              (2 * SA + 2 * SB + 4) * 8 + 16 + 2 * BN * 4 + scratch_for(plain);
+    if (smem_bytes > 227 * 1024) return F8_ERR_UNSUPPORTED;
     // the kernel owns all 512 TMEM columns: keep a second CTA off the SM
     const size_t smem_launch = smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes;
     const long long lin = (long long)a.n * (a.hin + 1) * PW;     // padded linear output space
@@ -427,25 +562,13 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     g.slots_pad = slots_pad;
     g.n_super = (int)((lin + TM - 1) / TM);
     g.ntiles_n = (a.cout_pad + BN - 1) / BN;
-    f8::Epilogue ep{};
-    ep.bias = a.bias;
-    ep.carry_in = a.carry_in;
-    ep.carry_out = a.carry_out;
-    ep.out0 = static_cast<uint8_t *>(a.out[0]);
-    ep.out1 = static_cast<uint8_t *>(a.out[1]);
-    ep.carry_shift = a.carry_shift;
-    ep.relu = a.relu;
-    ep.shift0 = a.out_shift[0]; ep.signed0 = a.out_signed[0];
-    ep.shift1 = a.out_shift[1]; ep.signed1 = a.out_signed[1];
-    ep.cout = a.cout;
-    ep.cout_pad = a.cout_pad;
     static bool attr_done = false;
     static int num_sms = 0;
     if (!attr_done) {
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         int dev = 0;
         F8_CUDA(cudaGetDevice(&dev));
         F8_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -460,7 +583,6 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
         F8_CUDA(cudaMemsetAsync(stats_dev, 0, 16 * 1024 * sizeof(long long), s));
         g.stats = stats_dev;
     }
-    const bool plain = f8::epilogue_is_plain_u8(ep);
     const unsigned gr = (unsigned)grid;
     if (a.in_signed) {
         if (plain) conv3x3_umma_kernel<BN, true, true><<<gr, (epi_warps_for(true) + 6) * 32, smem_launch, s>>>(g, ep);

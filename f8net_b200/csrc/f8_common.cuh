@@ -170,6 +170,77 @@ __device__ __forceinline__ void epilogue16(int32_t (&v)[16], const int32_t *bias
     epilogue16_t<false>(v, bias16, ep, o, gc, pixel, nullptr);
 }
 
+// The arithmetic of the epilogue alone (no memory traffic) for 16 channels of one pixel, written
+// branch-free on warp-uniform constants so that an element costs ~10 integer instructions:
+//   v += bias;  [v = (v << sv) + (carry << sc), clamp]  ;  v = max(v, floor)
+// where floor folds the residual clamp (INT_MIN+1) and the ReLU (0) into one max.
+struct EpiConst {
+    int sv, sc;        // residual alignment: v <<= sv ; carry <<= sc   (one of them is 0)
+    int floor;         // lower bound applied after bias / residual: 0 (ReLU), INT_MIN+1 (clamp) or INT_MIN
+};
+__device__ __forceinline__ EpiConst epi_const(const Epilogue &ep, bool has_carry) {
+    EpiConst k;
+    k.sv = has_carry && ep.carry_shift < 0 ? -ep.carry_shift : 0;
+    k.sc = has_carry && ep.carry_shift > 0 ? ep.carry_shift : 0;
+    k.floor = ep.relu ? 0 : (has_carry ? -2147483647 : (int)0x80000000);
+    return k;
+}
+__device__ __forceinline__ void epilogue16_math(int32_t (&v)[16], const int32_t *bias16,
+                                                const EpiConst &k, const int4 *c, bool has_carry) {
+#pragma unroll
+    for (int q = 0; q < 16; q += 4) {
+        const int4 b = *reinterpret_cast<const int4 *>(bias16 + q);
+        uint32_t t0 = (uint32_t)v[q + 0] + (uint32_t)b.x, t1 = (uint32_t)v[q + 1] + (uint32_t)b.y;
+        uint32_t t2 = (uint32_t)v[q + 2] + (uint32_t)b.z, t3 = (uint32_t)v[q + 3] + (uint32_t)b.w;
+        if (has_carry) {                       // warp-uniform
+            const int4 cc = c[q >> 2];
+            t0 = (t0 << k.sv) + ((uint32_t)cc.x << k.sc);
+            t1 = (t1 << k.sv) + ((uint32_t)cc.y << k.sc);
+            t2 = (t2 << k.sv) + ((uint32_t)cc.z << k.sc);
+            t3 = (t3 << k.sv) + ((uint32_t)cc.w << k.sc);
+        }
+        v[q + 0] = max((int32_t)t0, k.floor); v[q + 1] = max((int32_t)t1, k.floor);
+        v[q + 2] = max((int32_t)t2, k.floor); v[q + 3] = max((int32_t)t3, k.floor);
+    }
+}
+// 16 values -> 16 requantised, saturated bytes; the shift direction and signedness are
+// warp-uniform and tested once per call
+__device__ __forceinline__ uint4 requant_pack16(const int32_t (&v)[16], int n, int is_signed) {
+    int32_t r[16];
+    if (n > 0) {
+        const uint32_t half = 1u << (n - 1);
+        const uint32_t mask = (half << 1) - 1u;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t t = (uint32_t)v[i] + half;
+            r[i] = (int32_t)t >> n;
+            if ((t & mask) == 0u) r[i] &= ~1;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = (int32_t)((uint32_t)v[i] << (-n));
+    }
+    uint32_t w[4];
+    if (is_signed) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t hi;
+            const int32_t a = max(r[4 * q], -127), b = max(r[4 * q + 1], -127);
+            const int32_t c = max(r[4 * q + 2], -127), d = max(r[4 * q + 3], -127);
+            asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
+            asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w[q]) : "r"(b), "r"(a), "r"(hi));
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t hi;
+            asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(r[4 * q + 3]), "r"(r[4 * q + 2]), "r"(0));
+            asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w[q]) : "r"(r[4 * q + 1]), "r"(r[4 * q]), "r"(hi));
+        }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // Fast path of the same epilogue for the most common launch: no residual, no int32 carry
 // out, ONE unsigned 8-bit consumer reached by a right shift (n > 0).  ReLU is then absorbed
 // by the unsigned clamp (requant(relu(v)) == requant(v) for n > 0, SURVEY.md "exactness
