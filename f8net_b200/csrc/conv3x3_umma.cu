@@ -49,16 +49,18 @@ __host__ __device__ constexpr int sb_for(int bn, bool plain) { return plain ? (b
 __host__ __device__ constexpr int sa_for(bool plain) { return plain ? 3 : 2; }   // patch ring
 // a patch stage is signalled once A_LAG younger stages are issued (never the whole ring)
 __host__ __device__ constexpr int a_lag_for(bool plain) { return plain ? 1 : 0; }
-// per-warp staging of the generic epilogue: 2 carry buffers of 32 rows x (128 + 16) B and
-// 2 output buffers of 32 rows x (32 + 16) B
-constexpr int CARRY_PITCH = 144, CARRY_BUF = 32 * CARRY_PITCH;
-constexpr int OUT_PITCH = 48, OUT_BUF = 32 * OUT_PITCH;
-constexpr int WARP_SCRATCH = 2 * CARRY_BUF + 2 * OUT_BUF;
-__host__ __device__ constexpr int scratch_for(bool plain) { return plain ? 0 : 8 * WARP_SCRATCH; }
+// per-warp staging of the generic epilogue (16 warps, one 32-row x 64-column unit each, walked in
+// four 16-column steps): 2 carry buffers of 32 rows x (64 + 16) B (double-buffered cp.async
+// prefetch, reused in place for the carry-out rows) and one 32 x (64 + 16) B tile that collects
+// the unit's 8-bit output rows
+constexpr int CARRY_PITCH = 80, CARRY_BUF = 32 * CARRY_PITCH;
+constexpr int OUT_PITCH = 80, OUT_BUF = 32 * OUT_PITCH;
+constexpr int WARP_SCRATCH = 2 * CARRY_BUF + OUT_BUF;
+__host__ __device__ constexpr int scratch_for(bool plain) { return plain ? 0 : 16 * WARP_SCRATCH; }
 // epilogue warps: warp w reads TMEM lane group w % 4, column slice w / 4.  The plain-u8
 // epilogue is instruction-bound (16 warps); the generic one (residual carries) is bound by
 // memory latency and needs registers for its carry prefetch instead (8 warps).
-__host__ __device__ constexpr int epi_warps_for(bool plain) { return plain ? 16 : 8; }
+__host__ __device__ constexpr int epi_warps_for(bool plain) { return plain ? 16 : 16; }
 constexpr int LOADERS = 128;
 constexpr int MAX_SLOT_ITERS = 6;      // ceil((TM + 2*PW + 2) / 128) for TM = 512, PW <= 120
 
@@ -311,7 +313,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
         const int row = lg * 32 + lane;
         int buf = 0, acc_phase = 0;
         bool epi_primed = false;
-        long long w_full = 0;
+        long long w_full = 0, t_issue = 0, t_wait = 0, t_math = 0, t_store = 0;
         const long long t_begin = clock64();
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
             const int st = it / g.ntiles_n;
@@ -355,138 +357,133 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
                 }
             } else {
                 // ---- generic epilogue: residual carries, int32 carry out, dual / signed outputs ----
-                // Warp (lg, h) owns rows [32*lg, 32*lg+32) of the units u = h, h+2 (a unit = one M
-                // segment x 64 columns) and walks them in four half-units of 32 columns.  All global
-                // traffic is staged through a warp-private shared-memory tile so that each
-                // instruction moves whole 128-byte lines (lanes 8k..8k+7 -> one row): the carry of
-                // half-unit q+1 arrives by cp.async while q is computed.
+                // Warp (lg, u) owns rows [32*lg, 32*lg+32) of unit u (one M segment x 64 columns) and
+                // walks it in four steps of 16 columns.  The int32 carry traffic is staged through a
+                // warp-private shared-memory tile so that four lanes move one 64-byte row piece per
+                // instruction (cp.async in, 16-byte vector stores out); the carry of step q+1 arrives
+                // while step q is computed.  The unit's 8-bit rows of out0 are collected and stored
+                // as whole 64-byte rows at the end.
                 constexpr int UPS = BN / 64;                 // units per segment
                 const bool has_carry = ep.carry_in != nullptr;
                 const f8::EpiConst kc = f8::epi_const(ep, has_carry);
-                const int h = warp >> 2;
+                const int u = warp >> 2;
+                const int seg = u / UPS;
+                const int cbase = (u - seg * UPS) * 64;      // first column of the unit inside the tile
                 uint8_t *ws = scratch + warp * WARP_SCRATCH;
                 const uint32_t ws_u32 = f8::smem_u32(ws);
-                auto half_unit = [&](int st_, int n0_, int q, int &pix, int &col0, uint32_t &tcol) {
-                    const int u = h + 2 * (q >> 1);
-                    const int seg = u / UPS;
-                    col0 = (u - seg * UPS) * 64 + (q & 1) * 32;         // first column inside the tile
+                // element offset (pixel * cout_pad + n0 + cbase) of this thread's row, -1 if dropped
+                auto unit_offset = [&](int st_, int n0_) -> int {
                     const int m = st_ * TM + seg * 128 + row;
                     const int Yo = m / g.PW;
                     const int xo = m - Yo * g.PW;
                     const int img = Yo / HP;
                     const int y = Yo - img * HP;
-                    const bool valid = xo < g.W && y < g.H && img < g.N && n0_ + col0 < ep.cout_pad;
-                    pix = valid ? (img * g.H + y) * g.W + xo : -1;
-                    tcol = (uint32_t)(seg * BN + col0);
+                    const bool valid = xo < g.W && y < g.H && img < g.N;
+                    return valid ? ((img * g.H + y) * g.W + xo) * ep.cout_pad + n0_ + cbase : -1;
                 };
-                auto issue_carry = [&](int st_, int n0_, int q, int bufi) {
+                auto issue_carry = [&](int eo, int q, int n0_, int bufi) {
                     if (has_carry) {
-                        int pix, col0; uint32_t tcol;
-                        half_unit(st_, n0_, q, pix, col0, tcol);
+                        const bool lane_ok = n0_ + cbase + 16 * q + (lane & 3) * 4 < ep.cout_pad;
+                        const uint32_t dst = ws_u32 + bufi * CARRY_BUF + (lane >> 2) * CARRY_PITCH + (lane & 3) * 16;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int r = 4 * j + (lane >> 3);
-                            const int p = __shfl_sync(0xffffffffu, pix, r);
-                            const int32_t *src = ep.carry_in + ((size_t)(p < 0 ? 0 : p) * ep.cout_pad + n0_ + col0) +
-                                                 (lane & 7) * 4;
-                            cp_async16(ws_u32 + bufi * CARRY_BUF + r * CARRY_PITCH + (lane & 7) * 16, src,
-                                       p >= 0 && n0_ + col0 + (lane & 7) * 4 < ep.cout_pad);
+                        for (int j = 0; j < 4; ++j) {
+                            const int e = __shfl_sync(0xffffffffu, eo, 8 * j + (lane >> 2));
+                            const bool ok = e >= 0 && lane_ok;
+                            cp_async16(dst + j * 8 * CARRY_PITCH, ep.carry_in + (ok ? e + 16 * q + (lane & 3) * 4 : 0), ok);
                         }
                     }
                     cp_async_commit();
                 };
-                if (!epi_primed) {                // very first half-unit of this CTA
-                    issue_carry(st, n0, 0, 0);
+                const int eoff = unit_offset(st, n0);
+                if (!epi_primed) {                // very first step of this CTA
+                    issue_carry(eoff, 0, n0, 0);
                     epi_primed = true;
                 }
                 F8_TIMED_WAIT(w_full, mbar_wait(acc_full(buf), acc_phase));
                 tc_fence_after();
-#pragma unroll 1
+                const bool unit_ok = n0 + cbase < ep.cout_pad;          // warp-uniform
+                uint8_t *obuf = ws + 2 * CARRY_BUF;
+#pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    // request the next half-unit's carry (possibly the next tile's first one)
+                    const long long tq0 = g.stats ? clock64() : 0;
                     if (q < 3) {
-                        issue_carry(st, n0, q + 1, (q + 1) & 1);
+                        issue_carry(eoff, q + 1, n0, (q + 1) & 1);
                     } else {
                         const int it2 = it + gridDim.x;
                         if (it2 < total_items) {
                             const int st2 = it2 / g.ntiles_n;
-                            issue_carry(st2, (it2 - st2 * g.ntiles_n) * BN, 0, 0);
+                            const int n02 = (it2 - st2 * g.ntiles_n) * BN;
+                            issue_carry(unit_offset(st2, n02), 0, n02, 0);
                         } else {
                             cp_async_commit();
                         }
                     }
+                    const long long tq1 = g.stats ? clock64() : 0;
                     cp_async_wait<1>();
                     __syncwarp();
-                    int pix, col0; uint32_t tcol;
-                    half_unit(st, n0, q, pix, col0, tcol);
+                    const long long tq2 = g.stats ? clock64() : 0;
                     uint8_t *cbuf = ws + (q & 1) * CARRY_BUF;
-                    uint8_t *obuf0 = ws + 2 * CARRY_BUF, *obuf1 = obuf0 + OUT_BUF;
-                    const bool cols_ok = n0 + col0 < ep.cout_pad;        // warp-uniform
+                    const bool cols_ok = n0 + cbase + 16 * q < ep.cout_pad;      // warp-uniform
                     if (cols_ok) {
+                        int32_t v[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) +
+                                      (uint32_t)(buf * MB * BN + seg * BN + cbase + 16 * q), v);
+                        tmem_ld_wait();
+                        int4 c[4];
+                        if (has_carry) {
 #pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            int32_t v[16];
-                            tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * MB * BN) + tcol + 16 * hh, v);
-                            tmem_ld_wait();
-                            int4 c[4];
-                            if (has_carry) {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    c[k] = *reinterpret_cast<const int4 *>(cbuf + lane * CARRY_PITCH + hh * 64 + k * 16);
-                            }
-                            f8::epilogue16_math(v, bias_s + col0 + 16 * hh, kc, c, has_carry);
-                            if (ep.carry_out) {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    *reinterpret_cast<int4 *>(cbuf + lane * CARRY_PITCH + hh * 64 + k * 16) =
-                                        make_int4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-                            }
-                            if (ep.out0)
-                                *reinterpret_cast<uint4 *>(obuf0 + lane * OUT_PITCH + hh * 16) =
-                                    f8::requant_pack16(v, ep.shift0, ep.signed0);
-                            if (ep.out1)
-                                *reinterpret_cast<uint4 *>(obuf1 + lane * OUT_PITCH + hh * 16) =
-                                    f8::requant_pack16(v, ep.shift1, ep.signed1);
+                            for (int k = 0; k < 4; ++k)
+                                c[k] = *reinterpret_cast<const int4 *>(cbuf + lane * CARRY_PITCH + k * 16);
                         }
+                        f8::epilogue16_math(v, bias_s + cbase + 16 * q, kc, c, has_carry);
+                        if (ep.carry_out) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                *reinterpret_cast<int4 *>(cbuf + lane * CARRY_PITCH + k * 16) =
+                                    make_int4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                        }
+                        if (ep.out0)
+                            *reinterpret_cast<uint4 *>(obuf + lane * OUT_PITCH + q * 16) =
+                                f8::requant_pack16(v, ep.shift0, ep.signed0);
+                        if (ep.out1 && eoff >= 0)       // second image (downsample-block inputs): direct
+                            *reinterpret_cast<uint4 *>(ep.out1 + eoff + 16 * q) =
+                                f8::requant_pack16(v, ep.shift1, ep.signed1);
                     }
                     if (q == 3) {
                         tc_fence_before();
                         mbar_arrive(acc_empty(buf));     // this thread's accumulator columns are drained
                     }
                     __syncwarp();
-                    if (cols_ok) {
-                        // cooperative, line-sized stores of the staged results
-                        if (ep.carry_out) {
+                    const long long tq3 = g.stats ? clock64() : 0;
+                    if (cols_ok && ep.carry_out) {
+                        const bool lane_ok = n0 + cbase + 16 * q + (lane & 3) * 4 < ep.cout_pad;
+                        const uint8_t *srcp = cbuf + (lane >> 2) * CARRY_PITCH + (lane & 3) * 16;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int r = 4 * j + (lane >> 3);
-                                const int p = __shfl_sync(0xffffffffu, pix, r);
-                                const int4 val = *reinterpret_cast<const int4 *>(cbuf + r * CARRY_PITCH + (lane & 7) * 16);
-                                if (p >= 0 && n0 + col0 + (lane & 7) * 4 < ep.cout_pad)
-                                    *reinterpret_cast<int4 *>(ep.carry_out + ((size_t)p * ep.cout_pad + n0 + col0) +
-                                                              (lane & 7) * 4) = val;
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const int r = 16 * j + (lane >> 1);
-                            int p = __shfl_sync(0xffffffffu, pix, r);
-                            if (n0 + col0 + (lane & 1) * 16 >= ep.cout_pad) p = -1;   // partial last tile
-                            if (ep.out0) {
-                                const uint4 val = *reinterpret_cast<const uint4 *>(obuf0 + r * OUT_PITCH + (lane & 1) * 16);
-                                if (p >= 0)
-                                    *reinterpret_cast<uint4 *>(ep.out0 + ((size_t)p * ep.cout_pad + n0 + col0) +
-                                                               (lane & 1) * 16) = val;
-                            }
-                            if (ep.out1) {
-                                const uint4 val = *reinterpret_cast<const uint4 *>(obuf1 + r * OUT_PITCH + (lane & 1) * 16);
-                                if (p >= 0)
-                                    *reinterpret_cast<uint4 *>(ep.out1 + ((size_t)p * ep.cout_pad + n0 + col0) +
-                                                               (lane & 1) * 16) = val;
-                            }
+                        for (int j = 0; j < 4; ++j) {
+                            const int e = __shfl_sync(0xffffffffu, eoff, 8 * j + (lane >> 2));
+                            const int4 val = *reinterpret_cast<const int4 *>(srcp + j * 8 * CARRY_PITCH);
+                            if (e >= 0 && lane_ok)
+                                *reinterpret_cast<int4 *>(ep.carry_out + e + 16 * q + (lane & 3) * 4) = val;
                         }
                     }
-                    __syncwarp();       // staging tiles are free again
+                    __syncwarp();       // carry buffer (q & 1) is free again
+                    if (g.stats) {
+                        const long long tq4 = clock64();
+                        t_issue += tq1 - tq0; t_wait += tq2 - tq1; t_math += tq3 - tq2; t_store += tq4 - tq3;
+                    }
+                }
+                if (unit_ok && ep.out0) {
+                    // the unit's 8-bit rows: 4 lanes x 16 B per 64-byte row
+                    const bool lane_ok = n0 + cbase + (lane & 3) * 16 < ep.cout_pad;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = 8 * j + (lane >> 2);
+                        const int e = __shfl_sync(0xffffffffu, eoff, r);
+                        const uint4 val = *reinterpret_cast<const uint4 *>(obuf + r * OUT_PITCH + (lane & 3) * 16);
+                        if (e >= 0 && lane_ok)
+                            *reinterpret_cast<uint4 *>(ep.out0 + e + (lane & 3) * 16) = val;
+                    }
+                    __syncwarp();
                 }
             }
             if (PLAIN_U8) {
@@ -499,6 +496,10 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
         if (g.stats && tid == 0) {
             g.stats[blockIdx.x * 16 + 9] = clock64() - t_begin;
             g.stats[blockIdx.x * 16 + 10] = w_full;
+            g.stats[blockIdx.x * 16 + 11] = t_issue;
+            g.stats[blockIdx.x * 16 + 12] = t_wait;
+            g.stats[blockIdx.x * 16 + 13] = t_math;
+            g.stats[blockIdx.x * 16 + 14] = t_store;
         }
     }
 
@@ -603,9 +604,9 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
         fprintf(stderr,
                 "[f8 stats] conv3x3 BN=%d C=%d cout=%d HxW=%dx%d items=%lld/cta=%.1f | loader total %.0f wait_empty %.0f "
                 "wait_cp %.0f | wload total %.0f wait_bempty %.0f | mma total %.0f wait_acc %.0f wait_a %.0f "
-                "wait_b %.0f | epi total %.0f wait_full %.0f (cycles, mean per CTA)\n",
+                "wait_b %.0f | epi total %.0f wait_full %.0f issue %.0f cpwait %.0f math %.0f store %.0f (cycles, mean per CTA)\n",
                 BN, g.C, a.cout, g.H, g.W, items, (double)items / (double)grid, acc[0], acc[1], acc[2], acc[3],
-                acc[4], acc[5], acc[6], acc[7], acc[8], acc[9], acc[10]);
+                acc[4], acc[5], acc[6], acc[7], acc[8], acc[9], acc[10], acc[11], acc[12], acc[13], acc[14]);
     }
     return F8_OK;
 }
