@@ -43,24 +43,14 @@ using namespace f8u;
 // against operand fetch from shared memory (per K=32 MMA: 4 KB of A + 4 KB of B in 64 tensor
 // cycles); BN = 64 (MB = 4) serves the 64-channel layers.
 __host__ __device__ constexpr int mb_for(int bn) { return 256 / bn; }
-// Ring depths.  The generic (residual) epilogue needs ~96 KB of warp-private staging to make its
-// int32 carry traffic coalesced, so its operand rings are shallower.
-__host__ __device__ constexpr int sb_for(int bn, bool plain) { return plain ? (bn == 64 ? 12 : 8) : 6; }
-__host__ __device__ constexpr int sa_for(bool plain) { return plain ? 3 : 2; }   // patch ring
+// Ring depths.
+__host__ __device__ constexpr int sb_for(int bn, bool plain) { (void)plain; return bn == 64 ? 12 : 8; }
+__host__ __device__ constexpr int sa_for(bool plain) { (void)plain; return 3; }   // patch ring
 // a patch stage is signalled once A_LAG younger stages are issued (never the whole ring)
-__host__ __device__ constexpr int a_lag_for(bool plain) { return plain ? 1 : 0; }
-// per-warp staging of the generic epilogue (16 warps, one 32-row x 64-column unit each, walked in
-// four 16-column steps): 2 carry buffers of 32 rows x (64 + 16) B (double-buffered cp.async
-// prefetch, reused in place for the carry-out rows) and one 32 x (64 + 16) B tile that collects
-// the unit's 8-bit output rows
-constexpr int CARRY_PITCH = 80, CARRY_BUF = 32 * CARRY_PITCH;
-constexpr int OUT_PITCH = 80, OUT_BUF = 32 * OUT_PITCH;
-constexpr int WARP_SCRATCH = 2 * CARRY_BUF + OUT_BUF;
-__host__ __device__ constexpr int scratch_for(bool plain) { return plain ? 0 : 16 * WARP_SCRATCH; }
-// epilogue warps: warp w reads TMEM lane group w % 4, column slice w / 4.  The plain-u8
-// epilogue is instruction-bound (16 warps); the generic one (residual carries) is bound by
-// memory latency and needs registers for its carry prefetch instead (8 warps).
-__host__ __device__ constexpr int epi_warps_for(bool plain) { return plain ? 16 : 16; }
+__host__ __device__ constexpr int a_lag_for(bool plain) { (void)plain; return 1; }
+// epilogue warps: warp w reads TMEM lane group w % 4 and owns one 64-column unit (w / 4): the
+// exact integer requantisation is instruction-bound, hence 16 warps
+__host__ __device__ constexpr int epi_warps_for(bool plain) { (void)plain; return 16; }
 constexpr int LOADERS = 128;
 constexpr int MAX_SLOT_ITERS = 6;      // ceil((TM + 2*PW + 2) / 128) for TM = 512, PW <= 120
 
@@ -121,7 +111,6 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
     uint8_t *after = smem + SA * a_stage + SB * B_TILE + NBARS * 8;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(after);
     int32_t *sbias = reinterpret_cast<int32_t *>(after + 16);
-    uint8_t *scratch = after + 16 + 2 * BN * 4;            // generic epilogue: warp-private staging
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -313,6 +302,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
         const int row = lg * 32 + lane;
         int buf = 0, acc_phase = 0;
         bool epi_primed = false;
+        int4 cnext[4] = {};            // prefetched residual carry of the next 16-column step
         long long w_full = 0, t_issue = 0, t_wait = 0, t_math = 0, t_store = 0;
         const long long t_begin = clock64();
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
@@ -358,133 +348,77 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
             } else {
                 // ---- generic epilogue: residual carries, int32 carry out, dual / signed outputs ----
                 // Warp (lg, u) owns rows [32*lg, 32*lg+32) of unit u (one M segment x 64 columns) and
-                // walks it in four steps of 16 columns.  The int32 carry traffic is staged through a
-                // warp-private shared-memory tile so that four lanes move one 64-byte row piece per
-                // instruction (cp.async in, 16-byte vector stores out); the carry of step q+1 arrives
-                // while step q is computed.  The unit's 8-bit rows of out0 are collected and stored
-                // as whole 64-byte rows at the end.
+                // walks it in four steps of 16 columns.  int32 carries live in the pixel-interleaved
+                // layout of f8_common.cuh: the warp's 32 (nearly) consecutive pixels make every
+                // 16-byte carry access a contiguous 512-byte run.  The carry of step q+1 (or of the
+                // next tile's first step) is loaded into registers while step q is computed.
                 constexpr int UPS = BN / 64;                 // units per segment
                 const bool has_carry = ep.carry_in != nullptr;
                 const f8::EpiConst kc = f8::epi_const(ep, has_carry);
                 const int u = warp >> 2;
                 const int seg = u / UPS;
                 const int cbase = (u - seg * UPS) * 64;      // first column of the unit inside the tile
-                uint8_t *ws = scratch + warp * WARP_SCRATCH;
-                const uint32_t ws_u32 = f8::smem_u32(ws);
-                // element offset (pixel * cout_pad + n0 + cbase) of this thread's row, -1 if dropped
-                auto unit_offset = [&](int st_, int n0_) -> int {
+                auto unit_pixel = [&](int st_) -> int {      // output pixel of this thread's row, -1 = dropped
                     const int m = st_ * TM + seg * 128 + row;
                     const int Yo = m / g.PW;
                     const int xo = m - Yo * g.PW;
                     const int img = Yo / HP;
                     const int y = Yo - img * HP;
-                    const bool valid = xo < g.W && y < g.H && img < g.N;
-                    return valid ? ((img * g.H + y) * g.W + xo) * ep.cout_pad + n0_ + cbase : -1;
+                    return (xo < g.W && y < g.H && img < g.N) ? (img * g.H + y) * g.W + xo : -1;
                 };
-                auto issue_carry = [&](int eo, int q, int n0_, int bufi) {
-                    if (has_carry) {
-                        const bool lane_ok = n0_ + cbase + 16 * q + (lane & 3) * 4 < ep.cout_pad;
-                        const uint32_t dst = ws_u32 + bufi * CARRY_BUF + (lane >> 2) * CARRY_PITCH + (lane & 3) * 16;
+                auto load_carry = [&](int pix_, int col, int4 (&c)[4]) {
+                    if (has_carry && pix_ >= 0 && col < ep.cout_pad) {
+                        const int32_t *src = ep.carry_in + f8::carry_off((size_t)pix_, col, ep.cout_pad);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int e = __shfl_sync(0xffffffffu, eo, 8 * j + (lane >> 2));
-                            const bool ok = e >= 0 && lane_ok;
-                            cp_async16(dst + j * 8 * CARRY_PITCH, ep.carry_in + (ok ? e + 16 * q + (lane & 3) * 4 : 0), ok);
-                        }
+                        for (int k = 0; k < 4; ++k) c[k] = __ldg(reinterpret_cast<const int4 *>(src + k * 512));
                     }
-                    cp_async_commit();
                 };
-                const int eoff = unit_offset(st, n0);
+                const int pix = unit_pixel(st);
                 if (!epi_primed) {                // very first step of this CTA
-                    issue_carry(eoff, 0, n0, 0);
+                    load_carry(pix, n0 + cbase, cnext);
                     epi_primed = true;
                 }
                 F8_TIMED_WAIT(w_full, mbar_wait(acc_full(buf), acc_phase));
                 tc_fence_after();
-                const bool unit_ok = n0 + cbase < ep.cout_pad;          // warp-uniform
-                uint8_t *obuf = ws + 2 * CARRY_BUF;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const long long tq0 = g.stats ? clock64() : 0;
+                    int4 c[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) c[k] = cnext[k];
                     if (q < 3) {
-                        issue_carry(eoff, q + 1, n0, (q + 1) & 1);
+                        load_carry(pix, n0 + cbase + 16 * (q + 1), cnext);
                     } else {
                         const int it2 = it + gridDim.x;
                         if (it2 < total_items) {
                             const int st2 = it2 / g.ntiles_n;
-                            const int n02 = (it2 - st2 * g.ntiles_n) * BN;
-                            issue_carry(unit_offset(st2, n02), 0, n02, 0);
-                        } else {
-                            cp_async_commit();
+                            load_carry(unit_pixel(st2), (it2 - st2 * g.ntiles_n) * BN + cbase, cnext);
                         }
                     }
-                    const long long tq1 = g.stats ? clock64() : 0;
-                    cp_async_wait<1>();
-                    __syncwarp();
-                    const long long tq2 = g.stats ? clock64() : 0;
-                    uint8_t *cbuf = ws + (q & 1) * CARRY_BUF;
-                    const bool cols_ok = n0 + cbase + 16 * q < ep.cout_pad;      // warp-uniform
-                    if (cols_ok) {
+                    const int col = n0 + cbase + 16 * q;
+                    if (col < ep.cout_pad) {                               // warp-uniform
                         int32_t v[16];
                         tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) +
                                       (uint32_t)(buf * MB * BN + seg * BN + cbase + 16 * q), v);
                         tmem_ld_wait();
-                        int4 c[4];
-                        if (has_carry) {
+                        if (pix >= 0) {
+                            f8::epilogue16_math(v, bias_s + cbase + 16 * q, kc, c, has_carry);
+                            if (ep.carry_out) {
+                                int32_t *dst = ep.carry_out + f8::carry_off((size_t)pix, col, ep.cout_pad);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                c[k] = *reinterpret_cast<const int4 *>(cbuf + lane * CARRY_PITCH + k * 16);
+                                for (int k = 0; k < 4; ++k)
+                                    *reinterpret_cast<int4 *>(dst + k * 512) =
+                                        make_int4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                            }
+                            const size_t o = (size_t)pix * ep.cout_pad + col;
+                            if (ep.out0)
+                                *reinterpret_cast<uint4 *>(ep.out0 + o) = f8::requant_pack16(v, ep.shift0, ep.signed0);
+                            if (ep.out1)
+                                *reinterpret_cast<uint4 *>(ep.out1 + o) = f8::requant_pack16(v, ep.shift1, ep.signed1);
                         }
-                        f8::epilogue16_math(v, bias_s + cbase + 16 * q, kc, c, has_carry);
-                        if (ep.carry_out) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                *reinterpret_cast<int4 *>(cbuf + lane * CARRY_PITCH + k * 16) =
-                                    make_int4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-                        }
-                        if (ep.out0)
-                            *reinterpret_cast<uint4 *>(obuf + lane * OUT_PITCH + q * 16) =
-                                f8::requant_pack16(v, ep.shift0, ep.signed0);
-                        if (ep.out1 && eoff >= 0)       // second image (downsample-block inputs): direct
-                            *reinterpret_cast<uint4 *>(ep.out1 + eoff + 16 * q) =
-                                f8::requant_pack16(v, ep.shift1, ep.signed1);
-                    }
-                    if (q == 3) {
-                        tc_fence_before();
-                        mbar_arrive(acc_empty(buf));     // this thread's accumulator columns are drained
-                    }
-                    __syncwarp();
-                    const long long tq3 = g.stats ? clock64() : 0;
-                    if (cols_ok && ep.carry_out) {
-                        const bool lane_ok = n0 + cbase + 16 * q + (lane & 3) * 4 < ep.cout_pad;
-                        const uint8_t *srcp = cbuf + (lane >> 2) * CARRY_PITCH + (lane & 3) * 16;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int e = __shfl_sync(0xffffffffu, eoff, 8 * j + (lane >> 2));
-                            const int4 val = *reinterpret_cast<const int4 *>(srcp + j * 8 * CARRY_PITCH);
-                            if (e >= 0 && lane_ok)
-                                *reinterpret_cast<int4 *>(ep.carry_out + e + 16 * q + (lane & 3) * 4) = val;
-                        }
-                    }
-                    __syncwarp();       // carry buffer (q & 1) is free again
-                    if (g.stats) {
-                        const long long tq4 = clock64();
-                        t_issue += tq1 - tq0; t_wait += tq2 - tq1; t_math += tq3 - tq2; t_store += tq4 - tq3;
                     }
                 }
-                if (unit_ok && ep.out0) {
-                    // the unit's 8-bit rows: 4 lanes x 16 B per 64-byte row
-                    const bool lane_ok = n0 + cbase + (lane & 3) * 16 < ep.cout_pad;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int r = 8 * j + (lane >> 2);
-                        const int e = __shfl_sync(0xffffffffu, eoff, r);
-                        const uint4 val = *reinterpret_cast<const uint4 *>(obuf + r * OUT_PITCH + (lane & 3) * 16);
-                        if (e >= 0 && lane_ok)
-                            *reinterpret_cast<uint4 *>(ep.out0 + e + (lane & 3) * 16) = val;
-                    }
-                    __syncwarp();
-                }
+                tc_fence_before();
+                mbar_arrive(acc_empty(buf));     // this thread's accumulator columns are drained
             }
             if (PLAIN_U8) {
                 // every accumulator column this thread owns is in registers (or consumed)
@@ -545,7 +479,7 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     const bool plain = f8::epilogue_is_plain_u8(ep);
     const int SA = sa_for(plain), SB = sb_for(BN, plain);
     const size_t smem_bytes = (size_t)SA * slots_pad * 64 + (size_t)SB * B_TILE +
-                              (2 * SA + 2 * SB + 4) * 8 + 16 + 2 * BN * 4 + scratch_for(plain);
+                              (2 * SA + 2 * SB + 4) * 8 + 16 + 2 * BN * 4;
     if (smem_bytes > 227 * 1024) return F8_ERR_UNSUPPORTED;
     // the kernel owns all 512 TMEM columns: keep a second CTA off the SM
     const size_t smem_launch = smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes;

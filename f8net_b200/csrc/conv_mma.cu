@@ -265,11 +265,11 @@ conv_mma_kernel(const ConvGeom g, const f8::Epilogue ep) {
                     v1 = (int32_t)((uint32_t)v1 + (uint32_t)b.y);
                     int2 c = make_int2(0, 0);
                     if (has_carry)
-                        c = *reinterpret_cast<const int2 *>(ep.carry_in + (size_t)m * ep.cout_pad + gc);
+                        c = *reinterpret_cast<const int2 *>(ep.carry_in + f8::carry_off((size_t)m, gc, ep.cout_pad));
                     v0 = f8::residual_relu(v0, has_carry, c.x, ep.carry_shift, ep.relu);
                     v1 = f8::residual_relu(v1, has_carry, c.y, ep.carry_shift, ep.relu);
                     if (ep.carry_out)
-                        *reinterpret_cast<int2 *>(ep.carry_out + (size_t)m * ep.cout_pad + gc) =
+                        *reinterpret_cast<int2 *>(ep.carry_out + f8::carry_off((size_t)m, gc, ep.cout_pad)) =
                             make_int2(v0, v1);
                     if (ep.out_f32) {
                         float *o = ep.out_f32 + (size_t)m * ep.out_f32_ld + gc;

@@ -113,13 +113,14 @@ dw3x3_kernel(const DwGeom g, const f8::Epilogue ep) {
             const size_t o = m * ep.cout_pad + c4 * 4;
             const bool has_carry = ep.carry_in != nullptr;
             int4 cin = make_int4(0, 0, 0, 0);
-            if (has_carry) cin = *reinterpret_cast<const int4 *>(ep.carry_in + o);
+            if (has_carry) cin = *reinterpret_cast<const int4 *>(ep.carry_in + f8::carry_off(m, c4 * 4, ep.cout_pad));
             v[0] = f8::residual_relu(v[0], has_carry, cin.x, ep.carry_shift, ep.relu);
             v[1] = f8::residual_relu(v[1], has_carry, cin.y, ep.carry_shift, ep.relu);
             v[2] = f8::residual_relu(v[2], has_carry, cin.z, ep.carry_shift, ep.relu);
             v[3] = f8::residual_relu(v[3], has_carry, cin.w, ep.carry_shift, ep.relu);
             if (ep.carry_out)
-                *reinterpret_cast<int4 *>(ep.carry_out + o) = make_int4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<int4 *>(ep.carry_out + f8::carry_off(m, c4 * 4, ep.cout_pad)) =
+                    make_int4(v[0], v[1], v[2], v[3]);
             if (ep.out0) {
                 uint32_t pk = 0;
 #pragma unroll

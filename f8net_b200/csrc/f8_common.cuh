@@ -65,6 +65,17 @@ __device__ __forceinline__ uint32_t requant_pack4(int32_t a, int32_t b, int32_t 
     return out;
 }
 
+// int32 carry tensors (residual carries, max-pool / avg-pool inputs) use a pixel-interleaved
+// layout private to the engine: with p = pixel index inside the launch (image-major NHW order)
+// and C = cout_pad, element (p, c) lives at
+//     ((p >> 7) * (C >> 2) + (c >> 2)) * 512 + (p & 127) * 4 + (c & 3)
+// i.e. blocks of 128 pixels x 4 channels.  The tensor-core epilogues own one pixel per thread
+// (TMEM lane = pixel), so a warp's 16-byte accesses to 32 consecutive pixels are one contiguous
+// 512-byte run instead of 32 scattered pieces of an NHWC row.
+__host__ __device__ __forceinline__ size_t carry_off(size_t p, int c, int C) {
+    return ((p >> 7) * (size_t)(C >> 2) + (size_t)(c >> 2)) * 512 + (p & 127) * 4 + (size_t)(c & 3);
+}
+
 // Epilogue parameters, identical for every producing kernel (see f8_op in f8b200.h).
 struct Epilogue {
     const int32_t *bias;      // [cout_pad]
@@ -129,7 +140,7 @@ __device__ __forceinline__ void epilogue16_t(int32_t (&v)[16], const int32_t *bi
         if (has_carry) {
             int4 c;
             if (PRELOADED) c = carry16[q >> 2];
-            else c = ld_stream_int4(ep.carry_in + o + q);
+            else c = ld_stream_int4(ep.carry_in + carry_off(pixel, gc + q, ep.cout_pad));
             v[q + 0] = residual_relu(v[q + 0], true, c.x, ep.carry_shift, ep.relu);
             v[q + 1] = residual_relu(v[q + 1], true, c.y, ep.carry_shift, ep.relu);
             v[q + 2] = residual_relu(v[q + 2], true, c.z, ep.carry_shift, ep.relu);
@@ -139,7 +150,7 @@ __device__ __forceinline__ void epilogue16_t(int32_t (&v)[16], const int32_t *bi
             v[q + 2] = max(v[q + 2], 0); v[q + 3] = max(v[q + 3], 0);
         }
         if (ep.carry_out)
-            *reinterpret_cast<int4 *>(ep.carry_out + o + q) =
+            *reinterpret_cast<int4 *>(ep.carry_out + carry_off(pixel, gc + q, ep.cout_pad)) =
                 make_int4(v[q], v[q + 1], v[q + 2], v[q + 3]);
     }
     if (ep.out0) {

@@ -311,7 +311,7 @@ head_pool_kernel(const HGeom g, const f8::Epilogue ep) {
                     if (ep.carry_out) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
-                            *reinterpret_cast<int4 *>(ep.carry_out + o + 4 * q) =
+                            *reinterpret_cast<int4 *>(ep.carry_out + f8::carry_off(opix, grp * 16 + 4 * q, ep.cout_pad)) =
                                 make_int4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
                     }
                     if (ep.out0) {

@@ -13,7 +13,7 @@ namespace {
 
 constexpr int THREADS = 256;
 
-// in: int32 NHWC [n,hin,win,cpad] (post-ReLU head accumulator).  One thread = 4 channels
+// in: int32 [n,hin,win,cpad] in the carry layout of f8_common.cuh (post-ReLU head accumulator).  One thread = 4 channels
 // of one output pixel.  int -> float is monotone, so max-then-convert equals the
 // reference's convert-then-max; -inf padding never wins because every window holds at
 // least one real element.
@@ -40,7 +40,7 @@ maxpool_kernel(const int32_t *__restrict__ in, int n, int hin, int win, int hout
                 const int iw = q * 2 - 1 + s;
                 if ((unsigned)iw >= (unsigned)win) continue;
                 const int4 v = __ldg(reinterpret_cast<const int4 *>(
-                    in + (((size_t)img * hin + ih) * win + iw) * cpad + c4 * 4));
+                    in + f8::carry_off(((size_t)img * hin + ih) * win + iw, c4 * 4, cpad)));
                 m.x = max(m.x, v.x); m.y = max(m.y, v.y);
                 m.z = max(m.z, v.z); m.w = max(m.w, v.w);
             }
@@ -53,7 +53,8 @@ maxpool_kernel(const int32_t *__restrict__ in, int n, int hin, int win, int hout
             for (int c = 0; c < 4; ++c) v[c] = max(v[c], 0);
         }
         if (ep.carry_out)
-            *reinterpret_cast<int4 *>(ep.carry_out + o) = make_int4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<int4 *>(ep.carry_out + f8::carry_off(o / cpad, c4 * 4, cpad)) =
+                make_int4(v[0], v[1], v[2], v[3]);
         if (ep.out0) {
             uint32_t pk = 0;
 #pragma unroll
@@ -71,22 +72,35 @@ maxpool_kernel(const int32_t *__restrict__ in, int n, int hin, int win, int hout
     }
 }
 
-// in: int32 NHWC [n, hw, cpad] -> out0: 8-bit [n, cpad].  Sum wraps mod 2^32, which equals
-// the reference's int64 sum followed by .int() (fix_quant_ops.py:130-133).
+// in: int32 [n, hw, cpad] in the carry layout -> out0: 8-bit [n, cpad].  Sum wraps mod 2^32,
+// which equals the reference's int64 sum followed by .int() (fix_quant_ops.py:130-133).
+// One thread = 4 channels of one image; consecutive pixels of a channel quad are 16 B apart.
 __global__ void __launch_bounds__(THREADS)
 pool_requant_kernel(const int32_t *__restrict__ in, int n, int hw, int cpad,
                     const f8::Epilogue ep) {
-    const long long total = (long long)n * cpad;
+    const int c4n = cpad >> 2;
+    const long long total = (long long)n * c4n;
     for (long long idx = blockIdx.x * (long long)THREADS + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * THREADS) {
-        const int c = (int)(idx % cpad);
-        const int img = (int)(idx / cpad);
-        const int32_t *src = in + (size_t)img * hw * cpad + c;
-        uint32_t acc = 0;
-        for (int i = 0; i < hw; ++i) acc += (uint32_t)__ldg(src + (size_t)i * cpad);
-        const int32_t v = (int32_t)acc;
-        if (ep.carry_out) ep.carry_out[idx] = v;
-        if (ep.out0) ep.out0[idx] = (uint8_t)(f8::requant(v, ep.shift0, ep.signed0) & 0xff);
+        const int c4 = (int)(idx % c4n);
+        const int img = (int)(idx / c4n);
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        for (int i = 0; i < hw; ++i) {
+            const int4 v = __ldg(reinterpret_cast<const int4 *>(
+                in + f8::carry_off((size_t)img * hw + i, c4 * 4, cpad)));
+            a0 += (uint32_t)v.x; a1 += (uint32_t)v.y; a2 += (uint32_t)v.z; a3 += (uint32_t)v.w;
+        }
+        const int32_t v[4] = {(int32_t)a0, (int32_t)a1, (int32_t)a2, (int32_t)a3};
+        const size_t o = (size_t)img * cpad + c4 * 4;
+        if (ep.carry_out)       // plain [n, cpad] int32 (tests only)
+            *reinterpret_cast<int4 *>(ep.carry_out + o) = make_int4(v[0], v[1], v[2], v[3]);
+        if (ep.out0) {
+            uint32_t pk = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                pk |= ((uint32_t)f8::requant(v[c], ep.shift0, ep.signed0) & 0xffu) << (8 * c);
+            *reinterpret_cast<uint32_t *>(ep.out0 + o) = pk;
+        }
     }
 }
 
@@ -157,7 +171,7 @@ int launch_maxpool(const f8_conv_args &a, cudaStream_t s) {
 }
 
 int launch_pool_requant(const f8_conv_args &a, cudaStream_t s) {
-    const long long total = (long long)a.n * a.cin_pad;
+    const long long total = (long long)a.n * (a.cin_pad >> 2);
     pool_requant_kernel<<<grid_for(total), THREADS, 0, s>>>(static_cast<const int32_t *>(a.in),
                                                             a.n, a.hin * a.win, a.cin_pad,
                                                             make_ep(a));

@@ -99,9 +99,13 @@ class Plan:
         return b
 
     def carry(self, producer: Op):
+        """int32 image of ``producer``'s value in the engine's pixel-interleaved carry layout
+        (blocks of 128 pixels x 4 channels, csrc/f8_common.cuh): the pixel count is rounded up
+        to 128 per image so that any batch fits."""
         if producer.carry_out_buf < 0:
-            producer.carry_out_buf = self.new_buf(
-                producer.hout * producer.wout * producer.cout_pad * 4, f"{producer.name}:i32")
+            pixels = (producer.hout * producer.wout + 127) // 128 * 128
+            producer.carry_out_buf = self.new_buf(pixels * producer.cout_pad * 4,
+                                                  f"{producer.name}:i32")
         return producer.carry_out_buf
 
     # -- liveness + offsets -------------------------------------------------------------

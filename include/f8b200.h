@@ -16,8 +16,13 @@
  *     synchronisation.  A plan is immutable after creation, so f8_plan_run is re-entrant
  *     across streams as long as each caller brings its own workspace.
  *   - activations between layers are NHWC, 8 bit (u8 or s8 as the consumer's
- *     input_symmetric says), channels padded to a multiple of 16 with zeros; residual
- *     carries are NHWC int32 with the same channel padding.
+ *     input_symmetric says), channels padded to a multiple of 16 with zeros.
+ *   - int32 tensors that stay inside the engine (residual carries, the inputs of the max-pool
+ *     and the average pool) use a pixel-interleaved layout: with p the pixel index in
+ *     image-major NHW order inside the launch and C the padded channel count, element (p, c) is
+ *     at int32 index ((p >> 7) * (C / 4) + (c >> 2)) * 512 + (p & 127) * 4 + (c & 3)  -- blocks
+ *     of 128 pixels x 4 channels, so that a warp owning 32 consecutive pixels moves contiguous
+ *     512-byte runs.  A buffer holds ceil(pixels / 128) * 128 * C elements.
  */
 #ifndef F8B200_H_
 #define F8B200_H_
@@ -178,10 +183,10 @@ typedef struct f8_conv_args {
     const void *in;            /* 8-bit NHWC [n,hin,win,cin_pad] (int32 for maxpool / pool) */
     const void *wpack;         /* from f8_pack_weights                                    */
     const int32_t *bias;       /* [cout_pad], zero padded                                 */
-    const int32_t *carry_in;   /* int32 NHWC [n,hout,wout,cout_pad] or NULL               */
+    const int32_t *carry_in;   /* int32, carry layout (see top), n*hout*wout pixels, or NULL */
     int32_t carry_shift;
     int32_t relu;
-    int32_t *carry_out;        /* or NULL                                                 */
+    int32_t *carry_out;        /* same layout, or NULL                                    */
     void *out[2];              /* 8-bit NHWC [n,hout,wout,cout_pad] or NULL               */
     int32_t out_shift[2];
     int32_t out_signed[2];
@@ -202,7 +207,7 @@ F8_API int f8_conv_dense(const f8_conv_args *a, int backend, void *stream);
 /* Replaces: int nn.Conv2d.__call__ with groups == in_channels (fix_mobilenet_v1.py:33,
  * fix_mobilenet_v2.py:28) + consumer-side requant / ReLU. */
 F8_API int f8_conv_dw3x3(const f8_conv_args *a, void *stream);
-/* Replaces: self.head[-1](x.float()).int()  (fix_resnet.py:358-359). in = int32 NHWC. */
+/* Replaces: self.head[-1](x.float()).int()  (fix_resnet.py:358-359). in = int32, carry layout. */
 F8_API int f8_maxpool3x3s2(const f8_conv_args *a, void *stream);
 /* Replaces: x = self.head[:-1](x); x = self.head[-1](x.float()).int() in one launch
  * (fix_resnet.py:355-362): 7x7 s2 p3 conv of the NHWC4 image + bias + ReLU + float32 round trip
@@ -210,8 +215,8 @@ F8_API int f8_maxpool3x3s2(const f8_conv_args *a, void *stream);
  * sm_100 only; F8_ERR_UNSUPPORTED for any other geometry. */
 F8_API int f8_head_pool(const f8_conv_args *a, void *stream);
 /* Replaces: FXQAvgPool2d.forward int branch + int_op_only_fix_quant for the classifier
- * (fix_quant_ops.py:126-134, fix_resnet.py:367-374). in = int32 NHWC [n,h,w,c_pad],
- * out[0] = 8-bit [n,c_pad]. */
+ * (fix_quant_ops.py:126-134, fix_resnet.py:367-374). in = int32 carry layout, n*h*w pixels,
+ * out[0] = 8-bit [n,c_pad]; carry_out (tests) = plain int32 [n,c_pad]. */
 F8_API int f8_pool_requant(const f8_conv_args *a, void *stream);
 /* Replaces: the int32 NCHW tensor hand-over at model(x): repack to NHWC4 8 bit.
  * x int32 [n,3,h,w] -> out 8-bit [n,h,w,4]. */

@@ -8,7 +8,8 @@ import torch
 from f8net_b200 import _capi as C
 from oracle import oracle as O
 
-from util import cpad, nchw_to_nhwc8, nchw_to_nhwc32, nhwc_to_nchw  # noqa: F401 (re-exported)
+from util import (carry_elems, carry_to_nchw, cpad, nchw_to_carry, nchw_to_nhwc8,  # noqa: F401
+                  nchw_to_nhwc32, nhwc_to_nchw)
 
 DEV = "cuda:0"
 
@@ -64,14 +65,14 @@ def run_conv(lib, x, w, b, stride, pad, *, depthwise=False, in_signed=False, rel
     a.in_, a.wpack, a.bias = xd.data_ptr(), wd.data_ptr(), bd.data_ptr()
     keep = [xd, wd, bd]
     if carry is not None:
-        cd = dev(nchw_to_nhwc32(carry, cout_pad))
+        cd = dev(nchw_to_carry(carry, cout_pad))
         keep.append(cd)
         a.carry_in = cd.data_ptr()
     a.carry_shift, a.relu = carry_shift, int(relu)
     M = n * hout * wout
     co = None
     if want_carry:
-        co = torch.full((M, cout_pad), -12345, dtype=torch.int32, device=DEV)
+        co = torch.full((carry_elems(n, hout, wout, cout_pad),), -12345, dtype=torch.int32, device=DEV)
         a.carry_out = co.data_ptr()
     q = []
     for j, (s, g) in enumerate(outs):
@@ -91,7 +92,7 @@ def run_conv(lib, x, w, b, stride, pad, *, depthwise=False, in_signed=False, rel
     torch.cuda.synchronize()
     del keep
     shape = (n, hout, wout, cout_pad)
-    v = nhwc_to_nchw(co.cpu().numpy().reshape(shape), cout) if co is not None else None
+    v = carry_to_nchw(co.cpu().numpy(), n, cout, hout, wout, cout_pad) if co is not None else None
     qi = []
     for t, (s, g) in zip(q, outs):
         arr = t.cpu().numpy().reshape(shape)

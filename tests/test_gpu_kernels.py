@@ -11,7 +11,7 @@ torch = pytest.importorskip("torch")
 from f8net_b200 import _capi as C  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
-from util import cpad, nchw_to_nhwc32, nhwc_to_nchw  # noqa: E402
+from util import carry_elems, carry_to_nchw, cpad, nchw_to_carry, nhwc_to_nchw  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -186,17 +186,17 @@ def test_maxpool_float_round_trip(G, f8lib):
     x[2, 2] = rng.integers(2 ** 24, 2 ** 31 - 1, (h, h))
     want = O.maxpool_float_rt(x, 3, 2, 1)
     ho = want.shape[2]
-    xd = G.dev(nchw_to_nhwc32(x))
+    xd = G.dev(nchw_to_carry(x))
     a = _args_for_pool(n, c, h, ho, 3, 2, 1)
     a.in_ = xd.data_ptr()
-    co = torch.empty((n, ho, ho, cpad(c)), dtype=torch.int32, device="cuda:0")
+    co = torch.empty((carry_elems(n, ho, ho, cpad(c)),), dtype=torch.int32, device="cuda:0")
     q0 = torch.empty((n, ho, ho, cpad(c)), dtype=torch.uint8, device="cuda:0")
     a.carry_out = co.data_ptr()
     a.out[0] = q0.data_ptr()
     a.out_shift[0], a.out_signed[0] = 15, 0
     C.check(f8lib.f8_maxpool3x3s2(ctypes.byref(a), torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
-    assert np.array_equal(nhwc_to_nchw(co.cpu().numpy(), c), want)
+    assert np.array_equal(carry_to_nchw(co.cpu().numpy(), n, c, ho, ho), want)
     assert np.array_equal(nhwc_to_nchw(q0.cpu().numpy(), c), O.requant(want, 0, 15, False))
 
 
@@ -226,7 +226,7 @@ def test_head_conv_pool_fused(G, f8lib, signed):
     a.hin, a.win, a.hout, a.wout = 224, 224, 56, 56
     a.in_signed = int(signed)
     a.in_, a.wpack, a.bias = xd.data_ptr(), wd.data_ptr(), bd.data_ptr()
-    co = torch.full((n, 56, 56, 64), -7, dtype=torch.int32, device="cuda:0")
+    co = torch.full((carry_elems(n, 56, 56, 64),), -7, dtype=torch.int32, device="cuda:0")
     q = [torch.full((n, 56, 56, 64), 0x77, dtype=torch.uint8, device="cuda:0") for _ in outs]
     a.carry_out = co.data_ptr()
     for j, (s_, g_) in enumerate(outs):
@@ -234,7 +234,7 @@ def test_head_conv_pool_fused(G, f8lib, signed):
         a.out_shift[j], a.out_signed[j] = s_, int(g_)
     C.check(f8lib.f8_head_pool(ctypes.byref(a), torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
-    assert np.array_equal(nhwc_to_nchw(co.cpu().numpy(), 64), pooled)
+    assert np.array_equal(carry_to_nchw(co.cpu().numpy(), n, 64, 56, 56), pooled)
     assert np.array_equal(nhwc_to_nchw(q[0].cpu().numpy(), 64), want_q[0])
     assert np.array_equal(nhwc_to_nchw(q[1].cpu().numpy().view(np.int8), 64), want_q[1])
 
@@ -246,7 +246,7 @@ def test_pool_requant(G, f8lib):
     x = rng.integers(-2 ** 26, 2 ** 26, (n, c, 7, 7)).astype(np.int32)
     x[0, 0] = 2 ** 26                 # 49 * 2^26 wraps negative as int32
     want = O.avgpool_sum(np.minimum(x, 2 ** 26))
-    xd = G.dev(nchw_to_nhwc32(x))
+    xd = G.dev(nchw_to_carry(x))
     a = _args_for_pool(n, c, 7, 1, 7, 1, 0)
     a.in_ = xd.data_ptr()
     co = torch.empty((n, cpad(c)), dtype=torch.int32, device="cuda:0")

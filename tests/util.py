@@ -37,3 +37,30 @@ def checksum(a):
     wts = (np.arange(a.size, dtype=np.uint64) % np.uint64(65521)) + np.uint64(1)
     with np.errstate(over="ignore"):
         return np.uint64((a * wts).sum(dtype=np.uint64))
+
+
+def nchw_to_carry(x, c_pad=None):
+    """int32 [N,C,H,W] -> the engine's int32 carry layout (csrc/f8_common.cuh): with p the pixel
+    index in image-major NHW order, element (p, c) at ((p>>7)*(C/4) + (c>>2))*512 + (p&127)*4 + (c&3).
+    Returns a flat int32 array of ceil128(N*H*W) * c_pad elements."""
+    n, c, h, w = x.shape
+    c_pad = c_pad or cpad(c)
+    P = n * h * w
+    P128 = (P + 127) // 128 * 128
+    flat = np.zeros((P128, c_pad), dtype=np.int32)
+    flat[:P, :c] = np.transpose(x, (0, 2, 3, 1)).reshape(P, c)
+    return np.ascontiguousarray(flat.reshape(P128 // 128, 128, c_pad // 4, 4).transpose(0, 2, 1, 3)).reshape(-1)
+
+
+def carry_to_nchw(buf, n, c, h, w, c_pad=None):
+    """Inverse of nchw_to_carry."""
+    c_pad = c_pad or cpad(c)
+    P = n * h * w
+    P128 = (P + 127) // 128 * 128
+    flat = np.asarray(buf).reshape(-1)[:P128 * c_pad].reshape(P128 // 128, c_pad // 4, 128, 4)
+    flat = flat.transpose(0, 2, 1, 3).reshape(P128, c_pad)[:P, :c]
+    return np.ascontiguousarray(flat.reshape(n, h, w, c).transpose(0, 3, 1, 2)).astype(np.int32)
+
+
+def carry_elems(n, h, w, c_pad):
+    return (n * h * w + 127) // 128 * 128 * c_pad
