@@ -13,20 +13,20 @@
 // PERSISTENT kernel, one or two CTAs per SM, each looping over its tiles with one operand
 // ring and two TMEM accumulators, so the loads of tile i+1 and the epilogue of tile i-1
 // overlap the MMAs of tile i.  Warp roles:
-//   warps 8-11 producers.  Thread r owns tile row r (one output pixel): it gathers the
+//   4 warps    producers.  Thread r owns tile row r (one output pixel): it gathers the
 //              pixel's K bytes from the NHWC activation with 16-byte cp.async (zero fill for
 //              the padding halo) into the canonical K-major no-swizzle operand layout
 //              [K/16][128 rows][16 B] (core matrix = 8 rows x 16 B contiguous, SBO = 128 B,
 //              LBO = 2048 B), fences the generic->async proxy and arrives on the stage's
 //              "full" mbarrier.  Its thread 0 also posts the stage's weight bytes: 4 bulk
 //              copies of BN*16 contiguous bytes from the chunk-major weight image.
-//   warp 12    lane 0 issues the MMAs (tcgen05.mma is a single-thread instruction), commits
+//   1 warp     one elected lane issues the MMAs (tcgen05.mma is a single-thread instruction), commits
 //              each stage to its "empty" mbarrier and each finished accumulator to
-//              "acc_full".  Warp 12 also owns the TMEM allocation (2 x BN columns).
-//   warps 0-7  epilogue: warp w reads TMEM lane group w % 4 (lane = tile row), column half
-//              w / 4, 16 columns at a time, runs the integer epilogue of f8_common.cuh and
-//              releases the accumulator ("acc_empty").  Eight warps because the exact integer
-//              requantisation costs ~8 instructions per element.
+//              "acc_full".  It also owns the TMEM allocation (2 x BN columns).
+//   epilogue   8 (BN <= 128, two CTAs per SM) or 16 (BN = 256) warps: warp w reads TMEM lane
+//              group w % 4 (lane = tile row) and a column slice, 16 columns at a time, runs the
+//              integer epilogue of f8_common.cuh (residual carries prefetched two steps ahead)
+//              and releases the accumulator ("acc_empty").
 // Integer accumulation is associative mod 2^32: tiling and MMA order cannot change results.
 #include "umma_common.cuh"
 
@@ -34,12 +34,11 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int EPI_WARPS = 8;          // warps 0-7: epilogue (lane group w % 4, column half w / 4)
-constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int PRODUCER_WARP0 = 8;     // warps 8-11: A gather (+ thread 0 of them: B bulk copies)
+// epilogue warps: warp w reads TMEM lane group w % 4, column slice w / 4.  BN = 256 runs one CTA
+// per SM with 16 of them, BN <= 128 two CTAs per SM with 8 each: 16 epilogue warps per SM.
+__host__ __device__ constexpr int epi_warps_for(int bn) { return bn == 256 ? 16 : 8; }
 constexpr int PRODUCERS = 128;
-constexpr int MMA_WARP = 12;          // warp 12: TMEM alloc, lane 0 issues tcgen05.mma
-constexpr int THREADS = 416;
+__host__ __device__ constexpr int threads_for(int bn) { return (epi_warps_for(bn) + 5) * 32; }
 // ring depth per tile width: ~96-120 KB of operand bytes in flight per CTA
 __host__ __device__ constexpr int stages_for(int bn) { return bn <= 64 ? 8 : (bn <= 128 ? 6 : 5); }
 constexpr int A_STAGE = BM * BK;          // 8192 B: [4 chunks][128 rows][16 B]
@@ -63,9 +62,14 @@ using namespace f8u;
 // Persistent, warp-specialised kernel.  Static tile schedule: CTA b runs tiles b, b+grid, ...
 // with the N tile fastest, so CTAs that are co-resident read the same activation rows.
 template <int BN, bool A_SIGNED, bool SMALL_C>
-__global__ void __launch_bounds__(THREADS, (BN <= 128) ? 2 : 1)
+__global__ void __launch_bounds__(threads_for(BN), (BN <= 128) ? 2 : 1)
 conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const int ntiles_n) {
     extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int EPI_WARPS = epi_warps_for(BN);
+    constexpr int EPI_THREADS = EPI_WARPS * 32;
+    constexpr int PRODUCER_WARP0 = EPI_WARPS;     // 4 warps: A gather (+ its thread 0: B bulk copies)
+    constexpr int MMA_WARP = EPI_WARPS + 4;       // TMEM alloc, one elected lane issues tcgen05.mma
+    constexpr int THREADS = threads_for(BN);
     constexpr int S = stages_for(BN);
     constexpr int B_STAGE = BN * BK;
     constexpr int B_CHUNK = BN * 16;
@@ -218,10 +222,38 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
             if (++buf == 2) { buf = 0; acc_phase ^= 1; }
         }
     } else {
-        // =========================== epilogue (warps 0-7) =========================
-        const int lg = warp & 3;                       // TMEM lane group of this warp
-        const int ch = warp >> 2;                      // column half
+        // =========================== epilogue ====================================
+        // Warp (lg, cs): TMEM lane group lg = rows [32*lg, 32*lg+32) of the tile, column slice cs of
+        // CW columns, walked in steps of 16 columns.  Residual carries (pixel-interleaved layout,
+        // f8_common.cuh: contiguous 512-byte runs per warp access) are requested one or two steps ahead
+        // into registers -- across tile boundaries -- so that their DRAM latency is hidden.
+        const int lg = warp & 3;
+        const int cs = warp >> 2;
+        constexpr int CW = BN / (EPI_WARPS / 4);
+        constexpr int NS = CW / 16;                    // steps per tile for this warp
         const int row = lg * 32 + lane;                // TMEM lane == tile row
+        const bool has_carry = ep.carry_in != nullptr;
+        const bool plain = f8::epilogue_is_plain_u8(ep);
+        const f8::EpiConst kc = f8::epi_const(ep, has_carry);
+        // prefetch cursor: (tile, step) of the carry request two steps ahead of the consumer
+        int pf_t = blockIdx.x, pf_s = 0;
+        constexpr int PF = (BN == 256) ? 2 : 1;        // prefetch depth in steps (2 CTAs per SM need less)
+        int4 cq[PF][4] = {};
+        auto request = [&](int4 (&dst)[4]) {
+            if (has_carry && pf_t < total_tiles) {
+                const int mt = pf_t / ntiles_n;
+                const int col = (pf_t - mt * ntiles_n) * BN + cs * CW + 16 * pf_s;
+                const int m = mt * BM + row;
+                if (m < g.M && col < ep.cout_pad) {
+                    const int32_t *src = ep.carry_in + f8::carry_off((size_t)m, col, ep.cout_pad);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) dst[k] = __ldg(reinterpret_cast<const int4 *>(src + k * 512));
+                }
+            }
+            if (++pf_s == NS) { pf_s = 0; pf_t += gridDim.x; }
+        };
+#pragma unroll
+        for (int d = 0; d < PF; ++d) request(cq[d]);
         int buf = 0, acc_phase = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int mt = t / ntiles_n;
@@ -231,21 +263,56 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
             int ncols = ep.cout_pad - n0;
             if (ncols > BN) ncols = BN;
             int32_t *bias_s = sbias + buf * BN;
-            for (int i = tid; i < ncols; i += EPI_THREADS) bias_s[i] = __ldg(ep.bias + n0 + i);
+            for (int i = tid; i < ncols; i += EPI_THREADS) {
+                int32_t b = __ldg(ep.bias + n0 + i);
+                if (plain) b = (int32_t)((uint32_t)b + (1u << (ep.shift0 - 1)));   // bias + half
+                bias_s[i] = b;
+            }
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
             mbar_wait(acc_full_bar(buf), acc_phase);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * BN);
-            const int c_lo = ch * (BN / 2);
-            int c_hi = c_lo + BN / 2;
-            if (c_hi > ncols) c_hi = ncols;
-            for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
-                int32_t v[16];
-                tmem_ld16(trow + (uint32_t)c0, v);
-                tmem_ld_wait();
-                if (valid)
-                    f8::epilogue16(v, bias_s + c0, ep, (size_t)m * ep.cout_pad + n0 + c0, n0 + c0,
-                                   (size_t)m);
+#pragma unroll
+            for (int sidx = 0; sidx < NS; ++sidx) {
+                const int c0 = cs * CW + 16 * sidx;
+                int4 c[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    c[k] = cq[0][k];
+                    if (PF == 2) cq[0][k] = cq[PF - 1][k];
+                }
+                request(cq[PF - 1]);
+                if (c0 < ncols) {                               // warp-uniform
+                    int32_t v[16];
+                    tmem_ld16(trow + (uint32_t)c0, v);
+                    tmem_ld_wait();
+                    if (valid) {
+                        const int col = n0 + c0;
+                        const size_t o = (size_t)m * ep.cout_pad + col;
+                        if (plain) {
+                            f8::epilogue16_plain_u8(v, bias_s + c0, ep.out0 + o, ep.shift0);
+                        } else {
+                            f8::epilogue16_math(v, bias_s + c0, kc, c, has_carry);
+                            if (ep.carry_out) {
+                                int32_t *dst = ep.carry_out + f8::carry_off((size_t)m, col, ep.cout_pad);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    *reinterpret_cast<int4 *>(dst + k * 512) =
+                                        make_int4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                            }
+                            if (ep.out0)
+                                *reinterpret_cast<uint4 *>(ep.out0 + o) = f8::requant_pack16(v, ep.shift0, ep.signed0);
+                            if (ep.out1)
+                                *reinterpret_cast<uint4 *>(ep.out1 + o) = f8::requant_pack16(v, ep.shift1, ep.signed1);
+                            if (ep.out_f32) {
+                                float *f = ep.out_f32 + (size_t)m * ep.out_f32_ld + col;
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (col + i < ep.cout) f[i] = (float)v[i];
+                            }
+                        }
+                    }
+                }
             }
             tc_fence_before();
             mbar_arrive(acc_empty_bar(buf));       // this thread's columns are drained
@@ -286,7 +353,7 @@ int launch_t(const UGeom &g, const f8::Epilogue &ep, cudaStream_t s) {
     const int per_sm = (BN <= 128) ? 2 : 1;
     long long grid = (long long)num_sms * per_sm;
     if (grid > total) grid = total;
-    kern<<<(unsigned)grid, THREADS, smem_bytes, s>>>(g, ep, mtiles, ntn);
+    kern<<<(unsigned)grid, threads_for(BN), smem_bytes, s>>>(g, ep, mtiles, ntn);
     F8_CUDA(cudaGetLastError());
     return F8_OK;
 }
