@@ -1,4 +1,5 @@
-// conv3x3_umma.cu -- dense 3x3 / stride 1 / pad 1 int8 convolution on tcgen05 with the input
+// conv3x3_umma.cu -- dense 3x3 / pad 1 int8 convolution (stride 1, and stride 2 through four
+// input parity planes) on tcgen05 with the input
 // patch RESIDENT in shared memory: every input byte is fetched once per output tile and the
 // nine filter taps are nine shifted views of the same patch, expressed purely through the
 // start address of the tcgen05 shared-memory descriptor.
@@ -45,23 +46,25 @@ using namespace f8u;
 __host__ __device__ constexpr int mb_for(int bn) { return 256 / bn; }
 // Ring depths.
 __host__ __device__ constexpr int sb_for(int bn, bool plain) { (void)plain; return bn == 64 ? 12 : 8; }
-__host__ __device__ constexpr int sa_for(bool plain) { (void)plain; return 3; }   // patch ring
+__host__ __device__ constexpr int sa_for(int stride) { return stride == 2 ? 2 : 3; }   // patch ring (a stride-2 patch is 4 parity planes)
 // a patch stage is signalled once A_LAG younger stages are issued (never the whole ring)
-__host__ __device__ constexpr int a_lag_for(bool plain) { (void)plain; return 1; }
+__host__ __device__ constexpr int a_lag_for(int stride) { return stride == 2 ? 0 : 1; }
 // epilogue warps: warp w reads TMEM lane group w % 4 and owns one 64-column unit (w / 4): the
 // exact integer requantisation is instruction-bound, hence 16 warps
 __host__ __device__ constexpr int epi_warps_for(bool plain) { (void)plain; return 16; }
 constexpr int LOADERS = 128;
-constexpr int MAX_SLOT_ITERS = 6;      // ceil((TM + 2*PW + 2) / 128) for TM = 512, PW <= 120
+constexpr int MAX_SLOT_ITERS = 10;     // ceil(slots / 128): 512 + 2*PW + 2 (stride 1) or 4 * (256 + PW + 2) (stride 2)
 
 struct PGeom {
     const uint8_t *in;
     const uint8_t *wpack;   // [K_pad/16][wrows][16], k = (r*3+s)*C + c
     int wrows;
-    int N, H, W, C;         // C = cin_pad (multiple of 64)
+    int N, H, W, C;         // H x W = OUTPUT size per image, C = cin_pad (multiple of 64)
+    int Hin, Win;           // input size per image (= H, W for stride 1; 2H, 2W for stride 2)
+    int plane_slots;        // slots of one parity plane (stride 1: the only plane)
     int PW;                 // W + 1
     int tm;                 // 128 * MB
-    int slots;              // tm + 2*PW + 2
+    int slots;              // planes * plane_slots
     int slots_pad;          // slots rounded up to 8
     int n_super;            // tiles along the padded linear space
     int ntiles_n;           // cout_pad / BN (rounded up)
@@ -79,7 +82,7 @@ struct PGeom {
         }                                        \
     } while (0)
 
-template <int BN, bool A_SIGNED, bool PLAIN_U8>
+template <int BN, bool A_SIGNED, bool PLAIN_U8, int STRIDE>
 __global__ void __launch_bounds__((epi_warps_for(PLAIN_U8) + 6) * 32, 1)
 conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -91,8 +94,8 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
     constexpr int MB = mb_for(BN);
     constexpr int TM = 128 * MB;
     constexpr int SB = sb_for(BN, PLAIN_U8);
-    constexpr int SA = sa_for(PLAIN_U8);
-    constexpr int A_LAG = a_lag_for(PLAIN_U8);
+    constexpr int SA = sa_for(STRIDE);
+    constexpr int A_LAG = a_lag_for(STRIDE);
     constexpr int B_TILE = BN * 64;
     constexpr int CW = BN / (EPI_WARPS / 4);               // columns per epilogue warp slice (plain path)
     const int a_stage = g.slots_pad * 64;                 // bytes of one patch stage
@@ -149,27 +152,19 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
                 const int pl = lt + k * LOADERS;
                 off[k] = -1;
                 if (pl < g.slots) {
-                    const int pi = pi0 + pl;
+                    // stride 2: the patch is four parity planes (input row parity, column parity), each
+                    // laid out like a stride-1 patch of the OUTPUT-sized grid
+                    const int plane = STRIDE == 2 ? pl / g.plane_slots : 0;
+                    const int pi = pi0 + (pl - plane * g.plane_slots);
                     const int Yp = pi / g.PW;
                     const int xs = pi - Yp * g.PW;
                     const int img = Yp / HP;
                     const int yy = Yp - img * HP;
-                    if (xs >= 1 && yy >= 1 && img < g.N)
-                        off[k] = ((long long)(img * g.H + (yy - 1)) * g.W + (xs - 1)) * g.C;
-                }
-            }
-            if (!PLAIN_U8 && ep.carry_in != nullptr) {
-                // pull the residual carry of this tile's pixels into L2 now: the epilogue reads it
-                // one to three tiles later and then pays L2, not DRAM, latency per 16-byte load
-                const int n0 = (it - st * g.ntiles_n) * BN;
-#pragma unroll
-                for (int k = 0; k < MAX_SLOT_ITERS; ++k) {
-                    if (off[k] >= 0) {
-                        const char *cp = reinterpret_cast<const char *>(
-                            ep.carry_in + (size_t)(off[k] / g.C) * ep.cout_pad + n0);
-#pragma unroll
-                        for (int b = 0; b < BN * 4; b += 128)
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + b));
+                    if (xs >= 1 && yy >= 1 && img < g.N) {
+                        const int y = STRIDE == 2 ? 2 * (yy - 1) + (plane >> 1) : yy - 1;
+                        const int x = STRIDE == 2 ? 2 * (xs - 1) + (plane & 1) : xs - 1;
+                        if (y < g.Hin && x < g.Win)
+                            off[k] = ((long long)(img * g.Hin + y) * g.Win + x) * g.C;
                     }
                 }
             }
@@ -262,7 +257,11 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
                     tc_fence_after();
                     const uint32_t sb = sb_base + bslot * B_TILE;
                     const int r = tap / 3, s = tap - r * 3;
-                    const uint32_t a_lo0 = (((sa + (uint32_t)(r * g.PW + s) * 16) & 0x3ffffu) >> 4) | a_lbo_field;
+                    // slot offset of tap (r, s): stride 1: r*PW + s; stride 2: parity plane ((r != 1), (s != 1))
+                    // and a one-row / one-column step for r > 0 / s > 0
+                    const int tap_slots = STRIDE == 2 ? (((r != 1) * 2 + (s != 1)) * g.plane_slots + (r > 0) * g.PW + (s > 0))
+                                                      : r * g.PW + s;
+                    const uint32_t a_lo0 = (((sa + (uint32_t)tap_slots * 16) & 0x3ffffu) >> 4) | a_lbo_field;
                     const uint32_t b_lo0 = ((sb & 0x3ffffu) >> 4) | b_lbo_field;
                     const uint32_t first = (uint32_t)((cg | tap) != 0);
                     if (elect_one()) {
@@ -449,13 +448,14 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
 
 namespace {
 
-template <int BN>
+template <int BN, int STRIDE>
 int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     constexpr int MB = mb_for(BN);
     constexpr int TM = 128 * MB;
     constexpr int B_TILE = BN * 64;
-    const int PW = a.win + 1;
-    const int slots = TM + 2 * PW + 2;
+    const int PW = a.wout + 1;
+    const int plane_slots = TM + (STRIDE == 2 ? PW : 2 * PW) + 2;
+    const int slots = (STRIDE == 2 ? 4 : 1) * plane_slots;
     if ((slots + LOADERS - 1) / LOADERS > MAX_SLOT_ITERS) return F8_ERR_UNSUPPORTED;
     const int slots_pad = (slots + 7) / 8 * 8;
     f8::Epilogue ep{};
@@ -477,20 +477,23 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
         if (pv & 4) ep.out0 = nullptr;
     }
     const bool plain = f8::epilogue_is_plain_u8(ep);
-    const int SA = sa_for(plain), SB = sb_for(BN, plain);
+    constexpr int SA = sa_for(STRIDE);
+    const int SB = sb_for(BN, plain);
     const size_t smem_bytes = (size_t)SA * slots_pad * 64 + (size_t)SB * B_TILE +
                               (2 * SA + 2 * SB + 4) * 8 + 16 + 2 * BN * 4;
     if (smem_bytes > 227 * 1024) return F8_ERR_UNSUPPORTED;
     // the kernel owns all 512 TMEM columns: keep a second CTA off the SM
     const size_t smem_launch = smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes;
-    const long long lin = (long long)a.n * (a.hin + 1) * PW;     // padded linear output space
+    const long long lin = (long long)a.n * (a.hout + 1) * PW;     // padded linear output space
     if (lin > 0x7fffffffLL - TM) return F8_ERR_UNSUPPORTED;
     const f8host::DensePack pk = f8host::dense_pack_geometry(a.cin_pad, a.cout_pad, 3, 3);
     PGeom g{};
     g.in = static_cast<const uint8_t *>(a.in);
     g.wpack = static_cast<const uint8_t *>(a.wpack);
     g.wrows = pk.rows;
-    g.N = a.n; g.H = a.hin; g.W = a.win; g.C = a.cin_pad;
+    g.N = a.n; g.H = a.hout; g.W = a.wout; g.C = a.cin_pad;
+    g.Hin = a.hin; g.Win = a.win;
+    g.plane_slots = plane_slots;
     g.PW = PW;
     g.tm = TM;
     g.slots = slots;
@@ -500,10 +503,10 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     static bool attr_done = false;
     static int num_sms = 0;
     if (!attr_done) {
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, false, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, false, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, true, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, true, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         int dev = 0;
         F8_CUDA(cudaGetDevice(&dev));
         F8_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -520,11 +523,11 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     }
     const unsigned gr = (unsigned)grid;
     if (a.in_signed) {
-        if (plain) conv3x3_umma_kernel<BN, true, true><<<gr, (epi_warps_for(true) + 6) * 32, smem_launch, s>>>(g, ep);
-        else conv3x3_umma_kernel<BN, true, false><<<gr, (epi_warps_for(false) + 6) * 32, smem_launch, s>>>(g, ep);
+        if (plain) conv3x3_umma_kernel<BN, true, true, STRIDE><<<gr, (epi_warps_for(true) + 6) * 32, smem_launch, s>>>(g, ep);
+        else conv3x3_umma_kernel<BN, true, false, STRIDE><<<gr, (epi_warps_for(false) + 6) * 32, smem_launch, s>>>(g, ep);
     } else {
-        if (plain) conv3x3_umma_kernel<BN, false, true><<<gr, (epi_warps_for(true) + 6) * 32, smem_launch, s>>>(g, ep);
-        else conv3x3_umma_kernel<BN, false, false><<<gr, (epi_warps_for(false) + 6) * 32, smem_launch, s>>>(g, ep);
+        if (plain) conv3x3_umma_kernel<BN, false, true, STRIDE><<<gr, (epi_warps_for(true) + 6) * 32, smem_launch, s>>>(g, ep);
+        else conv3x3_umma_kernel<BN, false, false, STRIDE><<<gr, (epi_warps_for(false) + 6) * 32, smem_launch, s>>>(g, ep);
     }
     F8_CUDA(cudaGetLastError());
     if (want_stats) {
@@ -551,11 +554,16 @@ namespace f8host {
 
 // F8_ERR_UNSUPPORTED => the caller falls back to the gather kernel (conv_umma.cu)
 int launch_conv3x3_umma(const f8_conv_args &a, cudaStream_t s) {
-    if (a.kh != 3 || a.kw != 3 || a.stride != 1 || a.pad != 1 || a.cin_pad % 64 != 0 ||
-        a.cout_pad % 16 != 0 || a.hin != a.hout || a.win != a.wout || a.out_f32 != nullptr)
+    if (a.kh != 3 || a.kw != 3 || a.pad != 1 || a.cin_pad % 64 != 0 || a.cout_pad % 16 != 0 ||
+        a.out_f32 != nullptr)
         return F8_ERR_UNSUPPORTED;
-    if (a.cout_pad > 64) return launch_bn<128>(a, s);
-    return launch_bn<64>(a, s);
+    if (a.stride == 1 && a.hin == a.hout && a.win == a.wout) {
+        if (a.cout_pad > 64) return launch_bn<128, 1>(a, s);
+        return launch_bn<64, 1>(a, s);
+    }
+    // stride 2: four parity planes of the input; even input sizes only (every F8Net stage)
+    if (a.stride == 2 && a.hin == 2 * a.hout && a.win == 2 * a.wout) return launch_bn<128, 2>(a, s);
+    return F8_ERR_UNSUPPORTED;
 }
 
 }  // namespace f8host

@@ -17,10 +17,11 @@
 //             padded to 256) with shared->shared copies: global memory is read once.
 //   MMA (warp 12)  8 K=32 MMAs per segment into TMEM columns [64*s, 64*s+64); the 16 KB weight
 //             image stays resident in shared memory for the whole kernel.
-//   epilogue (warps 0-7)  four passes of 16 channels: TMEM -> +bias, ReLU, int->float -> shared
-//             staging tile; then each of 224 threads max-pools one pooled pixel (float bit
-//             patterns of non-negative floats order like integers), converts back with the
-//             x86 cvttss2si semantics of .int(), and writes carry / 8-bit images.
+//   epilogue (warps 0-7)  four passes of 16 channels: TMEM -> +bias, ReLU, int->float, horizontal
+//             3-max with the neighbouring lanes (shuffles) -> shared staging tile; then each of
+//             224 threads takes the vertical 3-max of one pooled pixel (on the integers: int -> float
+//             is monotone), applies the float32 round trip with the x86 cvttss2si semantics of
+//             .int(), and writes carry / 8-bit images.
 #include <cstdio>
 #include <cstdlib>
 
@@ -43,7 +44,7 @@ constexpr int A_STAGE = 128 * KPAD;         // 32 KB: [16 chunks][128][16]
 constexpr int A_CHUNK = 128 * 16;
 constexpr int SA = 2;
 constexpr int W_BYTES = COUT * KPAD;        // 16 KB: [16 chunks][64][16]
-constexpr int STAGE_BYTES = CPIX * 64;      // 16 channels x 4 B per conv pixel
+constexpr int STAGE_BYTES = CROWS * POOLED * 64 + 32 * 64;   // horizontally pooled tile (16 channels x 4 B per entry) + side buffer
 constexpr int EPI_WARPS = 8, EPI_THREADS = 256;
 constexpr int BUILD_WARP0 = 8, BUILDERS = 128;
 constexpr int MMA_WARP = 12;
@@ -236,6 +237,7 @@ head_pool_kernel(const HGeom g, const f8::Epilogue ep) {
         const int lg = warp & 3;                 // TMEM lane group
         const int shalf = warp >> 2;             // segments 4*shalf .. 4*shalf+3
         uint8_t *stage = smem + OFF_STAGE;
+        uint8_t *side = smem + OFF_STAGE + CROWS * POOLED * 64;   // raw lane-31 values, 32 x 64 B
         int tphase = 0;
         long long w_full = 0, t_p1 = 0, t_p2 = 0;
         const long long t_begin = clock64();
@@ -246,26 +248,51 @@ head_pool_kernel(const HGeom g, const f8::Epilogue ep) {
             tc_fence_after();
             for (int grp = 0; grp < 4; ++grp) {
                 const long long tp0 = g.stats ? clock64() : 0;
-                // ---- phase 1: accumulators -> relu -> float bits -> staging tile ----
+                // ---- phase 1: accumulators -> relu -> float bits -> HORIZONTAL 3-max -> staging ----
+                // Conv rows start at even lanes (112 = 3.5 warps), so the pooling centres (even
+                // columns) are the even lanes and their neighbours are the adjacent lanes: two
+                // shuffles per value.  Only a centre at lane 0 lacks its left neighbour (lane 31 of
+                // the previous 32-pixel run): every lane 31 parks its raw values in a side buffer
+                // that phase 2 folds in.  The staging tile shrinks to 9 x 56 entries of 64 B.
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int s = shalf * 4 + j;
                     const int m = s * 128 + lg * 32 + lane;
+                    const int cr = m / CONV, col = m - cr * CONV;
                     int32_t v[16];
                     tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(s * COUT + grp * 16), v);
                     tmem_ld_wait();
-                    if (m < CPIX) {
+                    int32_t x[16];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int4 b = *reinterpret_cast<const int4 *>(sbias + grp * 16 + 4 * q);
-                            const int32_t x0 = max((int32_t)((uint32_t)v[4 * q + 0] + (uint32_t)b.x), 0);
-                            const int32_t x1 = max((int32_t)((uint32_t)v[4 * q + 1] + (uint32_t)b.y), 0);
-                            const int32_t x2 = max((int32_t)((uint32_t)v[4 * q + 2] + (uint32_t)b.z), 0);
-                            const int32_t x3 = max((int32_t)((uint32_t)v[4 * q + 3] + (uint32_t)b.w), 0);
-                            *reinterpret_cast<int4 *>(stage + stage_off(m, q)) =
-                                make_int4(__float_as_int((float)x0), __float_as_int((float)x1),
-                                          __float_as_int((float)x2), __float_as_int((float)x3));
-                        }
+                    for (int q = 0; q < 4; ++q) {
+                        const int4 b = *reinterpret_cast<const int4 *>(sbias + grp * 16 + 4 * q);
+                        // int -> float is monotone, so the pooling maximum is taken on the integers and
+                        // the float32 round trip is applied once per pooled value in phase 2
+                        x[4 * q + 0] = max((int32_t)((uint32_t)v[4 * q + 0] + (uint32_t)b.x), 0);
+                        x[4 * q + 1] = max((int32_t)((uint32_t)v[4 * q + 1] + (uint32_t)b.y), 0);
+                        x[4 * q + 2] = max((int32_t)((uint32_t)v[4 * q + 2] + (uint32_t)b.z), 0);
+                        x[4 * q + 3] = max((int32_t)((uint32_t)v[4 * q + 3] + (uint32_t)b.w), 0);
+                    }
+                    if (lane == 31) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            *reinterpret_cast<int4 *>(side + (s * 4 + lg) * 64 + q * 16) =
+                                make_int4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+                    }
+                    const bool use_left = lane > 0 && col > 0;
+                    int32_t hm[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int32_t l = __shfl_up_sync(0xffffffffu, x[i], 1);
+                        const int32_t r = __shfl_down_sync(0xffffffffu, x[i], 1);
+                        hm[i] = max(max(x[i], r), use_left ? l : 0);
+                    }
+                    if (m < CPIX && !(col & 1)) {
+                        const int e = cr * POOLED + (col >> 1);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            *reinterpret_cast<int4 *>(stage + stage_off(e, q)) =
+                                make_int4(hm[4 * q], hm[4 * q + 1], hm[4 * q + 2], hm[4 * q + 3]);
                     }
                 }
                 if (grp == 3) {
@@ -275,7 +302,7 @@ head_pool_kernel(const HGeom g, const f8::Epilogue ep) {
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
                 const long long tp1 = g.stats ? clock64() : 0;
                 t_p1 += tp1 - tp0;
-                // ---- phase 2: 3x3 s2 p1 max-pool, .int(), carry + requantised images ----
+                // ---- phase 2: vertical 3-max, .int(), carry + requantised images ----
                 if (tid < TP * POOLED) {
                     const int pr = tid / POOLED, pq = tid - pr * POOLED;
                     int4 mx[4];
@@ -285,26 +312,28 @@ head_pool_kernel(const HGeom g, const f8::Epilogue ep) {
                     for (int dr = 0; dr < 3; ++dr) {
                         const int cr = 2 * pr + dr;                       // local conv row
                         if (2 * pr0 - 1 + cr < 0) continue;               // conv row -1 (padding)
+                        const int e = cr * POOLED + pq;
+                        const int mc = cr * CONV + 2 * pq;                // conv pixel of the centre
+                        const bool need_side = (mc & 31) == 0 && pq > 0;
 #pragma unroll
-                        for (int dc = 0; dc < 3; ++dc) {
-                            const int cq = 2 * pq - 1 + dc;
-                            if (cq < 0) continue;                         // conv col -1 (padding)
-                            const int m = cr * CONV + cq;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const int4 x = *reinterpret_cast<const int4 *>(stage + stage_off(m, q));
-                                mx[q].x = max(mx[q].x, x.x); mx[q].y = max(mx[q].y, x.y);
-                                mx[q].z = max(mx[q].z, x.z); mx[q].w = max(mx[q].w, x.w);
+                        for (int q = 0; q < 4; ++q) {
+                            const int4 xv = *reinterpret_cast<const int4 *>(stage + stage_off(e, q));
+                            mx[q].x = max(mx[q].x, xv.x); mx[q].y = max(mx[q].y, xv.y);
+                            mx[q].z = max(mx[q].z, xv.z); mx[q].w = max(mx[q].w, xv.w);
+                            if (need_side) {
+                                const int4 sv = *reinterpret_cast<const int4 *>(side + ((mc - 1) >> 5) * 64 + q * 16);
+                                mx[q].x = max(mx[q].x, sv.x); mx[q].y = max(mx[q].y, sv.y);
+                                mx[q].z = max(mx[q].z, sv.z); mx[q].w = max(mx[q].w, sv.w);
                             }
                         }
                     }
                     int32_t r[16];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        r[4 * q + 0] = f8::f2i_x86(__int_as_float(mx[q].x));
-                        r[4 * q + 1] = f8::f2i_x86(__int_as_float(mx[q].y));
-                        r[4 * q + 2] = f8::f2i_x86(__int_as_float(mx[q].z));
-                        r[4 * q + 3] = f8::f2i_x86(__int_as_float(mx[q].w));
+                        r[4 * q + 0] = f8::f2i_x86((float)mx[q].x);
+                        r[4 * q + 1] = f8::f2i_x86((float)mx[q].y);
+                        r[4 * q + 2] = f8::f2i_x86((float)mx[q].z);
+                        r[4 * q + 3] = f8::f2i_x86((float)mx[q].w);
                     }
                     const size_t opix = ((size_t)img * POOLED + (pr0 + pr)) * POOLED + pq;
                     const size_t o = opix * ep.cout_pad + grp * 16;
