@@ -115,6 +115,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(after);
     int32_t *sbias = reinterpret_cast<int32_t *>(after + 16);
 
+    const long long t_entry = clock64();
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int total_items = g.n_super * g.ntiles_n;
@@ -245,12 +246,14 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
         int aslot = 0, aphase = 0, bslot = 0, bphase = 0, buf = 0, acc_phase = 0;
         long long w_acc = 0, w_a = 0, w_b = 0;
         const long long t_begin = clock64();
+        long long t_first_a = 0;
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
             F8_TIMED_WAIT(w_acc, mbar_wait(acc_empty(buf), acc_phase ^ 1));
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(buf * MB * BN);
             for (int cg = 0; cg < ncg; ++cg) {
                 F8_TIMED_WAIT(w_a, mbar_wait(a_full(aslot), aphase));
+                if (g.stats && t_first_a == 0) t_first_a = clock64();
                 const uint32_t sa = smem_base + aslot * a_stage;
                 for (int tap = 0; tap < 9; ++tap) {
                     F8_TIMED_WAIT(w_b, mbar_wait(b_full(bslot), bphase));
@@ -293,6 +296,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
             g.stats[blockIdx.x * 16 + 6] = w_acc;
             g.stats[blockIdx.x * 16 + 7] = w_a;
             g.stats[blockIdx.x * 16 + 8] = w_b;
+            g.stats[blockIdx.x * 16 + 15] = ((t_begin - t_entry) << 32) | ((t_first_a - t_entry) & 0xffffffffll);
         }
     } else {
         // =========================== epilogue (warps 0-15) ========================
@@ -442,6 +446,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+    if (g.stats && tid == 0) g.stats[blockIdx.x * 16 + 11] = clock64() - t_entry;
 }
 
 }  // namespace
@@ -544,6 +549,14 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
                 "wait_b %.0f | epi total %.0f wait_full %.0f issue %.0f cpwait %.0f math %.0f store %.0f (cycles, mean per CTA)\n",
                 BN, g.C, a.cout, g.H, g.W, items, (double)items / (double)grid, acc[0], acc[1], acc[2], acc[3],
                 acc[4], acc[5], acc[6], acc[7], acc[8], acc[9], acc[10], acc[11], acc[12], acc[13], acc[14]);
+        {
+            double pro = 0, fa = 0;
+            for (long long b = 0; b < grid; ++b) {
+                pro += (double)(host[b * 16 + 15] >> 32) / (double)grid;
+                fa += (double)(host[b * 16 + 15] & 0xffffffffll) / (double)grid;
+            }
+            fprintf(stderr, "[f8 stats]   timeline: prologue done @%.0f, first patch landed @%.0f, kernel end @%.0f cycles (acc[11])\n", pro, fa, acc[11]);
+        }
     }
     return F8_OK;
 }

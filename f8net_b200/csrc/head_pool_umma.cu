@@ -11,15 +11,15 @@
 // One tile = 4 pooled rows x 56 pooled columns of one image = conv rows 2*pr0-1 .. 2*pr0+7
 // (9 rows x 112 = 1008 conv pixels = 8 MMA segments of 128) -- one conv row of overlap between
 // neighbouring tiles is recomputed.  Pipeline per tile:
-//   builders (warps 8-11)  stage the 23 x 232-pixel input patch (NHWC4 bytes, zero fill outside
+//   builders (warps 16-19)  stage the 23 x 232-pixel input patch (NHWC4 bytes, zero fill outside
 //             the image) with cp.async, then expand it segment by segment into the im2col
 //             operand [K/16][128 rows][16 B] (K = 7 filter rows x 8-pixel window x 4 B = 224,
 //             padded to 256) with shared->shared copies: global memory is read once.
-//   MMA (warp 12)  8 K=32 MMAs per segment into TMEM columns [64*s, 64*s+64); the 16 KB weight
+//   MMA (warp 20)  8 K=32 MMAs per segment into TMEM columns [64*s, 64*s+64); the 16 KB weight
 //             image stays resident in shared memory for the whole kernel.
-//   epilogue (warps 0-7)  four passes of 16 channels: TMEM -> +bias, ReLU, int->float, horizontal
+//   epilogue (warps 0-15) four passes of 16 channels: TMEM -> +bias, ReLU, int->float, horizontal
 //             3-max with the neighbouring lanes (shuffles) -> shared staging tile; then each of
-//             224 threads takes the vertical 3-max of one pooled pixel (on the integers: int -> float
+//             448 threads takes the vertical 3-max of 8 channels of one pooled pixel (on the integers: int -> float
 //             is monotone), applies the float32 round trip with the x86 cvttss2si semantics of
 //             .int(), and writes carry / 8-bit images.
 #include <cstdio>
@@ -45,10 +45,11 @@ constexpr int A_CHUNK = 128 * 16;
 constexpr int SA = 2;
 constexpr int W_BYTES = COUT * KPAD;        // 16 KB: [16 chunks][64][16]
 constexpr int STAGE_BYTES = CROWS * POOLED * 64 + 32 * 64;   // horizontally pooled tile (16 channels x 4 B per entry) + side buffer
-constexpr int EPI_WARPS = 8, EPI_THREADS = 256;
-constexpr int BUILD_WARP0 = 8, BUILDERS = 128;
-constexpr int MMA_WARP = 12;
-constexpr int THREADS = 13 * 32;
+// the epilogue is instruction-bound (~8 integer instructions per conv element): 16 warps
+constexpr int EPI_THREADS = 512;
+constexpr int BUILD_WARP0 = 16, BUILDERS = 128;
+constexpr int MMA_WARP = 20;
+constexpr int THREADS = 21 * 32;
 
 constexpr int OFF_PATCH = 0;                                   // 2 patch buffers
 constexpr int OFF_A = OFF_PATCH + 2 * ((PATCH_BYTES + 127) / 128 * 128);
@@ -235,7 +236,7 @@ head_pool_kernel(const HGeom g, const f8::Epilogue ep) {
     } else {
         // =========================== epilogue (warps 0-7) =========================
         const int lg = warp & 3;                 // TMEM lane group
-        const int shalf = warp >> 2;             // segments 4*shalf .. 4*shalf+3
+        const int sq = warp >> 2;                // segments 2*sq, 2*sq+1
         uint8_t *stage = smem + OFF_STAGE;
         uint8_t *side = smem + OFF_STAGE + CROWS * POOLED * 64;   // raw lane-31 values, 32 x 64 B
         int tphase = 0;
@@ -255,8 +256,8 @@ head_pool_kernel(const HGeom g, const f8::Epilogue ep) {
                 // the previous 32-pixel run): every lane 31 parks its raw values in a side buffer
                 // that phase 2 folds in.  The staging tile shrinks to 9 x 56 entries of 64 B.
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int s = shalf * 4 + j;
+                for (int j = 0; j < 2; ++j) {
+                    const int s = sq * 2 + j;
                     const int m = s * 128 + lg * 32 + lane;
                     const int cr = m / CONV, col = m - cr * CONV;
                     int32_t v[16];
@@ -303,11 +304,13 @@ head_pool_kernel(const HGeom g, const f8::Epilogue ep) {
                 const long long tp1 = g.stats ? clock64() : 0;
                 t_p1 += tp1 - tp0;
                 // ---- phase 2: vertical 3-max, .int(), carry + requantised images ----
-                if (tid < TP * POOLED) {
-                    const int pr = tid / POOLED, pq = tid - pr * POOLED;
-                    int4 mx[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) mx[q] = make_int4(0, 0, 0, 0);
+                if (tid < 2 * TP * POOLED) {
+                    // thread = (pooled pixel, 8-channel half of the 16-channel group)
+                    const int pp = tid >> 1, hf = tid & 1;
+                    const int pr = pp / POOLED, pq = pp - pr * POOLED;
+                    int4 mx[2];
+                    mx[0] = make_int4(0, 0, 0, 0);
+                    mx[1] = make_int4(0, 0, 0, 0);
 #pragma unroll
                     for (int dr = 0; dr < 3; ++dr) {
                         const int cr = 2 * pr + dr;                       // local conv row
@@ -316,49 +319,42 @@ head_pool_kernel(const HGeom g, const f8::Epilogue ep) {
                         const int mc = cr * CONV + 2 * pq;                // conv pixel of the centre
                         const bool need_side = (mc & 31) == 0 && pq > 0;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int4 xv = *reinterpret_cast<const int4 *>(stage + stage_off(e, q));
+                        for (int q = 0; q < 2; ++q) {
+                            const int4 xv = *reinterpret_cast<const int4 *>(stage + stage_off(e, 2 * hf + q));
                             mx[q].x = max(mx[q].x, xv.x); mx[q].y = max(mx[q].y, xv.y);
                             mx[q].z = max(mx[q].z, xv.z); mx[q].w = max(mx[q].w, xv.w);
                             if (need_side) {
-                                const int4 sv = *reinterpret_cast<const int4 *>(side + ((mc - 1) >> 5) * 64 + q * 16);
+                                const int4 sv = *reinterpret_cast<const int4 *>(side + ((mc - 1) >> 5) * 64 + (2 * hf + q) * 16);
                                 mx[q].x = max(mx[q].x, sv.x); mx[q].y = max(mx[q].y, sv.y);
                                 mx[q].z = max(mx[q].z, sv.z); mx[q].w = max(mx[q].w, sv.w);
                             }
                         }
                     }
-                    int32_t r[16];
+                    int32_t r[8];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < 2; ++q) {
                         r[4 * q + 0] = f8::f2i_x86((float)mx[q].x);
                         r[4 * q + 1] = f8::f2i_x86((float)mx[q].y);
                         r[4 * q + 2] = f8::f2i_x86((float)mx[q].z);
                         r[4 * q + 3] = f8::f2i_x86((float)mx[q].w);
                     }
                     const size_t opix = ((size_t)img * POOLED + (pr0 + pr)) * POOLED + pq;
-                    const size_t o = opix * ep.cout_pad + grp * 16;
+                    const int ch0 = grp * 16 + hf * 8;
+                    const size_t o = opix * ep.cout_pad + ch0;
                     if (ep.carry_out) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            *reinterpret_cast<int4 *>(ep.carry_out + f8::carry_off(opix, grp * 16 + 4 * q, ep.cout_pad)) =
+                        for (int q = 0; q < 2; ++q)
+                            *reinterpret_cast<int4 *>(ep.carry_out + f8::carry_off(opix, ch0 + 4 * q, ep.cout_pad)) =
                                 make_int4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
                     }
-                    if (ep.out0) {
-                        uint4 w;
-                        w.x = f8::requant_pack4(r[0], r[1], r[2], r[3], ep.shift0, ep.signed0);
-                        w.y = f8::requant_pack4(r[4], r[5], r[6], r[7], ep.shift0, ep.signed0);
-                        w.z = f8::requant_pack4(r[8], r[9], r[10], r[11], ep.shift0, ep.signed0);
-                        w.w = f8::requant_pack4(r[12], r[13], r[14], r[15], ep.shift0, ep.signed0);
-                        *reinterpret_cast<uint4 *>(ep.out0 + o) = w;
-                    }
-                    if (ep.out1) {
-                        uint4 w;
-                        w.x = f8::requant_pack4(r[0], r[1], r[2], r[3], ep.shift1, ep.signed1);
-                        w.y = f8::requant_pack4(r[4], r[5], r[6], r[7], ep.shift1, ep.signed1);
-                        w.z = f8::requant_pack4(r[8], r[9], r[10], r[11], ep.shift1, ep.signed1);
-                        w.w = f8::requant_pack4(r[12], r[13], r[14], r[15], ep.shift1, ep.signed1);
-                        *reinterpret_cast<uint4 *>(ep.out1 + o) = w;
-                    }
+                    if (ep.out0)
+                        *reinterpret_cast<uint2 *>(ep.out0 + o) =
+                            make_uint2(f8::requant_pack4(r[0], r[1], r[2], r[3], ep.shift0, ep.signed0),
+                                       f8::requant_pack4(r[4], r[5], r[6], r[7], ep.shift0, ep.signed0));
+                    if (ep.out1)
+                        *reinterpret_cast<uint2 *>(ep.out1 + o) =
+                            make_uint2(f8::requant_pack4(r[0], r[1], r[2], r[3], ep.shift1, ep.signed1),
+                                       f8::requant_pack4(r[4], r[5], r[6], r[7], ep.shift1, ep.signed1));
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
                 if (g.stats) t_p2 += clock64() - tp1;
