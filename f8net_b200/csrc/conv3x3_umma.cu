@@ -45,7 +45,9 @@ using namespace f8u;
 // cycles); BN = 64 (MB = 4) serves the 64-channel layers.
 __host__ __device__ constexpr int mb_for(int bn) { return 256 / bn; }
 // Ring depths.
-__host__ __device__ constexpr int sb_for(int bn, bool plain) { (void)plain; return bn == 64 ? 12 : 8; }
+// weight ring: one stage = one filter row (3 taps x 64 channels x BN columns), so the MMA warp
+// synchronises three times per 64-channel group instead of nine
+__host__ __device__ constexpr int sb_for(int bn, bool plain) { (void)plain; return bn == 64 ? 4 : 3; }
 __host__ __device__ constexpr int sa_for(int stride) { return stride == 2 ? 2 : 3; }   // patch ring (a stride-2 patch is 4 parity planes)
 // a patch stage is signalled once A_LAG younger stages are issued (never the whole ring)
 __host__ __device__ constexpr int a_lag_for(int stride) { return stride == 2 ? 0 : 1; }
@@ -63,6 +65,7 @@ struct PGeom {
     int Hin, Win;           // input size per image (= H, W for stride 1; 2H, 2W for stride 2)
     int plane_slots;        // slots of one parity plane (stride 1: the only plane)
     int PW;                 // W + 1
+    uint32_t mPW, mHP;      // floor(2^32 / d) + 1 for d = PW, H + 1: n / d == __umulhi(n, m) while n * d < 2^32
     int tm;                 // 128 * MB
     int slots;              // planes * plane_slots
     int slots_pad;          // slots rounded up to 8
@@ -96,13 +99,14 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
     constexpr int SB = sb_for(BN, PLAIN_U8);
     constexpr int SA = sa_for(STRIDE);
     constexpr int A_LAG = a_lag_for(STRIDE);
-    constexpr int B_TILE = BN * 64;
+    constexpr int B_TILE = BN * 64;                       // one tap
+    constexpr int B_STAGE = 3 * B_TILE;                   // one filter row
     constexpr int CW = BN / (EPI_WARPS / 4);               // columns per epilogue warp slice (plain path)
     const int a_stage = g.slots_pad * 64;                 // bytes of one patch stage
     const uint32_t lbo_a = (uint32_t)g.slots_pad * 16;
     const uint32_t smem_base = f8::smem_u32(smem);
     const uint32_t sb_base = smem_base + SA * a_stage;
-    const uint32_t bar_base = sb_base + SB * B_TILE;
+    const uint32_t bar_base = sb_base + SB * B_STAGE;
     // a_full[SA] a_empty[SA] b_full[SB] b_empty[SB] acc_full[2] acc_empty[2]
     auto a_full = [&](int s) { return bar_base + (uint32_t)s * 8; };
     auto a_empty = [&](int s) { return bar_base + (uint32_t)(SA + s) * 8; };
@@ -111,7 +115,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
     auto acc_full = [&](int b) { return bar_base + (uint32_t)(2 * SA + 2 * SB + b) * 8; };
     auto acc_empty = [&](int b) { return bar_base + (uint32_t)(2 * SA + 2 * SB + 2 + b) * 8; };
     constexpr int NBARS = 2 * SA + 2 * SB + 4;
-    uint8_t *after = smem + SA * a_stage + SB * B_TILE + NBARS * 8;
+    uint8_t *after = smem + SA * a_stage + SB * B_STAGE + NBARS * 8;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(after);
     int32_t *sbias = reinterpret_cast<int32_t *>(after + 16);
 
@@ -157,9 +161,9 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
                     // laid out like a stride-1 patch of the OUTPUT-sized grid
                     const int plane = STRIDE == 2 ? pl / g.plane_slots : 0;
                     const int pi = pi0 + (pl - plane * g.plane_slots);
-                    const int Yp = pi / g.PW;
+                    const int Yp = (int)__umulhi((uint32_t)pi, g.mPW);
                     const int xs = pi - Yp * g.PW;
-                    const int img = Yp / HP;
+                    const int img = (int)__umulhi((uint32_t)Yp, g.mHP);
                     const int yy = Yp - img * HP;
                     if (xs >= 1 && yy >= 1 && img < g.N) {
                         const int y = STRIDE == 2 ? 2 * (yy - 1) + (plane >> 1) : yy - 1;
@@ -217,16 +221,19 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
                 const int st = it / g.ntiles_n;
                 const int n0 = (it - st * g.ntiles_n) * BN;
                 for (int cg = 0; cg < ncg; ++cg)
-                    for (int tap = 0; tap < 9; ++tap) {
+                    for (int fr = 0; fr < 3; ++fr) {
                         F8_TIMED_WAIT(w_bempty, mbar_wait(b_empty(slot), phase ^ 1));
-                        const uint32_t sb = sb_base + slot * B_TILE;
-                        mbar_expect_tx(b_full(slot), B_TILE);
+                        const uint32_t sb = sb_base + slot * B_STAGE;
+                        mbar_expect_tx(b_full(slot), B_STAGE);
                         mbar_arrive(b_full(slot));
-                        const size_t kc = (size_t)(tap * g.C + cg * 64) >> 4;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            bulk_g2s(sb + j * (BN * 16), g.wpack + ((kc + j) * g.wrows + n0) * 16,
-                                     BN * 16, b_full(slot));
+                        for (int fs = 0; fs < 3; ++fs) {
+                            const size_t kc = (size_t)((fr * 3 + fs) * g.C + cg * 64) >> 4;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                bulk_g2s(sb + fs * B_TILE + j * (BN * 16), g.wpack + ((kc + j) * g.wrows + n0) * 16,
+                                         BN * 16, b_full(slot));
+                        }
                         if (++slot == SB) { slot = 0; phase ^= 1; }
                     }
             }
@@ -244,6 +251,17 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
         const uint32_t a_lbo_field = (lbo_a >> 4) << 16;
         constexpr uint32_t b_lbo_field = ((uint32_t)(BN * 16) >> 4) << 16;
         int aslot = 0, aphase = 0, bslot = 0, bphase = 0, buf = 0, acc_phase = 0;
+        // start-address offsets of the taps in descriptor units (16 B = one slot)
+        uint32_t tap_row[3], tap_col[2];
+        if (STRIDE == 2) {
+            // row fr: plane bit (fr != 1) * 2, plus one padded row for fr > 0; column fs: plane bit
+            // (fs != 1), plus one padded column for fs > 0
+            tap_row[0] = 2u * g.plane_slots; tap_row[1] = (uint32_t)g.PW; tap_row[2] = 2u * g.plane_slots + g.PW;
+            tap_col[0] = (uint32_t)g.plane_slots; tap_col[1] = (uint32_t)g.plane_slots + 1u;
+        } else {
+            tap_row[0] = 0u; tap_row[1] = (uint32_t)g.PW; tap_row[2] = 2u * g.PW;
+            tap_col[0] = tap_col[1] = 0u;
+        }
         long long w_acc = 0, w_a = 0, w_b = 0;
         const long long t_begin = clock64();
         long long t_first_a = 0;
@@ -255,28 +273,32 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
                 F8_TIMED_WAIT(w_a, mbar_wait(a_full(aslot), aphase));
                 if (g.stats && t_first_a == 0) t_first_a = clock64();
                 const uint32_t sa = smem_base + aslot * a_stage;
-                for (int tap = 0; tap < 9; ++tap) {
+                const uint32_t first = (uint32_t)(cg != 0);
+#pragma unroll
+                for (int fr = 0; fr < 3; ++fr) {
                     F8_TIMED_WAIT(w_b, mbar_wait(b_full(bslot), bphase));
                     tc_fence_after();
-                    const uint32_t sb = sb_base + bslot * B_TILE;
-                    const int r = tap / 3, s = tap - r * 3;
-                    // slot offset of tap (r, s): stride 1: r*PW + s; stride 2: parity plane ((r != 1), (s != 1))
-                    // and a one-row / one-column step for r > 0 / s > 0
-                    const int tap_slots = STRIDE == 2 ? (((r != 1) * 2 + (s != 1)) * g.plane_slots + (r > 0) * g.PW + (s > 0))
-                                                      : r * g.PW + s;
-                    const uint32_t a_lo0 = (((sa + (uint32_t)tap_slots * 16) & 0x3ffffu) >> 4) | a_lbo_field;
-                    const uint32_t b_lo0 = ((sb & 0x3ffffu) >> 4) | b_lbo_field;
-                    const uint32_t first = (uint32_t)((cg | tap) != 0);
+                    const uint32_t sb = sb_base + bslot * B_STAGE;
+                    const uint32_t a_row = (((sa & 0x3ffffu) >> 4) | a_lbo_field) + tap_row[fr];
+                    const uint32_t b_row = ((sb & 0x3ffffu) >> 4) | b_lbo_field;
                     if (elect_one()) {
 #pragma unroll
-                        for (int i = 0; i < MB; ++i) {
+                        for (int fs = 0; fs < 3; ++fs) {
+                            // slot offset of tap (fr, fs): stride 1: fr*PW + fs; stride 2: parity plane
+                            // ((fr != 1), (fs != 1)) and a one-row / one-column step for fr > 0 / fs > 0
+                            const uint32_t a_lo0 = a_row + (STRIDE == 2 ? (fs == 0 ? tap_col[0] : (fs == 1 ? 1u : tap_col[1]))
+                                                                        : (uint32_t)fs);
+                            const uint32_t b_lo0 = b_row + (uint32_t)(fs * (B_TILE >> 4));
 #pragma unroll
-                            for (int h = 0; h < 2; ++h)
-                                umma_i8_lohi(tacc + (uint32_t)(i * BN),
-                                             a_lo0 + (uint32_t)((i * 2048) >> 4) + (uint32_t)h * ((2 * lbo_a) >> 4),
-                                             desc_hi,
-                                             b_lo0 + (uint32_t)h * ((2 * BN * 16) >> 4), desc_hi, idesc,
-                                             h ? 1u : first);
+                            for (int i = 0; i < MB; ++i) {
+#pragma unroll
+                                for (int h = 0; h < 2; ++h)
+                                    umma_i8_lohi(tacc + (uint32_t)(i * BN),
+                                                 a_lo0 + (uint32_t)((i * 2048) >> 4) + (uint32_t)h * ((2 * lbo_a) >> 4),
+                                                 desc_hi,
+                                                 b_lo0 + (uint32_t)h * ((2 * BN * 16) >> 4), desc_hi, idesc,
+                                                 (h | fs | fr) ? 1u : first);
+                            }
                         }
                         umma_commit(b_empty(bslot));
                     }
@@ -327,9 +349,9 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
 #pragma unroll
                     for (int i = 0; i < MB; ++i) {
                         const int m = st * TM + i * 128 + row;
-                        const int Yo = m / g.PW;
+                        const int Yo = (int)__umulhi((uint32_t)m, g.mPW);
                         const int xo = m - Yo * g.PW;
-                        const int img = Yo / HP;
+                        const int img = (int)__umulhi((uint32_t)Yo, g.mHP);
                         const int y = Yo - img * HP;
                         const bool valid = xo < g.W && y < g.H && img < g.N;
                         const size_t opix = ((size_t)(img * g.H + y) * g.W + xo);
@@ -363,9 +385,9 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
                 const int cbase = (u - seg * UPS) * 64;      // first column of the unit inside the tile
                 auto unit_pixel = [&](int st_) -> int {      // output pixel of this thread's row, -1 = dropped
                     const int m = st_ * TM + seg * 128 + row;
-                    const int Yo = m / g.PW;
+                    const int Yo = (int)__umulhi((uint32_t)m, g.mPW);
                     const int xo = m - Yo * g.PW;
-                    const int img = Yo / HP;
+                    const int img = (int)__umulhi((uint32_t)Yo, g.mHP);
                     const int y = Yo - img * HP;
                     return (xo < g.W && y < g.H && img < g.N) ? (img * g.H + y) * g.W + xo : -1;
                 };
@@ -484,13 +506,14 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     const bool plain = f8::epilogue_is_plain_u8(ep);
     constexpr int SA = sa_for(STRIDE);
     const int SB = sb_for(BN, plain);
-    const size_t smem_bytes = (size_t)SA * slots_pad * 64 + (size_t)SB * B_TILE +
+    const size_t smem_bytes = (size_t)SA * slots_pad * 64 + (size_t)SB * 3 * B_TILE +
                               (2 * SA + 2 * SB + 4) * 8 + 16 + 2 * BN * 4;
     if (smem_bytes > 227 * 1024) return F8_ERR_UNSUPPORTED;
     // the kernel owns all 512 TMEM columns: keep a second CTA off the SM
     const size_t smem_launch = smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes;
     const long long lin = (long long)a.n * (a.hout + 1) * PW;     // padded linear output space
-    if (lin > 0x7fffffffLL - TM) return F8_ERR_UNSUPPORTED;
+    // (the magic-number divisions need (lin + TM) * PW < 2^32)
+    if ((lin + TM) * (long long)(PW > a.hout + 1 ? PW : a.hout + 1) >= 0xffffffffLL) return F8_ERR_UNSUPPORTED;
     const f8host::DensePack pk = f8host::dense_pack_geometry(a.cin_pad, a.cout_pad, 3, 3);
     PGeom g{};
     g.in = static_cast<const uint8_t *>(a.in);
@@ -500,6 +523,8 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     g.Hin = a.hin; g.Win = a.win;
     g.plane_slots = plane_slots;
     g.PW = PW;
+    g.mPW = (uint32_t)(0x100000000ULL / (uint32_t)PW) + 1u;
+    g.mHP = (uint32_t)(0x100000000ULL / (uint32_t)(a.hout + 1)) + 1u;
     g.tm = TM;
     g.slots = slots;
     g.slots_pad = slots_pad;
