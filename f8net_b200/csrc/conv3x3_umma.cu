@@ -32,8 +32,10 @@
 //   | warp 21 lane 0 weight-tile loader (cp.async.bulk).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <type_traits>
 
-#include "umma_common.cuh"
+#include "tma_common.cuh"
 
 namespace {
 
@@ -55,7 +57,6 @@ __host__ __device__ constexpr int a_lag_for(int stride) { return stride == 2 ? 0
 // exact integer requantisation is instruction-bound, hence 16 warps
 __host__ __device__ constexpr int epi_warps_for(bool plain) { (void)plain; return 16; }
 constexpr int LOADERS = 128;
-constexpr int MAX_SLOT_ITERS = 10;     // ceil(slots / 128): 512 + 2*PW + 2 (stride 1) or 4 * (256 + PW + 2) (stride 2)
 
 struct PGeom {
     const uint8_t *in;
@@ -72,6 +73,10 @@ struct PGeom {
     int n_super;            // tiles along the padded linear space
     int ntiles_n;           // cout_pad / BN (rounded up)
     long long *stats;       // debug (F8_STATS=1): per-CTA wait-cycle counters, else nullptr
+    int probe;              // debug (F8_PROBE): timing probes, WRONG results
+    int lx;                 // log2 of the 8-slot items per padded row (PW <= 8 << lx)
+    int BY;                 // TMA path: padded rows per box (1, or H + 1 = a whole image)
+    int box_slots;          // TMA path: BY * PW
 };
 
 #define F8_TIMED_WAIT(acc, stmt)                 \
@@ -87,8 +92,12 @@ struct PGeom {
 
 template <int BN, bool A_SIGNED, bool PLAIN_U8, int STRIDE>
 __global__ void __launch_bounds__((epi_warps_for(PLAIN_U8) + 6) * 32, 1)
-conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
-    extern __shared__ __align__(128) uint8_t smem[];
+conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    // stride 1: the patch arrives by TMA in the 64-byte-swizzled K-major layout [slot][64 B]
+    // (stage bases 1024-byte aligned); stride 2: cp.async into [16-byte chunk][slot][16 B]
+    constexpr bool TMA = STRIDE == 1;
+    uint8_t *smem = smem_raw + ((1024u - (f8::smem_u32(smem_raw) & 1023u)) & 1023u);
     constexpr int EPI_WARPS = epi_warps_for(PLAIN_U8);
     constexpr int EPI_THREADS = EPI_WARPS * 32;
     constexpr int LOADER_WARP0 = EPI_WARPS;
@@ -128,7 +137,8 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
 
     if (warp == MMA_WARP) {
         if (lane == 0) {
-            for (int s = 0; s < SA; ++s) { mbar_init(a_full(s), LOADERS); mbar_init(a_empty(s), 1); }
+            for (int s = 0; s < SA; ++s) { mbar_init(a_full(s), TMA ? 1 : LOADERS); mbar_init(a_empty(s), 1); }
+            if (TMA) tma_prefetch_desc(&tmap);
             for (int s = 0; s < SB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
             for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), EPI_THREADS); }
             fence_barrier_init();
@@ -141,52 +151,121 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= LOADER_WARP0 && warp < MMA_WARP) {
-        // =========================== patch loaders ================================
+    if (TMA && warp >= LOADER_WARP0 && warp < MMA_WARP) {
+        // =========================== patch loader (TMA) ===========================
+        // One warp; lane l issues the tensor load of box l of the stage: a box is one padded row
+        // (or one whole padded image when that is at most 64 slots) of 64 channels, start
+        // coordinate x = -1 / y = -1: the zero column, the zero row and everything outside the
+        // batch are the TMA's out-of-bounds zero fill.
+        if (warp == LOADER_WARP0) {
+            int slot = 0, phase = 0;
+            long long w_empty = 0;
+            const long long t_begin = clock64();
+            const int PW = g.PW, BY = g.BY, BS = g.box_slots;
+            for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+                const int st = it / g.ntiles_n;
+                const int pi0 = st * TM;
+                const int Y0 = (int)__umulhi((uint32_t)pi0, g.mPW);
+                const int Ylast = (int)__umulhi((uint32_t)(pi0 + g.plane_slots - 1), g.mPW);
+                const int Yb0 = BY == 1 ? Y0 : (int)__umulhi((uint32_t)Y0, g.mHP) * HP;
+                const int nbox = BY == 1 ? Ylast - Yb0 + 1 : (int)__umulhi((uint32_t)(Ylast - Yb0), g.mHP) + 1;
+                const int Yb = Yb0 + lane * BY;
+                const int img = (int)__umulhi((uint32_t)Yb, g.mHP);
+                const int yy = Yb - img * HP;
+                for (int cg = 0; cg < ncg; ++cg) {
+                    F8_TIMED_WAIT(w_empty, mbar_wait(a_empty(slot), phase ^ 1));
+                    if (lane == 0) {
+                        mbar_expect_tx(a_full(slot), (uint32_t)(nbox * BS * 64));
+                        mbar_arrive(a_full(slot));
+                    }
+                    __syncwarp();
+                    if (lane < nbox)
+                        tma_load_4d(smem_base + slot * a_stage + lane * BS * 64, &tmap, cg * 64, -1, yy - 1, img,
+                                    a_full(slot));
+                    if (++slot == SA) { slot = 0; phase ^= 1; }
+                }
+            }
+            if (g.stats && lane == 0) {
+                g.stats[blockIdx.x * 16 + 0] = clock64() - t_begin;
+                g.stats[blockIdx.x * 16 + 1] = w_empty;
+            }
+        }
+    } else if (warp >= LOADER_WARP0 && warp < MMA_WARP) {
+        // =========================== patch loaders (cp.async) =====================
         const int lt = tid - LOADER_WARP0 * 32;
-        int slot = 0, phase = 0, aslot = 0, issued = 0;
+        int slot = 0, phase = 0;
         long long w_empty = 0, w_cp = 0;
         const long long t_begin = clock64();
+        // Row-wise staging.  A batch is 8 "items" of 8 slots x 64 B (one warp instruction each:
+        // four consecutive lanes fetch the four 16-byte chunks of a slot, so an instruction reads
+        // 8 pixels x 64 contiguous bytes = whole sectors, and writes four 128-byte runs of shared
+        // memory).  A padded row holds XI = 2^LX items, so a batch covers 8 >> LX rows; the row
+        // is decoded once (warp uniform) and the 8 cp.async of a batch are issued back to back
+        // from 8 distinct address registers (cp.async holds its address registers until the
+        // request drains: reusing one stalls the warp).
+        constexpr int PLANES = STRIDE == 2 ? 4 : 1;
+        const int lw = lt >> 5;
+        const int jc = lane & 3, xl = lane >> 2;
+        const int PW = g.PW, Hin = g.Hin, Win = g.Win, C = g.C, NI = g.N, plane_slots = g.plane_slots;
+        const uint32_t mPW = g.mPW, mHP = g.mHP;
+        const uint8_t *const in = g.in + jc * 16;
+        const int lx = g.lx;                               // log2(items per row), 0..3
+        const int rows_per_batch = 8 >> lx;
+        int issued = 0, aslot = 0;
+        auto stage_rows = [&](auto lx_tag, uint32_t sa, int cg, int Y0, int pi0, int nrows) {
+            constexpr int LX = decltype(lx_tag)::value;
+            constexpr int RB = 8 >> LX, XI = 1 << LX;
+            const int nb = (nrows + RB - 1) / RB;                    // batches per plane
+#pragma unroll 1
+            for (int q = lw; q < nb * PLANES; q += 4) {
+                int plane = 0, bq = q;
+                if (STRIDE == 2) { while (bq >= nb) { bq -= nb; ++plane; } }
+                const uint8_t *src[8];
+                uint32_t dst[8];
+                uint32_t live = 0, ok = 0;
+#pragma unroll
+                for (int rr = 0; rr < RB; ++rr) {
+                    const int r = bq * RB + rr;
+                    const int Yp = Y0 + r;
+                    const int img = (int)__umulhi((uint32_t)Yp, mHP);
+                    const int yy = Yp - img * HP;
+                    const int y = STRIDE == 2 ? 2 * (yy - 1) + (plane >> 1) : yy - 1;
+                    const bool rowok = r < nrows && yy >= 1 && img < NI && y < Hin;
+                    const int p0 = Yp * PW - pi0;                    // in-plane slot of xs = 0
+                    const int x0 = STRIDE == 2 ? 2 * (xl - 1) + (plane & 1) : xl - 1;
+                    const uint8_t *rowbase = in + ((size_t)(img * Hin + y) * Win + x0) * C + cg * 64;
+                    const uint32_t d0 = sa + (uint32_t)((plane * plane_slots + p0 + xl) * 16);
+#pragma unroll
+                    for (int xi = 0; xi < XI; ++xi) {
+                        const int b = rr * XI + xi;
+                        const int xs = xi * 8 + xl;
+                        const int pin = p0 + xs;
+                        const int x = x0 + (STRIDE == 2 ? 16 : 8) * xi;
+                        const bool lv = r < nrows && xs < PW && pin >= 0 && pin < plane_slots;
+                        const bool k = lv && rowok && xs >= 1 && x < Win;
+                        live |= lv ? (1u << b) : 0u;
+                        ok |= k ? (1u << b) : 0u;
+                        src[b] = k ? rowbase + (size_t)((STRIDE == 2 ? 16 : 8) * xi) * C : g.in;
+                        dst[b] = d0 + (uint32_t)(xi * 128);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < 8; ++b)
+                    if (live & (1u << b)) cp_async16(dst[b], src[b], (ok >> b) & 1u);
+            }
+        };
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
             const int st = it / g.ntiles_n;
             const int pi0 = st * TM;
-            // decode this thread's slots once per tile: global byte offset of the pixel or -1
-            long long off[MAX_SLOT_ITERS];
-#pragma unroll
-            for (int k = 0; k < MAX_SLOT_ITERS; ++k) {
-                const int pl = lt + k * LOADERS;
-                off[k] = -1;
-                if (pl < g.slots) {
-                    // stride 2: the patch is four parity planes (input row parity, column parity), each
-                    // laid out like a stride-1 patch of the OUTPUT-sized grid
-                    const int plane = STRIDE == 2 ? pl / g.plane_slots : 0;
-                    const int pi = pi0 + (pl - plane * g.plane_slots);
-                    const int Yp = (int)__umulhi((uint32_t)pi, g.mPW);
-                    const int xs = pi - Yp * g.PW;
-                    const int img = (int)__umulhi((uint32_t)Yp, g.mHP);
-                    const int yy = Yp - img * HP;
-                    if (xs >= 1 && yy >= 1 && img < g.N) {
-                        const int y = STRIDE == 2 ? 2 * (yy - 1) + (plane >> 1) : yy - 1;
-                        const int x = STRIDE == 2 ? 2 * (xs - 1) + (plane & 1) : xs - 1;
-                        if (y < g.Hin && x < g.Win)
-                            off[k] = ((long long)(img * g.Hin + y) * g.Win + x) * g.C;
-                    }
-                }
-            }
+            const int Y0 = (int)__umulhi((uint32_t)pi0, mPW);
+            const int nrows = (int)__umulhi((uint32_t)(pi0 + plane_slots - 1), mPW) - Y0 + 1;
             for (int cg = 0; cg < ncg; ++cg) {
                 F8_TIMED_WAIT(w_empty, mbar_wait(a_empty(slot), phase ^ 1));
-                const uint32_t sa = smem_base + slot * a_stage;
-#pragma unroll
-                for (int k = 0; k < MAX_SLOT_ITERS; ++k) {
-                    const int pl = lt + k * LOADERS;
-                    if (pl < g.slots) {
-                        const bool ok = off[k] >= 0;
-                        const uint8_t *src = ok ? g.in + off[k] + cg * 64 : g.in;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            cp_async16(sa + j * lbo_a + pl * 16, src + j * 16, ok);
-                    }
-                }
+                const uint32_t sa = smem_base + slot * a_stage + jc * lbo_a;
+                if (lx == 3) stage_rows(std::integral_constant<int, 3>{}, sa, cg, Y0, pi0, nrows);
+                else if (lx == 2) stage_rows(std::integral_constant<int, 2>{}, sa, cg, Y0, pi0, nrows);
+                else if (lx == 1) stage_rows(std::integral_constant<int, 1>{}, sa, cg, Y0, pi0, nrows);
+                else stage_rows(std::integral_constant<int, 0>{}, sa, cg, Y0, pi0, nrows);
                 cp_async_commit();
                 if (++slot == SA) { slot = 0; phase ^= 1; }
                 // signal a stage as soon as its bytes have landed, WITHOUT first needing a free
@@ -206,6 +285,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
             mbar_arrive(a_full(aslot));
             if (++aslot == SA) aslot = 0;
         }
+        (void)rows_per_batch;
         if (g.stats && lt == 0) {
             g.stats[blockIdx.x * 16 + 0] = clock64() - t_begin;
             g.stats[blockIdx.x * 16 + 1] = w_empty;
@@ -248,7 +328,10 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
         // Descriptor high words are loop constants, low words advance by 32-bit adds.
         constexpr uint32_t idesc = instr_desc(A_SIGNED, BN);
         constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);          // SBO = 128 B, version 1
-        const uint32_t a_lbo_field = (lbo_a >> 4) << 16;
+        // TMA patch: SWIZZLE_64B (layout type 4), SBO = 8 rows x 64 B, LBO unused
+        constexpr uint32_t desc_hi_a = TMA ? ((512u >> 4) | (1u << 14) | (4u << 29)) : desc_hi;
+        constexpr uint32_t SLOT16 = TMA ? 4u : 1u;                      // one slot in descriptor units of 16 B
+        const uint32_t a_lbo_field = TMA ? (1u << 16) : ((lbo_a >> 4) << 16);
         constexpr uint32_t b_lbo_field = ((uint32_t)(BN * 16) >> 4) << 16;
         int aslot = 0, aphase = 0, bslot = 0, bphase = 0, buf = 0, acc_phase = 0;
         // start-address offsets of the taps in descriptor units (16 B = one slot)
@@ -259,7 +342,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
             tap_row[0] = 2u * g.plane_slots; tap_row[1] = (uint32_t)g.PW; tap_row[2] = 2u * g.plane_slots + g.PW;
             tap_col[0] = (uint32_t)g.plane_slots; tap_col[1] = (uint32_t)g.plane_slots + 1u;
         } else {
-            tap_row[0] = 0u; tap_row[1] = (uint32_t)g.PW; tap_row[2] = 2u * g.PW;
+            tap_row[0] = 0u; tap_row[1] = SLOT16 * (uint32_t)g.PW; tap_row[2] = SLOT16 * 2u * g.PW;
             tap_col[0] = tap_col[1] = 0u;
         }
         long long w_acc = 0, w_a = 0, w_b = 0;
@@ -269,10 +352,17 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
             F8_TIMED_WAIT(w_acc, mbar_wait(acc_empty(buf), acc_phase ^ 1));
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(buf * MB * BN);
+            int tile_soff = 0;                           // TMA: first slot of the tile inside its box-aligned patch
+            if (TMA) {
+                const int pi0 = (it / g.ntiles_n) * TM;
+                const int Y0 = (int)__umulhi((uint32_t)pi0, g.mPW);
+                const int Yb0 = g.BY == 1 ? Y0 : (int)__umulhi((uint32_t)Y0, g.mHP) * HP;
+                tile_soff = pi0 - Yb0 * g.PW;
+            }
             for (int cg = 0; cg < ncg; ++cg) {
                 F8_TIMED_WAIT(w_a, mbar_wait(a_full(aslot), aphase));
                 if (g.stats && t_first_a == 0) t_first_a = clock64();
-                const uint32_t sa = smem_base + aslot * a_stage;
+                const uint32_t sa = smem_base + aslot * a_stage + (TMA ? (uint32_t)tile_soff * 64u : 0u);
                 const uint32_t first = (uint32_t)(cg != 0);
 #pragma unroll
                 for (int fr = 0; fr < 3; ++fr) {
@@ -284,18 +374,20 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
                     if (elect_one()) {
 #pragma unroll
                         for (int fs = 0; fs < 3; ++fs) {
+                            if (g.probe & 32) continue;
                             // slot offset of tap (fr, fs): stride 1: fr*PW + fs; stride 2: parity plane
                             // ((fr != 1), (fs != 1)) and a one-row / one-column step for fr > 0 / fs > 0
                             const uint32_t a_lo0 = a_row + (STRIDE == 2 ? (fs == 0 ? tap_col[0] : (fs == 1 ? 1u : tap_col[1]))
-                                                                        : (uint32_t)fs);
+                                                                        : SLOT16 * (uint32_t)fs);
                             const uint32_t b_lo0 = b_row + (uint32_t)(fs * (B_TILE >> 4));
 #pragma unroll
                             for (int i = 0; i < MB; ++i) {
 #pragma unroll
                                 for (int h = 0; h < 2; ++h)
                                     umma_i8_lohi(tacc + (uint32_t)(i * BN),
-                                                 a_lo0 + (uint32_t)((i * 2048) >> 4) + (uint32_t)h * ((2 * lbo_a) >> 4),
-                                                 desc_hi,
+                                                 a_lo0 + (TMA ? (uint32_t)(i * 512 + h * 2)
+                                                              : (uint32_t)((i * 2048) >> 4) + (uint32_t)h * ((2 * lbo_a) >> 4)),
+                                                 desc_hi_a,
                                                  b_lo0 + (uint32_t)h * ((2 * BN * 16) >> 4), desc_hi, idesc,
                                                  (h | fs | fr) ? 1u : first);
                             }
@@ -345,7 +437,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep) {
             if (PLAIN_U8) {
                 F8_TIMED_WAIT(w_full, mbar_wait(acc_full(buf), acc_phase));
                 tc_fence_after();
-                if (cw0 < ncols) {
+                if (cw0 < ncols && !(g.probe & 16)) {
 #pragma unroll
                     for (int i = 0; i < MB; ++i) {
                         const int m = st * TM + i * 128 + row;
@@ -480,11 +572,18 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     constexpr int MB = mb_for(BN);
     constexpr int TM = 128 * MB;
     constexpr int B_TILE = BN * 64;
-    const int PW = a.wout + 1;
+    constexpr bool TMA = STRIDE == 1;
+    // TMA path: an even pitch keeps every box (one padded row of PW slots x 64 B) 128-byte aligned
+    const int PW = TMA ? ((a.wout + 2) & ~1) : a.wout + 1;
     const int plane_slots = TM + (STRIDE == 2 ? PW : 2 * PW) + 2;
     const int slots = (STRIDE == 2 ? 4 : 1) * plane_slots;
-    if ((slots + LOADERS - 1) / LOADERS > MAX_SLOT_ITERS) return F8_ERR_UNSUPPORTED;
-    const int slots_pad = (slots + 7) / 8 * 8;
+    const int HPh = a.hout + 1;
+    const int BY = (TMA && HPh * PW <= 64) ? HPh : 1;           // rows per TMA box
+    const int box_slots = BY * PW;
+    // a stage holds the boxes covering any tile's slot range: at most (range / box) + 2 boxes
+    const int max_boxes = (plane_slots + box_slots - 1) / box_slots + 1;
+    if (TMA && max_boxes > 32) return F8_ERR_UNSUPPORTED;
+    const int slots_pad = TMA ? (max_boxes * box_slots + 15) / 16 * 16 : (slots + 7) / 8 * 8;
     f8::Epilogue ep{};
     ep.bias = a.bias;
     ep.carry_in = a.carry_in;
@@ -497,17 +596,19 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     ep.shift1 = a.out_shift[1]; ep.signed1 = a.out_signed[1];
     ep.cout = a.cout;
     ep.cout_pad = a.cout_pad;
+    int probe_bits = 0;
     if (const char *probe = getenv("F8_PROBE")) {   // timing probes only: WRONG results
         const int pv = atoi(probe);
         if (pv & 1) ep.carry_in = nullptr;
         if (pv & 2) ep.carry_out = nullptr;
         if (pv & 4) ep.out0 = nullptr;
+        probe_bits = pv;
     }
     const bool plain = f8::epilogue_is_plain_u8(ep);
     constexpr int SA = sa_for(STRIDE);
     const int SB = sb_for(BN, plain);
     const size_t smem_bytes = (size_t)SA * slots_pad * 64 + (size_t)SB * 3 * B_TILE +
-                              (2 * SA + 2 * SB + 4) * 8 + 16 + 2 * BN * 4;
+                              (2 * SA + 2 * SB + 4) * 8 + 16 + 2 * BN * 4 + 1024;     // + base alignment slack
     if (smem_bytes > 227 * 1024) return F8_ERR_UNSUPPORTED;
     // the kernel owns all 512 TMEM columns: keep a second CTA off the SM
     const size_t smem_launch = smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes;
@@ -523,6 +624,11 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     g.Hin = a.hin; g.Win = a.win;
     g.plane_slots = plane_slots;
     g.PW = PW;
+    g.probe = probe_bits;
+    g.lx = PW <= 8 ? 0 : (PW <= 16 ? 1 : (PW <= 32 ? 2 : 3));
+    g.BY = BY;
+    g.box_slots = box_slots;
+    if (PW > 64) return F8_ERR_UNSUPPORTED;
     g.mPW = (uint32_t)(0x100000000ULL / (uint32_t)PW) + 1u;
     g.mHP = (uint32_t)(0x100000000ULL / (uint32_t)(a.hout + 1)) + 1u;
     g.tm = TM;
@@ -552,12 +658,23 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
         g.stats = stats_dev;
     }
     const unsigned gr = (unsigned)grid;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (TMA) {
+        // the NHWC activation as (C, W, H, N); box = 64 channels x PW pixels x BY rows of one image
+        const uint64_t dims[4] = {(uint64_t)a.cin_pad, (uint64_t)a.win, (uint64_t)a.hin, (uint64_t)a.n};
+        const uint64_t strides[3] = {(uint64_t)a.cin_pad, (uint64_t)a.win * a.cin_pad,
+                                     (uint64_t)a.hin * a.win * a.cin_pad};
+        const uint32_t box[4] = {64u, (uint32_t)PW, (uint32_t)BY, 1u};
+        const int rc = f8host::encode_tmap_u8_4d(&tmap, a.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc != F8_OK) return rc;
+    }
     if (a.in_signed) {
-        if (plain) conv3x3_umma_kernel<BN, true, true, STRIDE><<<gr, (epi_warps_for(true) + 6) * 32, smem_launch, s>>>(g, ep);
-        else conv3x3_umma_kernel<BN, true, false, STRIDE><<<gr, (epi_warps_for(false) + 6) * 32, smem_launch, s>>>(g, ep);
+        if (plain) conv3x3_umma_kernel<BN, true, true, STRIDE><<<gr, (epi_warps_for(true) + 6) * 32, smem_launch, s>>>(g, ep, tmap);
+        else conv3x3_umma_kernel<BN, true, false, STRIDE><<<gr, (epi_warps_for(false) + 6) * 32, smem_launch, s>>>(g, ep, tmap);
     } else {
-        if (plain) conv3x3_umma_kernel<BN, false, true, STRIDE><<<gr, (epi_warps_for(true) + 6) * 32, smem_launch, s>>>(g, ep);
-        else conv3x3_umma_kernel<BN, false, false, STRIDE><<<gr, (epi_warps_for(false) + 6) * 32, smem_launch, s>>>(g, ep);
+        if (plain) conv3x3_umma_kernel<BN, false, true, STRIDE><<<gr, (epi_warps_for(true) + 6) * 32, smem_launch, s>>>(g, ep, tmap);
+        else conv3x3_umma_kernel<BN, false, false, STRIDE><<<gr, (epi_warps_for(false) + 6) * 32, smem_launch, s>>>(g, ep, tmap);
     }
     F8_CUDA(cudaGetLastError());
     if (want_stats) {

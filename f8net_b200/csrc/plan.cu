@@ -14,6 +14,9 @@
 #include <vector>
 
 #include "f8_common.cuh"
+#ifdef F8_WITH_UMMA
+#include "tma_common.cuh"
+#endif
 
 namespace f8host {
 
@@ -31,6 +34,52 @@ int cuda_fail(cudaError_t e, const char *what) {
     (void)cudaGetLastError();
     return F8_ERR_CUDA;
 }
+
+#ifdef F8_WITH_UMMA
+// cuTensorMapEncodeTiled through the runtime's driver entry point: no link dependency on libcuda
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+static int encode_4d(CUtensorMap *out, CUtensorMapDataType dt, const void *base, const uint64_t dims[4],
+                     const uint64_t strides[3], const uint32_t box[4], CUtensorMapSwizzle swizzle) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return F8_ERR_CUDA; }
+    cuuint64_t gd[4] = {dims[0], dims[1], dims[2], dims[3]};
+    cuuint64_t gs[3] = {strides[0], strides[1], strides[2]};
+    cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    const CUresult r = fn(out, dt, 4, const_cast<void *>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): dims %llu %llu %llu %llu box %u %u %u %u", (int)r,
+                  (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                  (unsigned long long)dims[3], box[0], box[1], box[2], box[3]);
+        return F8_ERR_CUDA;
+    }
+    return F8_OK;
+}
+int encode_tmap_u8_4d(CUtensorMap *out, const void *base, const uint64_t dims[4], const uint64_t strides[3],
+                      const uint32_t box[4], CUtensorMapSwizzle swizzle) {
+    return encode_4d(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, base, dims, strides, box, swizzle);
+}
+int encode_tmap_u32_4d(CUtensorMap *out, const void *base, const uint64_t dims[4], const uint64_t strides[3],
+                       const uint32_t box[4]) {
+    return encode_4d(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+#endif
 
 }  // namespace f8host
 

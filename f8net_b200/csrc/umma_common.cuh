@@ -25,10 +25,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(0x989680u)      // suspend-time hint: park the warp instead of polling
             : "memory");
     } while (!done);
 }
