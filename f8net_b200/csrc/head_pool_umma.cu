@@ -383,7 +383,7 @@ namespace f8host {
 
 // a = the head convolution's arguments with hout/wout = the POOLED size (56) and the epilogue
 // of the pooled tensor.  F8_ERR_UNSUPPORTED => the caller runs conv + maxpool separately.
-int launch_head_pool(const f8_conv_args &a, cudaStream_t s) {
+int launch_head_pool_v1(const f8_conv_args &a, cudaStream_t s) {
     if (a.kh != 7 || a.kw != 7 || a.stride != 2 || a.pad != 3 || a.cin_pad != 4 || a.cout != COUT ||
         a.cout_pad != COUT || a.hin != IMG || a.win != IMG || a.hout != POOLED || a.wout != POOLED ||
         a.carry_in != nullptr || a.out_f32 != nullptr)
