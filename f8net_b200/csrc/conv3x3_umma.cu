@@ -66,7 +66,7 @@ struct PGeom {
     int Hin, Win;           // input size per image (= H, W for stride 1; 2H, 2W for stride 2)
     int plane_slots;        // slots of one parity plane (stride 1: the only plane)
     int PW;                 // W + 1
-    uint32_t mPW, mHP;      // floor(2^32 / d) + 1 for d = PW, H + 1: n / d == __umulhi(n, m) while n * d < 2^32
+    uint32_t mPW, mHP, mBY; // floor(2^32 / d) + 1 for d = PW, H + 1, BY: n / d == __umulhi(n, m) while n * d < 2^32
     int tm;                 // 128 * MB
     int slots;              // planes * plane_slots
     int slots_pad;          // slots rounded up to 8
@@ -75,7 +75,10 @@ struct PGeom {
     long long *stats;       // debug (F8_STATS=1): per-CTA wait-cycle counters, else nullptr
     int probe;              // debug (F8_PROBE): timing probes, WRONG results
     int lx;                 // log2 of the 8-slot items per padded row (PW <= 8 << lx)
-    int BY;                 // TMA path: padded rows per box (1, or H + 1 = a whole image)
+    int BY;                 // TMA path: padded rows per box, a divisor of H + 1 (boxes never straddle images)
+    int sa;                 // patch ring depth (<= sa_for(STRIDE))
+    int dw;                 // depthwise mode: output tile n reads only input channel group n, through a
+                            // block-diagonal 64 x 64 weight image per group (wpack = [group][36][64][16])
     int box_slots;          // TMA path: BY * PW
 };
 
@@ -90,7 +93,7 @@ struct PGeom {
         }                                        \
     } while (0)
 
-template <int BN, bool A_SIGNED, bool PLAIN_U8, int STRIDE>
+template <int BN, bool A_SIGNED, bool PLAIN_U8, int STRIDE, bool DW>
 __global__ void __launch_bounds__((epi_warps_for(PLAIN_U8) + 6) * 32, 1)
 conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -106,7 +109,8 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     constexpr int MB = mb_for(BN);
     constexpr int TM = 128 * MB;
     constexpr int SB = sb_for(BN, PLAIN_U8);
-    constexpr int SA = sa_for(STRIDE);
+    constexpr int SA_MAX = sa_for(STRIDE);
+    const int SA = g.sa;
     constexpr int A_LAG = a_lag_for(STRIDE);
     constexpr int B_TILE = BN * 64;                       // one tap
     constexpr int B_STAGE = 3 * B_TILE;                   // one filter row
@@ -118,12 +122,12 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     const uint32_t bar_base = sb_base + SB * B_STAGE;
     // a_full[SA] a_empty[SA] b_full[SB] b_empty[SB] acc_full[2] acc_empty[2]
     auto a_full = [&](int s) { return bar_base + (uint32_t)s * 8; };
-    auto a_empty = [&](int s) { return bar_base + (uint32_t)(SA + s) * 8; };
-    auto b_full = [&](int s) { return bar_base + (uint32_t)(2 * SA + s) * 8; };
-    auto b_empty = [&](int s) { return bar_base + (uint32_t)(2 * SA + SB + s) * 8; };
-    auto acc_full = [&](int b) { return bar_base + (uint32_t)(2 * SA + 2 * SB + b) * 8; };
-    auto acc_empty = [&](int b) { return bar_base + (uint32_t)(2 * SA + 2 * SB + 2 + b) * 8; };
-    constexpr int NBARS = 2 * SA + 2 * SB + 4;
+    auto a_empty = [&](int s) { return bar_base + (uint32_t)(SA_MAX + s) * 8; };
+    auto b_full = [&](int s) { return bar_base + (uint32_t)(2 * SA_MAX + s) * 8; };
+    auto b_empty = [&](int s) { return bar_base + (uint32_t)(2 * SA_MAX + SB + s) * 8; };
+    auto acc_full = [&](int b) { return bar_base + (uint32_t)(2 * SA_MAX + 2 * SB + b) * 8; };
+    auto acc_empty = [&](int b) { return bar_base + (uint32_t)(2 * SA_MAX + 2 * SB + 2 + b) * 8; };
+    constexpr int NBARS = 2 * SA_MAX + 2 * SB + 4;
     uint8_t *after = smem + SA * a_stage + SB * B_STAGE + NBARS * 8;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(after);
     int32_t *sbias = reinterpret_cast<int32_t *>(after + 16);
@@ -132,7 +136,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int total_items = g.n_super * g.ntiles_n;
-    const int ncg = g.C >> 6;
+    const int ncg = DW ? 1 : g.C >> 6;          // 64-channel groups in the K loop
     const int HP = g.H + 1;
 
     if (warp == MMA_WARP) {
@@ -164,11 +168,12 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
             const int PW = g.PW, BY = g.BY, BS = g.box_slots;
             for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
                 const int st = it / g.ntiles_n;
+                const int cg0 = DW ? it - st * g.ntiles_n : 0;
                 const int pi0 = st * TM;
                 const int Y0 = (int)__umulhi((uint32_t)pi0, g.mPW);
                 const int Ylast = (int)__umulhi((uint32_t)(pi0 + g.plane_slots - 1), g.mPW);
-                const int Yb0 = BY == 1 ? Y0 : (int)__umulhi((uint32_t)Y0, g.mHP) * HP;
-                const int nbox = BY == 1 ? Ylast - Yb0 + 1 : (int)__umulhi((uint32_t)(Ylast - Yb0), g.mHP) + 1;
+                const int Yb0 = BY == 1 ? Y0 : (int)__umulhi((uint32_t)Y0, g.mBY) * BY;
+                const int nbox = BY == 1 ? Ylast - Yb0 + 1 : (int)__umulhi((uint32_t)(Ylast - Yb0), g.mBY) + 1;
                 const int Yb = Yb0 + lane * BY;
                 const int img = (int)__umulhi((uint32_t)Yb, g.mHP);
                 const int yy = Yb - img * HP;
@@ -180,7 +185,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                     }
                     __syncwarp();
                     if (lane < nbox)
-                        tma_load_4d(smem_base + slot * a_stage + lane * BS * 64, &tmap, cg * 64, -1, yy - 1, img,
+                        tma_load_4d(smem_base + slot * a_stage + lane * BS * 64, &tmap, (cg0 + cg) * 64, -1, yy - 1, img,
                                     a_full(slot));
                     if (++slot == SA) { slot = 0; phase ^= 1; }
                 }
@@ -299,7 +304,9 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
             const long long t_begin = clock64();
             for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
                 const int st = it / g.ntiles_n;
-                const int n0 = (it - st * g.ntiles_n) * BN;
+                const int n0 = DW ? 0 : (it - st * g.ntiles_n) * BN;
+                const int Ck = DW ? 64 : g.C;
+                const uint8_t *wsrc = g.wpack + (DW ? (size_t)(it - st * g.ntiles_n) * (36 * 64 * 16) : 0);
                 for (int cg = 0; cg < ncg; ++cg)
                     for (int fr = 0; fr < 3; ++fr) {
                         F8_TIMED_WAIT(w_bempty, mbar_wait(b_empty(slot), phase ^ 1));
@@ -308,10 +315,10 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                         mbar_arrive(b_full(slot));
 #pragma unroll
                         for (int fs = 0; fs < 3; ++fs) {
-                            const size_t kc = (size_t)((fr * 3 + fs) * g.C + cg * 64) >> 4;
+                            const size_t kc = (size_t)((fr * 3 + fs) * Ck + cg * 64) >> 4;
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
-                                bulk_g2s(sb + fs * B_TILE + j * (BN * 16), g.wpack + ((kc + j) * g.wrows + n0) * 16,
+                                bulk_g2s(sb + fs * B_TILE + j * (BN * 16), wsrc + ((kc + j) * g.wrows + n0) * 16,
                                          BN * 16, b_full(slot));
                         }
                         if (++slot == SB) { slot = 0; phase ^= 1; }
@@ -353,10 +360,12 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(buf * MB * BN);
             int tile_soff = 0;                           // TMA: first slot of the tile inside its box-aligned patch
+            // depthwise: does this tile's channel group have channels 32..63?
+            const int dw_halves = (DW && ep.cout_pad - (it - (it / g.ntiles_n) * g.ntiles_n) * BN <= 32) ? 1 : 2;
             if (TMA) {
                 const int pi0 = (it / g.ntiles_n) * TM;
                 const int Y0 = (int)__umulhi((uint32_t)pi0, g.mPW);
-                const int Yb0 = g.BY == 1 ? Y0 : (int)__umulhi((uint32_t)Y0, g.mHP) * HP;
+                const int Yb0 = g.BY == 1 ? Y0 : (int)__umulhi((uint32_t)Y0, g.mBY) * g.BY;
                 tile_soff = pi0 - Yb0 * g.PW;
             }
             for (int cg = 0; cg < ncg; ++cg) {
@@ -380,6 +389,22 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                             const uint32_t a_lo0 = a_row + (STRIDE == 2 ? (fs == 0 ? tap_col[0] : (fs == 1 ? 1u : tap_col[1]))
                                                                         : SLOT16 * (uint32_t)fs);
                             const uint32_t b_lo0 = b_row + (uint32_t)(fs * (B_TILE >> 4));
+                            if constexpr (DW) {
+                                // diagonal 64 x 64 block: K half h (channels 32h..32h+31) only reaches output
+                                // columns 32h..32h+31 -> two N = 32 MMAs on disjoint columns (one if the
+                                // group has no upper half)
+                                constexpr uint32_t idesc32 = instr_desc(A_SIGNED, 32);
+#pragma unroll
+                                for (int i = 0; i < MB; ++i) {
+#pragma unroll
+                                    for (int h = 0; h < 2; ++h)
+                                        if (h < dw_halves)
+                                            umma_i8_lohi(tacc + (uint32_t)(i * BN + 32 * h),
+                                                         a_lo0 + (uint32_t)(i * 512 + h * 2), desc_hi_a,
+                                                         b_lo0 + (uint32_t)h * (((2 * BN * 16) >> 4) + 32u), desc_hi, idesc32,
+                                                         (fs | fr) ? 1u : first);
+                                }
+                            } else {
 #pragma unroll
                             for (int i = 0; i < MB; ++i) {
 #pragma unroll
@@ -390,6 +415,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                                                  desc_hi_a,
                                                  b_lo0 + (uint32_t)h * ((2 * BN * 16) >> 4), desc_hi, idesc,
                                                  (h | fs | fr) ? 1u : first);
+                            }
                             }
                         }
                         umma_commit(b_empty(bslot));
@@ -567,8 +593,9 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
 
 namespace {
 
-template <int BN, int STRIDE>
+template <int BN, int STRIDE, bool DW = false>
 int launch_bn(const f8_conv_args &a, cudaStream_t s) {
+    constexpr bool dw = DW;
     constexpr int MB = mb_for(BN);
     constexpr int TM = 128 * MB;
     constexpr int B_TILE = BN * 64;
@@ -578,7 +605,15 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     const int plane_slots = TM + (STRIDE == 2 ? PW : 2 * PW) + 2;
     const int slots = (STRIDE == 2 ? 4 : 1) * plane_slots;
     const int HPh = a.hout + 1;
-    const int BY = (TMA && HPh * PW <= 64) ? HPh : 1;           // rows per TMA box
+    // rows per TMA box: a whole padded image when that is at most 64 slots, else one row -- or the
+    // smallest divisor of H + 1 that keeps a stage within 32 boxes (one per lane of the TMA warp)
+    int BY = (TMA && HPh * PW <= 64) ? HPh : 1;
+    if (TMA)
+        for (int d = BY; d <= HPh; ++d)
+            if (HPh % d == 0 && d * PW <= 256) {
+                BY = d;
+                if ((plane_slots + d * PW - 1) / (d * PW) + 1 <= 32) break;
+            }
     const int box_slots = BY * PW;
     // a stage holds the boxes covering any tile's slot range: at most (range / box) + 2 boxes
     const int max_boxes = (plane_slots + box_slots - 1) / box_slots + 1;
@@ -605,10 +640,15 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
         probe_bits = pv;
     }
     const bool plain = f8::epilogue_is_plain_u8(ep);
-    constexpr int SA = sa_for(STRIDE);
+    constexpr int SA_MAX = sa_for(STRIDE);
     const int SB = sb_for(BN, plain);
-    const size_t smem_bytes = (size_t)SA * slots_pad * 64 + (size_t)SB * 3 * B_TILE +
-                              (2 * SA + 2 * SB + 4) * 8 + 16 + 2 * BN * 4 + 1024;     // + base alignment slack
+    int SA = SA_MAX;
+    auto smem_for = [&](int sa) {
+        return (size_t)sa * slots_pad * 64 + (size_t)SB * 3 * B_TILE + (2 * SA_MAX + 2 * SB + 4) * 8 + 16 +
+               2 * BN * 4 + 1024;                                                      // + base alignment slack
+    };
+    while (SA > 2 && smem_for(SA) > 227 * 1024) --SA;          // wide images: a shallower patch ring
+    const size_t smem_bytes = smem_for(SA);
     if (smem_bytes > 227 * 1024) return F8_ERR_UNSUPPORTED;
     // the kernel owns all 512 TMEM columns: keep a second CTA off the SM
     const size_t smem_launch = smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes;
@@ -620,6 +660,10 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     g.in = static_cast<const uint8_t *>(a.in);
     g.wpack = static_cast<const uint8_t *>(a.wpack);
     g.wrows = pk.rows;
+    if (dw) {       // block-diagonal group images behind the dp4a words of the depthwise pack
+        g.wpack += f8host::dw_dense_offset(a.cin_pad);
+        g.wrows = 64;
+    }
     g.N = a.n; g.H = a.hout; g.W = a.wout; g.C = a.cin_pad;
     g.Hin = a.hin; g.Win = a.win;
     g.plane_slots = plane_slots;
@@ -628,9 +672,12 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     g.lx = PW <= 8 ? 0 : (PW <= 16 ? 1 : (PW <= 32 ? 2 : 3));
     g.BY = BY;
     g.box_slots = box_slots;
-    if (PW > 64) return F8_ERR_UNSUPPORTED;
+    if (!TMA && PW > 64) return F8_ERR_UNSUPPORTED;
+    g.sa = SA;
+    g.dw = dw ? 1 : 0;
     g.mPW = (uint32_t)(0x100000000ULL / (uint32_t)PW) + 1u;
     g.mHP = (uint32_t)(0x100000000ULL / (uint32_t)(a.hout + 1)) + 1u;
+    g.mBY = (uint32_t)(0x100000000ULL / (uint32_t)BY) + 1u;
     g.tm = TM;
     g.slots = slots;
     g.slots_pad = slots_pad;
@@ -639,10 +686,10 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     static bool attr_done = false;
     static int num_sms = 0;
     if (!attr_done) {
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, false, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, false, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, true, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, true, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, false, STRIDE, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, false, STRIDE, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, true, STRIDE, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, true, STRIDE, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         int dev = 0;
         F8_CUDA(cudaGetDevice(&dev));
         F8_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -670,11 +717,11 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
         if (rc != F8_OK) return rc;
     }
     if (a.in_signed) {
-        if (plain) conv3x3_umma_kernel<BN, true, true, STRIDE><<<gr, (epi_warps_for(true) + 6) * 32, smem_launch, s>>>(g, ep, tmap);
-        else conv3x3_umma_kernel<BN, true, false, STRIDE><<<gr, (epi_warps_for(false) + 6) * 32, smem_launch, s>>>(g, ep, tmap);
+        if (plain) conv3x3_umma_kernel<BN, true, true, STRIDE, DW><<<gr, (epi_warps_for(true) + 6) * 32, smem_launch, s>>>(g, ep, tmap);
+        else conv3x3_umma_kernel<BN, true, false, STRIDE, DW><<<gr, (epi_warps_for(false) + 6) * 32, smem_launch, s>>>(g, ep, tmap);
     } else {
-        if (plain) conv3x3_umma_kernel<BN, false, true, STRIDE><<<gr, (epi_warps_for(true) + 6) * 32, smem_launch, s>>>(g, ep, tmap);
-        else conv3x3_umma_kernel<BN, false, false, STRIDE><<<gr, (epi_warps_for(false) + 6) * 32, smem_launch, s>>>(g, ep, tmap);
+        if (plain) conv3x3_umma_kernel<BN, false, true, STRIDE, DW><<<gr, (epi_warps_for(true) + 6) * 32, smem_launch, s>>>(g, ep, tmap);
+        else conv3x3_umma_kernel<BN, false, false, STRIDE, DW><<<gr, (epi_warps_for(false) + 6) * 32, smem_launch, s>>>(g, ep, tmap);
     }
     F8_CUDA(cudaGetLastError());
     if (want_stats) {
@@ -706,6 +753,15 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
 }  // namespace
 
 namespace f8host {
+
+// depthwise 3x3 stride 1 on the tensor core: every 64-channel group is a dense 64 -> 64 conv
+// with a diagonal weight matrix (F8_ERR_UNSUPPORTED => the CUDA-core kernel of dw_conv.cu)
+int launch_conv3x3_dw(const f8_conv_args &a, cudaStream_t s) {
+    if (a.kh != 3 || a.kw != 3 || a.pad != 1 || a.stride != 1 || a.cin_pad != a.cout_pad || a.cin_pad % 16 != 0 ||
+        a.hin != a.hout || a.win != a.wout || a.out_f32 != nullptr)
+        return F8_ERR_UNSUPPORTED;
+    return launch_bn<64, 1, true>(a, s);
+}
 
 // F8_ERR_UNSUPPORTED => the caller falls back to the gather kernel (conv_umma.cu)
 int launch_conv3x3_umma(const f8_conv_args &a, cudaStream_t s) {

@@ -14,6 +14,8 @@
 // each channel the 9 taps are packed 4+4+1 into three dp4a operands, which cuts the integer
 // instruction count ~2.4x against one IMAD per tap per channel.  HBM-bound by design: each input
 // byte is read once from DRAM.
+#include <cstdlib>
+
 #include "f8_common.cuh"
 
 namespace {
@@ -171,6 +173,14 @@ dw3x3_kernel(const DwGeom g, const f8::Epilogue ep, const long long total, const
 namespace f8host {
 
 int launch_dw3x3(const f8_conv_args &a, cudaStream_t s) {
+#ifdef F8_WITH_UMMA
+    // stride 1: the tensor-core kernel (diagonal 64 x 64 weight blocks over the TMA-staged patch)
+    static const bool cuda_core_only = getenv("F8_DW_CUDA_CORE") != nullptr;
+    if (!cuda_core_only && a.stride == 1) {
+        const int rc = launch_conv3x3_dw(a, s);
+        if (rc != F8_ERR_UNSUPPORTED) return rc;
+    }
+#endif
     if (a.kh != 3 || a.kw != 3 || a.pad != 1 || (a.stride != 1 && a.stride != 2) ||
         a.cin_pad != a.cout_pad || a.cin_pad % 16 != 0) {
         set_error("conv_dw3x3: only 3x3 pad 1 stride 1|2 with cin_pad == cout_pad (multiple of 16)");

@@ -317,6 +317,11 @@ int launch_conv_umma(const f8_conv_args &a, cudaStream_t s);
 int launch_conv3x3_umma(const f8_conv_args &a, cudaStream_t s);
 int launch_head_pool(const f8_conv_args &a, cudaStream_t s);
 int launch_dw3x3(const f8_conv_args &a, cudaStream_t s);
+int launch_conv3x3_dw(const f8_conv_args &a, cudaStream_t s);
+// depthwise weight pack = [12][cpad/4] dp4a words, then (256-byte aligned) one block-diagonal
+// dense image [36 chunks][64 rows][16 B] per 64-channel group for the tensor-core path
+inline size_t dw_dense_offset(int cpad) { return ((size_t)12 * (size_t)cpad + 255) / 256 * 256; }
+inline size_t dw_pack_bytes(int cpad) { return dw_dense_offset(cpad) + (size_t)((cpad + 63) / 64) * 36 * 64 * 16; }
 int launch_maxpool(const f8_conv_args &a, cudaStream_t s);
 int launch_pool_requant(const f8_conv_args &a, cudaStream_t s);
 int launch_convert_input(const int32_t *x, void *out, int n, int h, int w, int is_signed,

@@ -58,7 +58,7 @@ constexpr int PLANE_BYTES = 5632;             // 6 * 928 = 5568 rounded up to 12
 constexpr int COPY_BYTES = 4 * PLANE_BYTES;
 constexpr int STAGE_BYTES = 2 * COPY_BYTES;   // 45056
 constexpr int BOX_BYTES = PLANE_ROWS * ROW_BYTES;
-constexpr int NSTAGE = 2;
+constexpr int NSTAGE = 3;
 constexpr int EPI_WARPS = 16, EPI_THREADS = 512;
 constexpr int LOAD_WARP = 16, MMA_WARP = 17, SHIFT_WARP0 = 18, SHIFT_WARPS = 2;
 constexpr int THREADS = 20 * 32;
@@ -83,6 +83,17 @@ constexpr int OFF_BAR = OFF_W + W_BYTES;
 constexpr int NBARS = 3 * NSTAGE + 4 + 1;     // stage_full, stage_empty, acc_full[2], acc_empty[2], w_full, stageb_full
 constexpr int OFF_MISC = OFF_BAR + (NBARS * 8 + 15) / 16 * 16;    // tmem slot, bias-safe flag, bias[64]
 constexpr int SMEM_BYTES = OFF_MISC + 32 + COUT * 4 + 128;         // + base alignment slack
+
+#define H2_TIMED(acc, stmt)                      \
+    do {                                         \
+        if (g.stats) {                           \
+            const long long _t0 = clock64();     \
+            stmt;                                \
+            acc += clock64() - _t0;              \
+        } else {                                 \
+            stmt;                                \
+        }                                        \
+    } while (0)
 
 struct H2Geom {
     const uint8_t *wpack;   // [16][wrows][16]: chunk 2r + half of filter row r
@@ -184,8 +195,10 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
         // zero pixels 226, 227 of one row becoming the zero pixels -6, -5 of the next
         const int sw = warp - SHIFT_WARP0;
         int slot = 0, phase = 0;
+        long long w_sa = 0;
+        const long long t_begin = clock64();
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            mbar_wait(stage_full(slot), phase);
+            H2_TIMED(w_sa, mbar_wait(stage_full(slot), phase));
 #pragma unroll
             for (int kk = 0; kk < 4 / SHIFT_WARPS; ++kk) {
                 const int k = sw * (4 / SHIFT_WARPS) + kk;
@@ -202,6 +215,10 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
             mbar_arrive(stageb_full(slot));
             if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
         }
+        if (g.stats && tid == SHIFT_WARP0 * 32) {
+            g.stats[blockIdx.x * 16 + 6] = clock64() - t_begin;
+            g.stats[blockIdx.x * 16 + 7] = w_sa;
+        }
     } else if (warp == MMA_WARP) {
         // =========================== MMA issuer ===================================
         constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);            // SBO = 128 B, version 1
@@ -210,11 +227,13 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
         const uint32_t w_lo0 = ((smem_base + OFF_W) & 0x3ffffu) >> 4;
         int slot = 0, phase = 0;
         uint32_t ph = 0;                                                  // dx phase counter
+        long long w_stage = 0, w_stageb = 0, w_acc = 0;
+        const long long t_begin = clock64();
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int img = t / TILES_IMG;
             const int L0 = (t - img * TILES_IMG) * 128;
             const int p0 = L0 / LP;
-            mbar_wait(stage_full(slot), phase);
+            H2_TIMED(w_stage, mbar_wait(stage_full(slot), phase));
             tc_fence_after();
             // descriptor start (16-byte units) of lane 0 in copy A, plane 0, row 0
             const uint32_t a_lo0 =
@@ -224,8 +243,8 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
                 constexpr int kDx[3] = {1, 0, 2};        // copy A (dx = 1) first: copy B is still being made
                 const int dx = kDx[dxi];
                 const int buf = ph & 1;
-                if (dxi == 1) { mbar_wait(stageb_full(slot), phase); tc_fence_after(); }
-                mbar_wait(acc_empty(buf), ((ph >> 1) & 1) ^ 1);
+                if (dxi == 1) { H2_TIMED(w_stageb, mbar_wait(stageb_full(slot), phase)); tc_fence_after(); }
+                H2_TIMED(w_acc, mbar_wait(acc_empty(buf), ((ph >> 1) & 1) ^ 1));
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(buf * ACC_COLS);
                 if (elect_one()) {
@@ -252,6 +271,12 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
             }
             if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
         }
+        if (g.stats && lane == 0) {
+            g.stats[blockIdx.x * 16 + 0] = clock64() - t_begin;
+            g.stats[blockIdx.x * 16 + 1] = w_stage;
+            g.stats[blockIdx.x * 16 + 2] = w_stageb;
+            g.stats[blockIdx.x * 16 + 3] = w_acc;
+        }
     } else {
         // =========================== epilogue (warps 0-15) ========================
         const int lg = warp & 3;                 // TMEM lane group
@@ -259,6 +284,8 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
         const bool safe = *bias_safe != 0;
         const int32_t *b16 = sbias + cgp * 16;
         uint32_t ph = 0;
+        long long w_full = 0;
+        const long long t_begin = clock64();
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int img = t / TILES_IMG;
             const int L = (t - img * TILES_IMG) * 128 + lg * 32 + lane;
@@ -274,7 +301,7 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
                 constexpr int kDx[3] = {1, 0, 2};
                 const int dx = kDx[dxi];
                 const int buf = ph & 1;
-                mbar_wait(acc_full(buf), (ph >> 1) & 1);
+                H2_TIMED(w_full, mbar_wait(acc_full(buf), (ph >> 1) & 1));
                 tc_fence_after();
                 const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * ACC_COLS + cgp * 16);
                 int32_t v0[16], v1[16], v2[16];
@@ -323,6 +350,10 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
                 if (ep.out0) *reinterpret_cast<uint4 *>(ep.out0 + o) = f8::requant_pack16(r, ep.shift0, ep.signed0);
                 if (ep.out1) *reinterpret_cast<uint4 *>(ep.out1 + o) = f8::requant_pack16(r, ep.shift1, ep.signed1);
             }
+        }
+        if (g.stats && tid == 0) {
+            g.stats[blockIdx.x * 16 + 4] = clock64() - t_begin;
+            g.stats[blockIdx.x * 16 + 5] = w_full;
         }
     }
 
@@ -382,9 +413,28 @@ int launch_head_pool(const f8_conv_args &a, cudaStream_t s) {
     if (rc != F8_OK) return rc;
     long long grid = (long long)a.n * TILES_IMG;
     if (grid > num_sms) grid = num_sms;
+    static const bool want_stats = getenv("F8_STATS") != nullptr;
+    static long long *stats_dev = nullptr;
+    if (want_stats) {
+        if (!stats_dev) F8_CUDA(cudaMalloc(&stats_dev, 16 * 1024 * sizeof(long long)));
+        F8_CUDA(cudaMemsetAsync(stats_dev, 0, 16 * 1024 * sizeof(long long), s));
+        g.stats = stats_dev;
+    }
     if (a.in_signed) head_pool2_kernel<true><<<(unsigned)grid, THREADS, SMEM_BYTES, s>>>(g, ep, tmap);
     else head_pool2_kernel<false><<<(unsigned)grid, THREADS, SMEM_BYTES, s>>>(g, ep, tmap);
     F8_CUDA(cudaGetLastError());
+    if (want_stats) {
+        static long long host[16 * 1024];
+        F8_CUDA(cudaStreamSynchronize(s));
+        F8_CUDA(cudaMemcpy(host, stats_dev, sizeof(host), cudaMemcpyDeviceToHost));
+        double acc[16] = {0};
+        for (long long b = 0; b < grid; ++b)
+            for (int k = 0; k < 16; ++k) acc[k] += (double)host[b * 16 + k] / (double)grid;
+        fprintf(stderr,
+                "[f8 stats] head_pool2 tiles/cta=%.1f | mma total %.0f wait_stage %.0f wait_stageb %.0f wait_acc %.0f | "
+                "epi total %.0f wait_full %.0f | shift total %.0f wait_stage %.0f (cycles, mean per CTA)\n",
+                (double)a.n * TILES_IMG / (double)grid, acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], acc[6], acc[7]);
+    }
     return F8_OK;
 }
 

@@ -116,7 +116,9 @@ struct f8_plan {
 extern "C" size_t f8_pack_weights_bytes(int kind, int cin, int cout, int cin_pad, int cout_pad,
                                         int kh, int kw) {
     (void)cin; (void)cout;
-    if (kind == F8_OP_CONV_DW) return (size_t)12 * (size_t)cin_pad;   // [12][cpad/4] u32
+    // [12][cpad/4] u32 for the CUDA-core kernel + block-diagonal 64 x 64 images per channel
+    // group for the tensor-core kernel (f8_common.cuh)
+    if (kind == F8_OP_CONV_DW) return f8host::dw_pack_bytes(cin_pad);
     if (kind == F8_OP_CONV_DENSE) {
         const f8host::DensePack p = f8host::dense_pack_geometry(cin_pad, cout_pad, kh, kw);
         return (size_t)p.rows * (size_t)p.K_pad;
@@ -154,6 +156,16 @@ extern "C" int f8_pack_weights(int kind, const int32_t *weight, int cin, int cou
                 }
                 const int k = t >> 2, byte = t & 3;
                 dst[(size_t)(c * 3 + k) * c4n + c4] |= ((uint32_t)w & 0xffu) << (8 * byte);
+            }
+        }
+        // tensor-core form: group gi = ch / 64 is a dense 64 -> 64 3x3 conv whose weight matrix is
+        // diagonal: K byte k = tap * 64 + c of output row o = c, image [36 chunks][64 rows][16 B]
+        int8_t *dense = static_cast<int8_t *>(dst_host) + f8host::dw_dense_offset(cin_pad);
+        for (int ch = 0; ch < cin; ++ch) {
+            const int gi = ch >> 6, c = ch & 63;
+            for (int t = 0; t < 9; ++t) {
+                const size_t kc = (size_t)t * 4 + (c >> 4);
+                dense[(size_t)gi * (36 * 64 * 16) + (kc * 64 + c) * 16 + (c & 15)] = (int8_t)weight[(size_t)ch * 9 + t];
             }
         }
         return F8_OK;
