@@ -28,7 +28,10 @@
 //              integer epilogue of f8_common.cuh (residual carries prefetched two steps ahead)
 //              and releases the accumulator ("acc_empty").
 // Integer accumulation is associative mod 2^32: tiling and MMA order cannot change results.
-#include "umma_common.cuh"
+#include <cstdlib>
+#include <cstring>
+
+#include "tma_common.cuh"
 
 namespace {
 
@@ -61,10 +64,15 @@ using namespace f8u;
 
 // Persistent, warp-specialised kernel.  Static tile schedule: CTA b runs tiles b, b+grid, ...
 // with the N tile fastest, so CTAs that are co-resident read the same activation rows.
-template <int BN, bool A_SIGNED, bool SMALL_C>
+// TMA_A (1x1 stride 1 convolutions and nn.Linear, cin_pad % 64 == 0): the A tile of a stage is one
+// TMA box {64 channels, 128 pixels} of the activation seen as a (C, M) matrix, landing in the
+// 64-byte-swizzled K-major layout; rows past M are the out-of-bounds zero fill.
+template <int BN, bool A_SIGNED, bool SMALL_C, bool TMA_A>
 __global__ void __launch_bounds__(threads_for(BN), (BN <= 128) ? 2 : 1)
-conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const int ntiles_n) {
-    extern __shared__ __align__(128) uint8_t smem[];
+conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const int ntiles_n,
+                 const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (f8::smem_u32(smem_raw) & 1023u)) & 1023u);
     constexpr int EPI_WARPS = epi_warps_for(BN);
     constexpr int EPI_THREADS = EPI_WARPS * 32;
     constexpr int PRODUCER_WARP0 = EPI_WARPS;     // 4 warps: A gather (+ its thread 0: B bulk copies)
@@ -91,7 +99,7 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
     if (warp == MMA_WARP) {
         if (lane == 0) {
             for (int s = 0; s < S; ++s) {
-                mbar_init(full_bar(s), PRODUCERS);
+                mbar_init(full_bar(s), TMA_A ? 1 : PRODUCERS);
                 mbar_init(empty_bar(s), 1);
             }
             for (int b = 0; b < 2; ++b) {
@@ -108,7 +116,29 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= PRODUCER_WARP0 && warp < MMA_WARP) {
+    if (TMA_A && warp >= PRODUCER_WARP0 && warp < MMA_WARP) {
+        // =========================== producer: one thread, A by TMA + B bulk copies =====
+        if (tid == PRODUCER_WARP0 * 32) {
+            tma_prefetch_desc(&tmap);
+            int slot = 0, phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int mt = t / ntiles_n;
+                const int n0 = (t - mt * ntiles_n) * BN;
+                for (int kt = 0; kt < g.ktiles; ++kt) {
+                    mbar_wait(empty_bar(slot), phase ^ 1);
+                    const uint32_t sa = smem_base + slot * STAGE;
+                    mbar_expect_tx(full_bar(slot), A_STAGE + B_STAGE);
+                    mbar_arrive(full_bar(slot));
+                    tma_load_4d(sa, &tmap, kt * BK, mt * BM, 0, 0, full_bar(slot));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        bulk_g2s(sa + A_STAGE + j * B_CHUNK, g.wpack + ((size_t)(kt * 4 + j) * g.wrows + n0) * 16,
+                                 B_CHUNK, full_bar(slot));
+                    if (++slot == S) { slot = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= PRODUCER_WARP0 && warp < MMA_WARP) {
         // =========================== producers: A gather + B bulk copies ==========
         const int row = tid - PRODUCER_WARP0 * 32;
         const int HW = g.hout * g.wout;
@@ -194,7 +224,10 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
         // high words are constants, low words advance by 32-bit adds
         constexpr uint32_t idesc = instr_desc(A_SIGNED, BN);
         constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);          // SBO = 128 B, version 1
-        constexpr uint32_t a_lbo_field = ((uint32_t)A_CHUNK >> 4) << 16;
+        // TMA_A: SWIZZLE_64B (layout type 4), SBO = 8 rows x 64 B, second K half at +32 B
+        constexpr uint32_t desc_hi_a = TMA_A ? ((512u >> 4) | (1u << 14) | (4u << 29)) : desc_hi;
+        constexpr uint32_t a_lbo_field = TMA_A ? (1u << 16) : (((uint32_t)A_CHUNK >> 4) << 16);
+        constexpr uint32_t a_khalf = TMA_A ? 2u : (uint32_t)((2 * A_CHUNK) >> 4);
         constexpr uint32_t b_lbo_field = ((uint32_t)B_CHUNK >> 4) << 16;
         int slot = 0, phase = 0;
         int buf = 0, acc_phase = 0;
@@ -209,8 +242,8 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
                 const uint32_t a_lo = ((sa & 0x3ffffu) >> 4) | a_lbo_field;
                 const uint32_t b_lo = (((sa + A_STAGE) & 0x3ffffu) >> 4) | b_lbo_field;
                 if (elect_one()) {
-                    umma_i8_lohi(tacc, a_lo, desc_hi, b_lo, desc_hi, idesc, (uint32_t)(kt != 0));
-                    umma_i8_lohi(tacc, a_lo + ((2 * A_CHUNK) >> 4), desc_hi, b_lo + ((2 * B_CHUNK) >> 4),
+                    umma_i8_lohi(tacc, a_lo, desc_hi_a, b_lo, desc_hi, idesc, (uint32_t)(kt != 0));
+                    umma_i8_lohi(tacc, a_lo + a_khalf, desc_hi_a, b_lo + ((2 * B_CHUNK) >> 4),
                                  desc_hi, idesc, 1u);
                     umma_commit(empty_bar(slot));   // frees the stage once these MMAs have read it
                 }
@@ -330,13 +363,23 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
 
 template <int BN>
 constexpr int smem_bytes_for() {
-    return stages_for(BN) * (A_STAGE + BN * BK) + (2 * stages_for(BN) + 4) * 8 + 16 + 2 * BN * 4;
+    return stages_for(BN) * (A_STAGE + BN * BK) + (2 * stages_for(BN) + 4) * 8 + 16 + 2 * BN * 4 + 1024;
 }
 
-template <int BN, bool A_SIGNED, bool SMALL_C>
+template <int BN, bool A_SIGNED, bool SMALL_C, bool TMA_A>
 int launch_t(const UGeom &g, const f8::Epilogue &ep, cudaStream_t s) {
     constexpr int smem_bytes = smem_bytes_for<BN>();
-    auto kern = conv_umma_kernel<BN, A_SIGNED, SMALL_C>;
+    auto kern = conv_umma_kernel<BN, A_SIGNED, SMALL_C, TMA_A>;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (TMA_A) {
+        const uint64_t dims[4] = {(uint64_t)g.cin_pad, (uint64_t)g.M, 1u, 1u};
+        const uint64_t row = (uint64_t)g.cin_pad, all = (uint64_t)g.cin_pad * (uint64_t)g.M;
+        const uint64_t strides[3] = {row, all, all};
+        const uint32_t box[4] = {(uint32_t)BK, (uint32_t)BM, 1u, 1u};
+        const int rc = f8host::encode_tmap_u8_4d(&tmap, g.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc != F8_OK) return rc;
+    }
     static bool attr_done = false;
     static int num_sms = 0;
     if (!attr_done) {
@@ -353,15 +396,16 @@ int launch_t(const UGeom &g, const f8::Epilogue &ep, cudaStream_t s) {
     const int per_sm = (BN <= 128) ? 2 : 1;
     long long grid = (long long)num_sms * per_sm;
     if (grid > total) grid = total;
-    kern<<<(unsigned)grid, threads_for(BN), smem_bytes, s>>>(g, ep, mtiles, ntn);
+    kern<<<(unsigned)grid, threads_for(BN), smem_bytes, s>>>(g, ep, mtiles, ntn, tmap);
     F8_CUDA(cudaGetLastError());
     return F8_OK;
 }
 
 template <int BN>
-int launch_bn(const UGeom &g, const f8::Epilogue &ep, bool sgn, bool small_c, cudaStream_t s) {
-    if (small_c) return sgn ? launch_t<BN, true, true>(g, ep, s) : launch_t<BN, false, true>(g, ep, s);
-    return sgn ? launch_t<BN, true, false>(g, ep, s) : launch_t<BN, false, false>(g, ep, s);
+int launch_bn(const UGeom &g, const f8::Epilogue &ep, bool sgn, bool small_c, bool tma_a, cudaStream_t s) {
+    if (small_c) return sgn ? launch_t<BN, true, true, false>(g, ep, s) : launch_t<BN, false, true, false>(g, ep, s);
+    if (tma_a) return sgn ? launch_t<BN, true, false, true>(g, ep, s) : launch_t<BN, false, false, true>(g, ep, s);
+    return sgn ? launch_t<BN, true, false, false>(g, ep, s) : launch_t<BN, false, false, false>(g, ep, s);
 }
 
 }  // namespace
@@ -406,9 +450,13 @@ int launch_conv_umma(const f8_conv_args &a, cudaStream_t s) {
     ep.cout_pad = a.cout_pad;
     const bool sgn = a.in_signed != 0;
     const bool small_c = pk.mode == 1;
-    if (a.cout_pad <= 64) return launch_bn<64>(g, ep, sgn, small_c, s);
-    if (a.cout_pad <= 128) return launch_bn<128>(g, ep, sgn, small_c, s);
-    return launch_bn<256>(g, ep, sgn, small_c, s);
+    // 1x1 stride 1 (and nn.Linear): the A operand is a plain (C, M) matrix -> TMA
+    static const bool no_tma = getenv("F8_GATHER_NO_TMA") != nullptr;
+    const bool tma_a = !no_tma && !small_c && a.kh == 1 && a.kw == 1 && a.stride == 1 && a.pad == 0 &&
+                       a.cin_pad % 64 == 0 && (g.M * (long long)a.cin_pad) < (1LL << 40);
+    if (a.cout_pad <= 64) return launch_bn<64>(g, ep, sgn, small_c, tma_a, s);
+    if (a.cout_pad <= 128) return launch_bn<128>(g, ep, sgn, small_c, tma_a, s);
+    return launch_bn<256>(g, ep, sgn, small_c, tma_a, s);
 }
 
 }  // namespace f8host
