@@ -64,7 +64,7 @@ using namespace f8u;
 
 // Persistent, warp-specialised kernel.  Static tile schedule: CTA b runs tiles b, b+grid, ...
 // with the N tile fastest, so CTAs that are co-resident read the same activation rows.
-// TMA_A (1x1 stride 1 convolutions and nn.Linear, cin_pad % 64 == 0): the A tile of a stage is one
+// TMA_A (1x1 stride 1 convolutions and nn.Linear): the A tile of a stage is one
 // TMA box {64 channels, 128 pixels} of the activation seen as a (C, M) matrix, landing in the
 // 64-byte-swizzled K-major layout; rows past M are the out-of-bounds zero fill.
 template <int BN, bool A_SIGNED, bool SMALL_C, bool TMA_A>
@@ -453,7 +453,7 @@ int launch_conv_umma(const f8_conv_args &a, cudaStream_t s) {
     // 1x1 stride 1 (and nn.Linear): the A operand is a plain (C, M) matrix -> TMA
     static const bool no_tma = getenv("F8_GATHER_NO_TMA") != nullptr;
     const bool tma_a = !no_tma && !small_c && a.kh == 1 && a.kw == 1 && a.stride == 1 && a.pad == 0 &&
-                       a.cin_pad % 64 == 0 && (g.M * (long long)a.cin_pad) < (1LL << 40);
+                       a.cin_pad % 16 == 0 && (g.M * (long long)a.cin_pad) < (1LL << 40);   // channels past cin_pad: zero fill
     if (a.cout_pad <= 64) return launch_bn<64>(g, ep, sgn, small_c, tma_a, s);
     if (a.cout_pad <= 128) return launch_bn<128>(g, ep, sgn, small_c, tma_a, s);
     return launch_bn<256>(g, ep, sgn, small_c, tma_a, s);
