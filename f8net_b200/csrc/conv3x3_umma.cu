@@ -444,6 +444,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
         const int cw0 = (warp >> 2) * CW;              // this warp's column slice of the tile
         const int row = lg * 32 + lane;
         int buf = 0, acc_phase = 0;
+        int bias_n0[2] = {-1, -1};                     // N tile whose bias each buffer's shared copy holds
         bool epi_primed = false;
         int4 cnext[4] = {};            // prefetched residual carry of the next 16-column step
         long long w_full = 0, t_issue = 0, t_wait = 0, t_math = 0, t_store = 0;
@@ -454,12 +455,17 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
             int ncols = ep.cout_pad - n0;
             if (ncols > BN) ncols = BN;
             int32_t *bias_s = sbias + buf * BN;
-            if (tid < ncols) {
-                int32_t b = __ldg(ep.bias + n0 + tid);
-                if (PLAIN_U8) b = (int32_t)((uint32_t)b + (1u << (ep.shift0 - 1)));   // bias + half
-                bias_s[tid] = b;
+            if (bias_n0[buf] != n0) {            // warp-uniform: reload only when this buffer's N tile changes
+                // every warp is done with the tile that last read this copy before it is rewritten
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                if (tid < ncols) {
+                    int32_t b = __ldg(ep.bias + n0 + tid);
+                    if (PLAIN_U8) b = (int32_t)((uint32_t)b + (1u << (ep.shift0 - 1)));   // bias + half
+                    bias_s[tid] = b;
+                }
+                bias_n0[buf] = n0;
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
             if (PLAIN_U8) {
                 F8_TIMED_WAIT(w_full, mbar_wait(acc_full(buf), acc_phase));
                 tc_fence_after();

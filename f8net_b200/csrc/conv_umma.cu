@@ -288,6 +288,7 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
 #pragma unroll
         for (int d = 0; d < PF; ++d) request(cq[d]);
         int buf = 0, acc_phase = 0;
+        int bias_n0[2] = {-1, -1};                     // N tile whose bias each buffer's shared copy holds
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int mt = t / ntiles_n;
             const int n0 = (t - mt * ntiles_n) * BN;
@@ -296,12 +297,17 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
             int ncols = ep.cout_pad - n0;
             if (ncols > BN) ncols = BN;
             int32_t *bias_s = sbias + buf * BN;
-            for (int i = tid; i < ncols; i += EPI_THREADS) {
-                int32_t b = __ldg(ep.bias + n0 + i);
-                if (plain) b = (int32_t)((uint32_t)b + (1u << (ep.shift0 - 1)));   // bias + half
-                bias_s[i] = b;
+            if (bias_n0[buf] != n0) {            // warp-uniform; a single N tile loads its bias twice per launch
+                // every warp is done with the tile that last read this copy before it is rewritten
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                for (int i = tid; i < ncols; i += EPI_THREADS) {
+                    int32_t b = __ldg(ep.bias + n0 + i);
+                    if (plain) b = (int32_t)((uint32_t)b + (1u << (ep.shift0 - 1)));   // bias + half
+                    bias_s[i] = b;
+                }
+                bias_n0[buf] = n0;
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
             mbar_wait(acc_full_bar(buf), acc_phase);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * BN);
