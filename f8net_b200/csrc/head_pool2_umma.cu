@@ -311,22 +311,31 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(acc_empty(buf));     // this thread's columns are in registers
-                if (!(dx == 0 && no_dx0)) {
-                    if (safe) {
+                // the pool's padding row / column: replace the excluded values by the identity of max
+                // (rare: only lanes of the first pooled row / column, so a branch, not 16 selects)
+                const int32_t ident = safe ? (int32_t)0x80000000 : 0;
+                if (no_dy0) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int32_t a0 = no_dy0 ? (int32_t)0x80000000 : v0[i];
-                            m[i] = max(max(m[i], a0), max(v1[i], v2[i]));
-                        }
-                    } else {
-                        // bias first (wrapping, like the reference's conv), ReLU through m >= 0
+                    for (int i = 0; i < 16; ++i) v0[i] = ident;
+                }
+                if (dx == 0 && no_dx0) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const uint32_t b = (uint32_t)b16[i];
-                            const int32_t a0 = no_dy0 ? 0 : (int32_t)((uint32_t)v0[i] + b);
-                            const int32_t a1 = (int32_t)((uint32_t)v1[i] + b), a2 = (int32_t)((uint32_t)v2[i] + b);
-                            m[i] = max(max(m[i], a0), max(a1, a2));
-                        }
+                    for (int i = 0; i < 16; ++i) v0[i] = v1[i] = v2[i] = ident;
+                }
+                if (safe) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) m[i] = max(max(m[i], v0[i]), max(v1[i], v2[i]));
+                } else {
+                    // bias first (wrapping, like the reference's conv), ReLU through m >= 0; an excluded
+                    // value must stay at the identity, so the bias is skipped for it
+                    const bool skip0 = no_dy0 || (dx == 0 && no_dx0), skip12 = dx == 0 && no_dx0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t b = (uint32_t)b16[i];
+                        const int32_t a0 = skip0 ? 0 : (int32_t)((uint32_t)v0[i] + b);
+                        const int32_t a1 = skip12 ? 0 : (int32_t)((uint32_t)v1[i] + b);
+                        const int32_t a2 = skip12 ? 0 : (int32_t)((uint32_t)v2[i] + b);
+                        m[i] = max(max(m[i], a0), max(a1, a2));
                     }
                 }
                 ++ph;
