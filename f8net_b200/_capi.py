@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "libf8b200.so")
 
 F8_ABI_VERSION = 1
 F8_OK, F8_ERR_ARG, F8_ERR_CUDA, F8_ERR_UNSUPPORTED, F8_ERR_NOMEM = 0, -1, -2, -3, -4
-F8_IN_NCHW_I32, F8_IN_NHWC4_8 = 0, 1
+F8_IN_NCHW_I32, F8_IN_NHWC4_8, F8_IN_NCHW_F32, F8_IN_NHWC3_U8 = 0, 1, 2, 3
 F8_OP_CONVERT_INPUT, F8_OP_CONV_DENSE, F8_OP_CONV_DW, F8_OP_MAXPOOL, F8_OP_POOL_REQUANT, \
     F8_OP_HEAD_POOL = range(6)
 
@@ -85,6 +85,13 @@ SYMBOLS = {
     "f8_convert_input": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
     "f8_requant_i32": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_int, _vp]),
+    "f8_plan_set_input_prep": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int,
+                                              ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
+    "f8_integerize_f32": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_int, _vp]),
+    "f8_integerize_u8": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
+    "f8_make_input_lut": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float),
+                                         ctypes.POINTER(ctypes.c_float), _vp]),
     "f8_last_error": (ctypes.c_char_p, []),
     "f8_abi_version": (ctypes.c_int, []),
     "f8_has_umma": (ctypes.c_int, [ctypes.c_int]),

@@ -328,6 +328,10 @@ int launch_convert_input(const int32_t *x, void *out, int n, int h, int w, int i
                          cudaStream_t s);
 int launch_requant_i32(const int32_t *x, int32_t *y, size_t count, int shift, int is_signed,
                        cudaStream_t s);
+int launch_integerize_f32(const float *x, void *out, int n, int h, int w, int normalize, int fraclen,
+                          cudaStream_t s);
+int launch_integerize_u8(const uint8_t *x, const uint8_t *lut_dev, void *out, int n, int h, int w,
+                         cudaStream_t s);
 
 // Dense weight image geometry (shared by the packer and the kernels)
 struct DensePack {

@@ -108,6 +108,9 @@ struct f8_plan {
     int convert_op = -1;        // index of the F8_OP_CONVERT_INPUT op, if any
     uint8_t *blob = nullptr;    // device: packed weights + biases of every op
     size_t blob_bytes = 0;
+    // forward_loss's input integerisation (f8_plan_set_input_prep)
+    int prep_normalize = 0, prep_fraclen = 8;
+    uint8_t *lut_dev = nullptr; // [3][256] table for F8_IN_NHWC3_U8
 };
 
 // ---------------------------------------------------------------------------------------
@@ -295,7 +298,64 @@ extern "C" int f8_plan_create(const f8_model_desc *desc, int device, f8_plan **o
 extern "C" void f8_plan_destroy(f8_plan *plan) {
     if (!plan) return;
     if (plan->blob) cudaFree(plan->blob);
+    if (plan->lut_dev) cudaFree(plan->lut_dev);
     delete plan;
+}
+
+// uint8 pixel p of channel c -> the 8-bit value forward_loss hands to the head, with torch's
+// float32 operation order: ToTensor p / 255, Normalize (x - mean) / std (fix_train.py:299-318),
+// then (255 x).round() or clamp(round(x * 2^fl), -127, 127) (fix_train.py:676-692).
+extern "C" int f8_make_input_lut(int normalize, int fraclen, const float *mean3, const float *std3,
+                                 uint8_t *lut) {
+    if (!lut || fraclen < 0 || fraclen > 8) { set_error("make_input_lut: bad arguments"); return F8_ERR_ARG; }
+    for (int c = 0; c < 3; ++c) {
+        const float mean = (normalize && mean3) ? mean3[c] : 0.0f;
+        const float sd = (normalize && std3) ? std3[c] : 1.0f;
+        for (int p = 0; p < 256; ++p) {
+            volatile float x = (float)p / 255.0f;            // volatile: one IEEE rounding per operation
+            if (normalize) {
+                x = x - mean;
+                x = x / sd;
+                volatile float r = x * ldexpf(1.0f, fraclen);
+                r = nearbyintf(r);
+                float q = r < -127.0f ? -127.0f : (r > 127.0f ? 127.0f : r);
+                lut[c * 256 + p] = (uint8_t)(int8_t)(int)q;
+            } else {
+                volatile float r = 255.0f * x;
+                r = nearbyintf(r);
+                lut[c * 256 + p] = (uint8_t)((int)r & 0xff);
+            }
+        }
+    }
+    return F8_OK;
+}
+
+extern "C" int f8_plan_set_input_prep(f8_plan *plan, int normalize, int fraclen, const float *mean3,
+                                      const float *std3) {
+    if (!plan || fraclen < 0 || fraclen > 8) { set_error("set_input_prep: bad arguments"); return F8_ERR_ARG; }
+    uint8_t lut[768];
+    int rc = f8_make_input_lut(normalize, fraclen, mean3, std3, lut);
+    if (rc) return rc;
+    int cur = -1;
+    F8_CUDA(cudaGetDevice(&cur));
+    if (cur != plan->device) F8_CUDA(cudaSetDevice(plan->device));
+    if (!plan->lut_dev) F8_CUDA(cudaMalloc(&plan->lut_dev, 768));
+    F8_CUDA(cudaMemcpy(plan->lut_dev, lut, 768, cudaMemcpyHostToDevice));
+    plan->prep_normalize = normalize ? 1 : 0;
+    plan->prep_fraclen = fraclen;
+    return F8_OK;
+}
+
+extern "C" int f8_integerize_f32(const float *x, void *out, int n, int h, int w, int normalize, int fraclen,
+                                 void *stream) {
+    if (!x || !out || n <= 0 || fraclen < 0 || fraclen > 8) { set_error("integerize_f32: bad arguments"); return F8_ERR_ARG; }
+    return f8host::launch_integerize_f32(x, out, n, h, w, normalize, fraclen, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int f8_integerize_u8(const uint8_t *x, const uint8_t *lut_dev, void *out, int n, int h, int w,
+                                void *stream) {
+    if (!x || !lut_dev || !out || n <= 0) { set_error("integerize_u8: bad arguments"); return F8_ERR_ARG; }
+    return f8host::launch_integerize_u8(x, lut_dev, out, n, h, w, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int f8_plan_workspace_bytes(const f8_plan *plan, int max_batch, size_t *bytes) {
@@ -319,12 +379,13 @@ extern "C" int f8_plan_launch_count(const f8_plan *plan, int x_layout, int n, in
     if (chunk <= 0 || chunk > n) chunk = n;
     const int passes = (n + chunk - 1) / chunk;
     int per = (int)plan->ops.size();
-    if (x_layout == F8_IN_NHWC4_8 && plan->convert_op >= 0) --per;
+    if (x_layout == F8_IN_NHWC4_8 && plan->convert_op >= 0) --per;   // every other layout runs the convert op
     return per * passes;
 }
 
-static int run_op(const f8_plan *p, const PlanOp &po, int n, const uint8_t *x, bool x_is_nhwc4,
+static int run_op(const f8_plan *p, const PlanOp &po, int n, const uint8_t *x, int x_layout,
                   float *logits, uint8_t *ws, int cap, cudaStream_t s) {
+    const bool x_is_nhwc4 = x_layout == F8_IN_NHWC4_8;
     const f8_op &o = po.op;
     auto buf = [&](int b) -> uint8_t * {
         if (b < 0) return nullptr;
@@ -334,6 +395,13 @@ static int run_op(const f8_plan *p, const PlanOp &po, int n, const uint8_t *x, b
     };
     if (o.kind == F8_OP_CONVERT_INPUT) {
         if (x_is_nhwc4) return F8_OK;
+        if (x_layout == F8_IN_NCHW_F32)
+            return f8host::launch_integerize_f32(reinterpret_cast<const float *>(x), buf(o.out_buf[0]), n, o.hin,
+                                                 o.win, p->prep_normalize, p->prep_fraclen, s);
+        if (x_layout == F8_IN_NHWC3_U8) {
+            if (!p->lut_dev) { set_error("plan_run: call f8_plan_set_input_prep before a uint8 image input"); return F8_ERR_ARG; }
+            return f8host::launch_integerize_u8(x, p->lut_dev, buf(o.out_buf[0]), n, o.hin, o.win, s);
+        }
         return f8host::launch_convert_input(reinterpret_cast<const int32_t *>(x), buf(o.out_buf[0]),
                                             n, o.hin, o.win, o.in_signed, s);
     }
@@ -380,6 +448,15 @@ static int plan_run_impl(f8_plan *plan, const void *x_dev, int x_layout, int n,
                          float *logits_dev, void *workspace_dev, size_t workspace_bytes,
                          int chunk, void *stream, std::vector<cudaEvent_t> *events);
 
+static size_t input_image_bytes(const f8_plan *plan, int x_layout) {
+    const size_t hw = (size_t)plan->image_h * plan->image_w;
+    switch (x_layout) {
+        case F8_IN_NHWC4_8: return hw * 4;
+        case F8_IN_NHWC3_U8: return hw * 3;
+        default: return hw * 3 * 4;          // int32 / float32 NCHW
+    }
+}
+
 extern "C" int f8_plan_run(f8_plan *plan, const void *x_dev, int x_layout, int n,
                            float *logits_dev, void *workspace_dev, size_t workspace_bytes,
                            int chunk, void *stream) {
@@ -424,12 +501,12 @@ static int plan_run_impl(f8_plan *plan, const void *x_dev, int x_layout, int n,
         set_error("plan_run: bad arguments");
         return F8_ERR_ARG;
     }
-    if (x_layout != F8_IN_NCHW_I32 && x_layout != F8_IN_NHWC4_8) {
+    if (x_layout < F8_IN_NCHW_I32 || x_layout > F8_IN_NHWC3_U8) {
         set_error("plan_run: unknown input layout %d", x_layout);
         return F8_ERR_ARG;
     }
-    if (x_layout == F8_IN_NCHW_I32 && plan->convert_op < 0) {
-        set_error("plan_run: plan has no CONVERT_INPUT op for an int32 NCHW input");
+    if (x_layout != F8_IN_NHWC4_8 && plan->convert_op < 0) {
+        set_error("plan_run: plan has no CONVERT_INPUT op for input layout %d", x_layout);
         return F8_ERR_ARG;
     }
     if (chunk <= 0 || chunk > n) chunk = n;
@@ -442,9 +519,7 @@ static int plan_run_impl(f8_plan *plan, const void *x_dev, int x_layout, int n,
     F8_CUDA(cudaGetDevice(&cur));
     if (cur != plan->device) F8_CUDA(cudaSetDevice(plan->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const bool nhwc4 = x_layout == F8_IN_NHWC4_8;
-    const size_t x_img = nhwc4 ? (size_t)plan->image_h * plan->image_w * 4
-                               : (size_t)plan->image_h * plan->image_w * 3 * sizeof(int32_t);
+    const size_t x_img = input_image_bytes(plan, x_layout);
     for (int i0 = 0; i0 < n; i0 += chunk) {
         const int nn = (n - i0 < chunk) ? (n - i0) : chunk;
         const uint8_t *x = static_cast<const uint8_t *>(x_dev) + (size_t)i0 * x_img;
@@ -458,7 +533,7 @@ static int plan_run_impl(f8_plan *plan, const void *x_dev, int x_layout, int n,
                 events->push_back(b);
                 F8_CUDA(cudaEventRecord(a, s));
             }
-            int rc = run_op(plan, po, nn, x, nhwc4, lg, static_cast<uint8_t *>(workspace_dev),
+            int rc = run_op(plan, po, nn, x, x_layout, lg, static_cast<uint8_t *>(workspace_dev),
                             chunk, s);
             if (rc) return rc;
             if (events) F8_CUDA(cudaEventRecord(events->back(), s));
@@ -476,9 +551,7 @@ extern "C" int f8_plan_run_host(f8_plan *plan, const void *x_host, int x_layout,
         return F8_ERR_ARG;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const size_t x_img = x_layout == F8_IN_NHWC4_8
-                             ? (size_t)plan->image_h * plan->image_w * 4
-                             : (size_t)plan->image_h * plan->image_w * 3 * sizeof(int32_t);
+    const size_t x_img = input_image_bytes(plan, x_layout);
     int cur = -1;
     F8_CUDA(cudaGetDevice(&cur));
     if (cur != plan->device) F8_CUDA(cudaSetDevice(plan->device));

@@ -121,6 +121,60 @@ convert_input_kernel(const int32_t *__restrict__ x, uint32_t *__restrict__ out, 
     }
 }
 
+// forward_loss's integerisation (fix_train.py:676-692) of the float32 NCHW tensor, in float32
+// with round-half-even exactly as torch does: (255 * x).round().int()  or
+// clamp(round(x * 2^fl), -127, 127); the low byte is kept (like the int32 path).
+__global__ void __launch_bounds__(THREADS)
+integerize_f32_kernel(const float *__restrict__ x, uint32_t *__restrict__ out, int n, int hw, int normalize,
+                      float scale) {
+    const long long total = (long long)n * hw;
+    for (long long idx = blockIdx.x * (long long)THREADS + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * THREADS) {
+        const int img = (int)(idx / hw);
+        const int px = (int)(idx - (long long)img * hw);
+        const float *src = x + (size_t)img * 3 * hw + px;
+        uint32_t q[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float r = rintf(__fmul_rn(__ldg(src + (size_t)c * hw), scale));
+            int32_t v;
+            if (normalize) v = (int32_t)fminf(fmaxf(r, -127.0f), 127.0f);
+            else v = f8::f2i_x86(r);
+            q[c] = (uint32_t)v & 0xffu;
+        }
+        out[idx] = q[0] | (q[1] << 8) | (q[2] << 16);
+    }
+}
+
+// decoded image bytes [n, hw, 3] through the per-channel table -> NHWC4
+__global__ void __launch_bounds__(THREADS)
+integerize_u8_kernel(const uint8_t *__restrict__ x, const uint8_t *__restrict__ lut, uint32_t *__restrict__ out,
+                     long long total) {
+    __shared__ uint8_t slut[768];
+    for (int i = threadIdx.x; i < 768; i += THREADS) slut[i] = lut[i];
+    __syncthreads();
+    // four pixels (12 bytes = three aligned words) per thread
+    const long long quads = total >> 2;
+    for (long long qd = blockIdx.x * (long long)THREADS + threadIdx.x; qd < quads;
+         qd += (long long)gridDim.x * THREADS) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(x) + qd * 3;
+        const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+        const uint32_t b[12] = {w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u, w0 >> 24,
+                                w1 & 255u, (w1 >> 8) & 255u, (w1 >> 16) & 255u, w1 >> 24,
+                                w2 & 255u, (w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24};
+        uint4 o;
+        o.x = slut[b[0]] | (slut[256 + b[1]] << 8) | (slut[512 + b[2]] << 16);
+        o.y = slut[b[3]] | (slut[256 + b[4]] << 8) | (slut[512 + b[5]] << 16);
+        o.z = slut[b[6]] | (slut[256 + b[7]] << 8) | (slut[512 + b[8]] << 16);
+        o.w = slut[b[9]] | (slut[256 + b[10]] << 8) | (slut[512 + b[11]] << 16);
+        reinterpret_cast<uint4 *>(out)[qd] = o;
+    }
+    // tail (total % 4 pixels)
+    for (long long i = (quads << 2) + blockIdx.x * (long long)THREADS + threadIdx.x; i < total;
+         i += (long long)gridDim.x * THREADS)
+        out[i] = slut[x[i * 3]] | (slut[256 + x[i * 3 + 1]] << 8) | (slut[512 + x[i * 3 + 2]] << 16);
+}
+
 __global__ void __launch_bounds__(THREADS)
 requant_i32_kernel(const int32_t *__restrict__ x, int32_t *__restrict__ y, size_t count,
                    int shift, int is_signed) {
@@ -183,6 +237,25 @@ int launch_convert_input(const int32_t *x, void *out, int n, int h, int w, int, 
     const long long total = (long long)n * h * w;
     convert_input_kernel<<<grid_for(total), THREADS, 0, s>>>(x, static_cast<uint32_t *>(out), n,
                                                              h * w);
+    F8_CUDA(cudaGetLastError());
+    return F8_OK;
+}
+
+int launch_integerize_f32(const float *x, void *out, int n, int h, int w, int normalize, int fraclen,
+                          cudaStream_t s) {
+    const long long total = (long long)n * h * w;
+    const float scale = normalize ? ldexpf(1.0f, fraclen) : 255.0f;
+    integerize_f32_kernel<<<grid_for(total), THREADS, 0, s>>>(x, static_cast<uint32_t *>(out), n, h * w,
+                                                              normalize, scale);
+    F8_CUDA(cudaGetLastError());
+    return F8_OK;
+}
+
+int launch_integerize_u8(const uint8_t *x, const uint8_t *lut_dev, void *out, int n, int h, int w,
+                         cudaStream_t s) {
+    const long long total = (long long)n * h * w;
+    integerize_u8_kernel<<<grid_for((total + 3) / 4), THREADS, 0, s>>>(x, lut_dev, static_cast<uint32_t *>(out),
+                                                                        total);
     F8_CUDA(cudaGetLastError());
     return F8_OK;
 }

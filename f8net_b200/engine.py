@@ -3,6 +3,10 @@
     engine = f8net_b200.compile(int_model)                    # a reference IntModel, or
     engine = f8net_b200.compile(state_dict, arch="resnet18")  # its state_dict (+ arch name)
     logits = engine(x)      # x: int32 [N,3,224,224] NCHW, values in the head's 8-bit range
+    logits = engine(xf)     # xf: the DataLoader's float32 [N,3,224,224] -- forward_loss's
+                            # integerisation (fix_train.py:676-692) then runs on the device
+    logits = engine(img)    # img: decoded uint8 [N,224,224,3] -- ToTensor + Normalize + the
+                            # integerisation folded into one table lookup on the device
 
 mirrors ``output = model(input)`` (/root/reference/fix_train.py:693) for the IntModel built
 at /root/reference/fix_train.py:930-935: same input tensor, same float32 ``[N, 1000]`` output
@@ -75,6 +79,31 @@ class Engine:
         self._logits = None
         self.head_fraclen = int(np.asarray(state_dict["head.0.input_fraclen"]).reshape(-1)[0]) \
             if "head.0.input_fraclen" in state_dict else None
+        # forward_loss's input preparation: FLAGS.normalize <=> signed head (fix_resnet.py:437-438)
+        self.set_input_prep(bool(net.head.sym))
+
+    IMAGENET_MEAN = (0.485, 0.456, 0.406)      # fix_train.py:303-304
+    IMAGENET_STD = (0.229, 0.224, 0.225)
+
+    def set_input_prep(self, normalize: bool, mean=None, std=None, fraclen=None):
+        """How float32 / uint8 inputs become the head's 8-bit integers (fix_train.py:676-692):
+        normalize False: (255 x).round(); True: clamp(round(x 2^fl), -127, 127) with
+        fl = head.input_fraclen, on x = (p / 255 - mean) / std for uint8 pixels p."""
+        if normalize:
+            mean = self.IMAGENET_MEAN if mean is None else mean
+            std = self.IMAGENET_STD if std is None else std
+            if fraclen is None:
+                fraclen = self.head_fraclen
+            if fraclen is None:
+                raise ValueError("normalize=True needs head.0.input_fraclen (or fraclen=)")
+        else:
+            mean, std, fraclen = (0.0, 0.0, 0.0), (1.0, 1.0, 1.0), 8
+        m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
+        s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
+        with self._torch.cuda.device(self.device):
+            C.check(self.lib.f8_plan_set_input_prep(self._h, int(bool(normalize)), int(fraclen), m3, s3))
+        self.input_prep = {"normalize": bool(normalize), "mean": tuple(mean), "std": tuple(std),
+                           "fraclen": int(fraclen)}
 
     # ------------------------------------------------------------------------------------
     def set_backend(self, backend: int):
@@ -106,26 +135,35 @@ class Engine:
             self._ws = self._torch.empty(need, dtype=self._torch.uint8, device=self.device)
         return self._ws
 
-    # ------------------------------------------------------------------------------------
-    def run_device(self, x, out=None, chunk=None, stream=None):
-        """x: CUDA tensor, either int32 [N,3,H,W] (the reference's tensor) or 8-bit
-        [N,H,W,4] (engine-native NHWC, channel 3 zero).  Enqueues on the current stream
-        (or ``stream``) and returns the float32 [N, classes] logits tensor, no sync."""
+    def _layout_of(self, x):
         torch = self._torch
-        if x.device != self.device:
-            raise ValueError(f"input is on {x.device}, the engine on {self.device}")
         S = self.net.image_size
-        if x.dtype == torch.int32 and tuple(x.shape[1:]) == (3, S, S):
-            layout = C.F8_IN_NCHW_I32
-        elif x.dtype in (torch.uint8, torch.int8) and tuple(x.shape[1:]) == (S, S, 4):
-            layout = C.F8_IN_NHWC4_8
+        shape = tuple(x.shape[1:])
+        if x.dtype == torch.int32 and shape == (3, S, S):
+            return C.F8_IN_NCHW_I32
+        if x.dtype == torch.float32 and shape == (3, S, S):
+            return C.F8_IN_NCHW_F32
+        if x.dtype == torch.uint8 and shape == (S, S, 3):
+            return C.F8_IN_NHWC3_U8
+        if x.dtype in (torch.uint8, torch.int8) and shape == (S, S, 4):
             want = torch.int8 if self.net.head.sym else torch.uint8
             if x.dtype != want:
                 raise TypeError(f"head conv is {'signed' if self.net.head.sym else 'unsigned'}: "
                                 f"expected {want}, got {x.dtype}")
-        else:
-            raise TypeError(f"expected int32 [N,3,{S},{S}] or 8-bit [N,{S},{S},4]; got "
-                            f"{x.dtype} {tuple(x.shape)}")
+            return C.F8_IN_NHWC4_8
+        raise TypeError(f"expected int32 / float32 [N,3,{S},{S}], uint8 [N,{S},{S},3] or 8-bit "
+                        f"[N,{S},{S},4]; got {x.dtype} {tuple(x.shape)}")
+
+    # ------------------------------------------------------------------------------------
+    def run_device(self, x, out=None, chunk=None, stream=None):
+        """x: CUDA tensor: int32 [N,3,H,W] (the reference's tensor), float32 [N,3,H,W] (the
+        DataLoader's tensor, integerised on the device), uint8 [N,H,W,3] (decoded pixels) or
+        8-bit [N,H,W,4] (engine-native NHWC, channel 3 zero).  Enqueues on the current stream
+        (or ``stream``) and returns the float32 [N, classes] logits tensor, no sync."""
+        torch = self._torch
+        if x.device != self.device:
+            raise ValueError(f"input is on {x.device}, the engine on {self.device}")
+        layout = self._layout_of(x)
         if not x.is_contiguous():
             x = x.contiguous()
         n = x.shape[0]
@@ -148,13 +186,7 @@ class Engine:
         ``sync=False`` (x and out pinned) leaves the stream running so a second Engine on
         another stream can overlap its copies with this one's compute."""
         torch = self._torch
-        S = self.net.image_size
-        if x.dtype == torch.int32:
-            layout = C.F8_IN_NCHW_I32
-        elif x.dtype in (torch.uint8, torch.int8):
-            layout = C.F8_IN_NHWC4_8
-        else:
-            raise TypeError(f"expected an int32 or 8-bit tensor, got {x.dtype}")
+        layout = self._layout_of(x)
         x = x.contiguous()
         n = x.shape[0]
         if out is None:
@@ -179,7 +211,7 @@ class Engine:
     def profile(self, x, chunk=None):
         """Per-launch device times (ms) of one run_device(x): list of (op name, kind, ms)."""
         torch = self._torch
-        layout = C.F8_IN_NCHW_I32 if x.dtype == torch.int32 else C.F8_IN_NHWC4_8
+        layout = self._layout_of(x)
         n = x.shape[0]
         chunk = min(int(chunk or self.chunk), n)
         ws = self._workspace(chunk)
@@ -191,6 +223,11 @@ class Engine:
                                          ws.data_ptr(), ws.numel(), chunk, st.cuda_stream,
                                          ms, nops))
         return [(op.name, op.kind, float(ms[i])) for i, op in enumerate(self.plan.ops)]
+
+    def topk(self, logits, ks=(1, 5)):
+        """forward_loss's prediction step (fix_train.py:698-703): indices of the max(ks) largest
+        logits per image, on the logits' device."""
+        return logits.topk(max(ks))[1]
 
     def __call__(self, x, strict=False):
         """``IntModel.forward(x)``: int32 NCHW in, float32 logits out, on x's device.

@@ -54,7 +54,12 @@ typedef enum f8_status {
  * NCHW, fix_resnet.py:352 / fix_mobilenet_v1.py:120 / fix_mobilenet_v2.py:207). */
 typedef enum f8_input_layout {
     F8_IN_NCHW_I32 = 0,   /* the reference's own tensor: int32 [N,3,H,W], values in 8-bit range */
-    F8_IN_NHWC4_8 = 1     /* engine-native: 8-bit [N,H,W,4] (channel 3 = 0), u8 or s8 per head   */
+    F8_IN_NHWC4_8 = 1,    /* engine-native: 8-bit [N,H,W,4] (channel 3 = 0), u8 or s8 per head   */
+    /* the two tensors BEFORE forward_loss's integerisation (fix_train.py:676-692): the engine
+     * applies that step on the device, bit-exactly (see f8_plan_set_input_prep) */
+    F8_IN_NCHW_F32 = 2,   /* the DataLoader's tensor: float32 [N,3,H,W] (ToTensor + Normalize)    */
+    F8_IN_NHWC3_U8 = 3    /* decoded image bytes: uint8 [N,H,W,3]; ToTensor + Normalize +
+                             integerisation folded into one 3 x 256 table                        */
 } f8_input_layout;
 
 typedef enum f8_op_kind {
@@ -147,9 +152,21 @@ F8_API int f8_plan_workspace_bytes(const f8_plan *plan, int max_batch, size_t *b
 F8_API int f8_plan_run(f8_plan *plan, const void *x_dev, int x_layout, int n, float *logits_dev,
                 void *workspace_dev, size_t workspace_bytes, int chunk, void *stream);
 
+/* Replaces: the input preparation of forward_loss (fix_train.py:676-692) and the transform in
+ * front of it (ToTensor + Normalize, fix_train.py:299-318) for the F8_IN_NCHW_F32 / F8_IN_NHWC3_U8
+ * layouts.  normalize = FLAGS.normalize:
+ *   0: x_int = (255 * x).round().int()                    (unsigned head, fraclen 8)
+ *   1: x_int = clamp(round(x * 2^fraclen), -127, 127)      (signed head, fraclen = head.input_fraclen)
+ * with float32 arithmetic and round-half-even exactly as torch computes them; for uint8 pixels p
+ * the float tensor is x = (p / 255 - mean[c]) / std[c] (mean 0 / std 1 when normalize = 0).
+ * Defaults without this call: normalize = the head's signedness, fraclen = 8 (unsigned) or the
+ * head's input_fraclen given here.  The low byte of x_int is kept, like F8_IN_NCHW_I32. */
+F8_API int f8_plan_set_input_prep(f8_plan *plan, int normalize, int fraclen, const float *mean3,
+                           const float *std3);
+
 /* Same, with HOST buffers (pinned or pageable): copies x host->device, runs, copies the
  * logits back, all on `stream`, then (sync != 0) synchronises the stream.  x_stage_dev must hold the
- * input (n * 3*H*W*4 bytes for NCHW_I32, n * H*W*4 for NHWC4_8).  sync = 0 leaves the stream
+ * input (n * 3*H*W*4 bytes for NCHW_I32 / NCHW_F32, n * H*W*4 for NHWC4_8, n * H*W*3 for NHWC3_U8).  sync = 0 leaves the stream
  * unsynchronised (x_host / logits_host must then be pinned and stay alive) so that a caller
  * can overlap the copies of one batch with the compute of another on a second stream.  This
  * is the entry the reference-facing call surface uses for CPU tensors. */
@@ -221,6 +238,17 @@ F8_API int f8_pool_requant(const f8_conv_args *a, void *stream);
 /* Replaces: the int32 NCHW tensor hand-over at model(x): repack to NHWC4 8 bit.
  * x int32 [n,3,h,w] -> out 8-bit [n,h,w,4]. */
 F8_API int f8_convert_input(const int32_t *x, void *out, int n, int h, int w, void *stream);
+/* Replaces: forward_loss's integerisation of the float tensor (fix_train.py:676-692), see
+ * f8_plan_set_input_prep.  x float32 [n,3,h,w] -> out 8-bit [n,h,w,4]. */
+F8_API int f8_integerize_f32(const float *x, void *out, int n, int h, int w, int normalize, int fraclen,
+                      void *stream);
+/* Replaces: ToTensor + Normalize + the same integerisation for decoded uint8 pixels.
+ * x uint8 [n,h,w,3], lut_dev: device table [3][256] of 8-bit values -> out 8-bit [n,h,w,4].
+ * f8_make_input_lut fills the (host) table for given normalize / fraclen / mean / std. */
+F8_API int f8_integerize_u8(const uint8_t *x, const uint8_t *lut_dev, void *out, int n, int h, int w,
+                     void *stream);
+F8_API int f8_make_input_lut(int normalize, int fraclen, const float *mean3, const float *std3,
+                      uint8_t *lut_host768);
 /* Replaces: int_op_only_fix_quant as a standalone op (fix_quant_ops.py:90-114):
  * y[i] = requant(x[i], input_fl - fl, is_signed), int32 in / int32 out. */
 F8_API int f8_requant_i32(const int32_t *x, int32_t *y, size_t count, int fl, int input_fl,

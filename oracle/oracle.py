@@ -162,3 +162,16 @@ def input_s8(x, fl):
     y = np.empty(x.shape, dtype=np.int32)
     lib().f8o_input_s8(x.ctypes.data_as(_f32p), _p(y), ctypes.c_size_t(x.size), int(fl))
     return y
+
+
+def image_prep_u8(pix, normalize, fl=8, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+    """Decoded uint8 pixels [..., H, W, 3] -> the int32 NCHW tensor forward_loss hands to the head:
+    torchvision ToTensor (p / 255 in float32) and Normalize ((x - mean) / std, float32,
+    /root/reference/fix_train.py:299-318; mean 0 / std 1 when normalize is False) followed by
+    input_u8 / input_s8 (fix_train.py:676-692).  One float32 rounding per operation, like torch."""
+    p = np.asarray(pix, dtype=np.uint8)
+    x = p.astype(np.float32) / np.float32(255.0)
+    if normalize:
+        x = (x - np.asarray(mean, dtype=np.float32)) / np.asarray(std, dtype=np.float32)
+    x = np.moveaxis(x.astype(np.float32), -1, -3)          # HWC -> CHW
+    return input_s8(x, fl) if normalize else input_u8(x)

@@ -105,7 +105,8 @@ def test_pack_depthwise_dp4a_operands(f8lib):
     w = rng.integers(-127, 128, (24, 1, 3, 3)).astype(np.int32)
     rc, img = _pack(f8lib, C.F8_OP_CONV_DW, w, 32, 32)
     assert rc == 0
-    img = img.view(np.uint32).reshape(12, 8)
+    raw = img
+    img = raw[:12 * 32].view(np.uint32).reshape(12, 8)        # dp4a words of the CUDA-core kernel
     for ch in range(24):
         taps = w[ch, 0].reshape(9)
         for k in range(3):
@@ -115,6 +116,14 @@ def test_pack_depthwise_dp4a_operands(f8lib):
                 want = int(taps[t]) & 0xFF if t < 9 else 0
                 assert (word >> (8 * byte)) & 0xFF == want
     assert not img[:, 6:].any()              # padded channels stay zero
+    # tensor-core form behind it (256-byte aligned): one diagonal 64 x 64 image per channel group,
+    # [36 chunks][64 rows][16 B], K byte k = tap * 64 + c of row o = c
+    dense = raw[512:].view(np.int8).reshape(36, 64, 16)
+    want = np.zeros((36, 64, 16), np.int8)
+    for ch in range(24):
+        for t in range(9):
+            want[t * 4 + ch // 16, ch, ch % 16] = w[ch, 0].reshape(9)[t]
+    assert raw.size == 512 + 36 * 64 * 16 and np.array_equal(dense, want)
 
 
 def test_pack_rejects_weights_outside_8_bits(f8lib):
@@ -139,3 +148,19 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(C, "LIB_PATH", "/nonexistent/libf8b200.so")
     with pytest.raises(ImportError, match="no CPU fallback"):
         C.lib()
+
+
+def test_input_lut_matches_reference(f8lib):
+    """f8_make_input_lut (host code of the product) against the reference-generated vectors."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "input_prep.npz"))
+    pix = g["u8_pix"]
+    mean = (ctypes.c_float * 3)(0.485, 0.456, 0.406)
+    std = (ctypes.c_float * 3)(0.229, 0.224, 0.225)
+    for normalize, fl, key in ((0, 8, "u8_u_y"), (1, 3, "u8_s3_y"), (1, 5, "u8_s5_y"), (1, 7, "u8_s7_y")):
+        lut = np.zeros(768, dtype=np.uint8)
+        assert f8lib.f8_make_input_lut(normalize, fl, mean, std, lut.ctypes.data) == 0
+        got = np.stack([lut[c * 256 + pix[..., c].astype(np.int64)] for c in range(3)])   # [3,16,16]
+        want = g[key][0]
+        got = got.view(np.int8).astype(np.int32) if normalize else got.astype(np.int32)
+        assert np.array_equal(got, want), key

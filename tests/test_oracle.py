@@ -157,3 +157,29 @@ def test_input_integerisation():
     got = O.input_s8(xs, 5)
     want = [int(max(-127, min(127, np.rint(v * 32)))) for v in xs]
     assert list(got) == want
+
+
+# ---------------------------------------------------------------------------------------------
+# forward_loss input preparation (A12) against vectors produced by the reference's own code
+# (tests/golden/make_input_golden.py: fix_train.py:676-692 + models.fix_quant_ops.fix_quant)
+# ---------------------------------------------------------------------------------------------
+def _input_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "input_prep.npz"))
+
+
+def test_input_prep_float_matches_reference():
+    g = _input_golden()
+    assert np.array_equal(O.input_u8(g["f32_u_x"]), g["f32_u_y"])
+    for fl in (3, 5, 7):
+        assert np.array_equal(O.input_s8(g[f"f32_s{fl}_x"], fl), g[f"f32_s{fl}_y"])
+
+
+def test_input_prep_uint8_matches_reference():
+    g = _input_golden()
+    assert np.array_equal(O.image_prep_u8(g["u8_pix"][None], False), g["u8_u_y"])
+    for fl in (3, 5, 7):
+        assert np.array_equal(O.image_prep_u8(g["u8_pix"][None], True, fl), g[f"u8_s{fl}_y"])
+    # normalize False is the identity on pixel values: (255 * (p / 255)).round() == p
+    p = np.arange(256, dtype=np.uint8).reshape(1, 16, 16, 1).repeat(3, axis=3)
+    assert np.array_equal(O.image_prep_u8(p, False)[0, 0].reshape(-1), np.arange(256))
