@@ -36,8 +36,8 @@ UNIT = "images/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="f8net_b200", choices=["f8net_b200", "reference"])
     ap.add_argument("--arch", default="resnet18")
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
@@ -142,7 +142,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -315,6 +315,33 @@ def gpu_arm(args):
            "input": "pinned int32 NCHW (the reference's tensor), two engines on two streams",
            "timer": "host perf_counter around the loop, stream syncs inside"}
 
+    # ---- the same call fed with decoded uint8 pixels [B,H,W,3]: ToTensor +
+    # Normalize + forward_loss's integerisation run on the device, 4x fewer PCIe bytes ----
+    hp = [torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+
+    def e2e_u8_steps(k):
+        for i in range(k):
+            j = i % 2
+            streams[j].synchronize()
+            engines[j].run_host(hp[j], out=hy[j], sync=False, stream=streams[j])
+        for s in streams:
+            s.synchronize()
+
+    e2e_u8_steps(3)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_u8_steps(args.steps)
+    barrier()
+    u8_dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([u8_dt], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        u8_dt = float(t.item())
+    e2e_u8 = {"value": world * B * args.steps / u8_dt, "unit": UNIT,
+              "h2d_bytes_per_step": B * 3 * S * S, "d2h_bytes_per_step": B * eng.net.num_classes * 4,
+              "input": "pinned uint8 [B,H,W,3] decoded pixels; ToTensor + Normalize + integerisation "
+                       "(fix_train.py:299-318, :676-692) on the device"}
+
     line = None
     if rank == 0:
         # ---- roofline of the dominant kernel family: per-launch CUDA events ----
@@ -382,7 +409,7 @@ def gpu_arm(args):
                 "cuda_graph": graphs is not None,
                 "l2": f"{R} distinct resident input batches ({R * in_bytes / 1e6:.0f} MB > 126 MB L2) rotated per step",
                 "resident_input": "NHWC 8-bit [B,224,224,4]"}),
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
+            "e2e": e2e, "e2e_uint8_input": e2e_u8, "gpu_launches": launches, "clocks": clocks.summary(),
             "roofline": roofline, "cpu_baseline": cb,
         }
     if world > 1:

@@ -127,7 +127,9 @@ def test_compile_from_module_like_object_and_bound_method(cuda, f8lib):
 def test_input_validation(cuda, f8lib):
     eng = _engine("mobilenet_v1", synth.make_state_dict("mobilenet_v1"))
     with pytest.raises(TypeError):
-        eng(torch.zeros((1, 3, 224, 224), dtype=torch.float32).cuda())
+        eng(torch.zeros((1, 3, 224, 224), dtype=torch.float16).cuda())
+    with pytest.raises(TypeError):
+        eng(torch.zeros((1, 3, 112, 112), dtype=torch.float32).cuda())              # wrong image size
     with pytest.raises(TypeError):
         eng.run_device(torch.zeros((1, 224, 224, 4), dtype=torch.int8).cuda())   # head is unsigned
     bad = torch.full((1, 3, 224, 224), 300, dtype=torch.int32)
