@@ -58,6 +58,12 @@ __host__ __device__ constexpr int a_lag_for(int stride) { return stride == 2 ? 0
 __host__ __device__ constexpr int epi_warps_for(bool plain) { (void)plain; return 16; }
 constexpr int LOADERS = 128;
 
+// stride 1: m[0] = the NHWC activation; stride 2: m[p] = its parity plane p = (row parity, column
+// parity) as a strided view (every second pixel of every second row)
+struct TMaps {
+    CUtensorMap m[4];
+};
+
 struct PGeom {
     const uint8_t *in;
     const uint8_t *wpack;   // [K_pad/16][wrows][16], k = (r*3+s)*C + c
@@ -77,6 +83,8 @@ struct PGeom {
     int lx;                 // log2 of the 8-slot items per padded row (PW <= 8 << lx)
     int BY;                 // TMA path: padded rows per box, a divisor of H + 1 (boxes never straddle images)
     int sa;                 // patch ring depth (<= sa_for(STRIDE))
+    int sb;                 // weight ring depth (<= sb_for(BN))
+    int pps;                // slots of one plane's box-aligned patch region in a stage (stride 2)
     int dw;                 // depthwise mode: output tile n reads only input channel group n, through a
                             // block-diagonal 64 x 64 weight image per group (wpack = [group][36][64][16])
     int box_slots;          // TMA path: BY * PW
@@ -95,11 +103,12 @@ struct PGeom {
 
 template <int BN, bool A_SIGNED, bool PLAIN_U8, int STRIDE, bool DW>
 __global__ void __launch_bounds__((epi_warps_for(PLAIN_U8) + 6) * 32, 1)
-conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant__ CUtensorMap tmap) {
+conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant__ TMaps tmaps) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // stride 1: the patch arrives by TMA in the 64-byte-swizzled K-major layout [slot][64 B]
     // (stage bases 1024-byte aligned); stride 2: cp.async into [16-byte chunk][slot][16 B]
-    constexpr bool TMA = STRIDE == 1;
+    constexpr bool TMA = true;
+    constexpr int PLANES = STRIDE == 2 ? 4 : 1;
     uint8_t *smem = smem_raw + ((1024u - (f8::smem_u32(smem_raw) & 1023u)) & 1023u);
     constexpr int EPI_WARPS = epi_warps_for(PLAIN_U8);
     constexpr int EPI_THREADS = EPI_WARPS * 32;
@@ -108,7 +117,8 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     constexpr int WLOAD_WARP = EPI_WARPS + 5;
     constexpr int MB = mb_for(BN);
     constexpr int TM = 128 * MB;
-    constexpr int SB = sb_for(BN, PLAIN_U8);
+    constexpr int SB_MAX = sb_for(BN, PLAIN_U8);
+    const int SB = g.sb;
     constexpr int SA_MAX = sa_for(STRIDE);
     const int SA = g.sa;
     constexpr int A_LAG = a_lag_for(STRIDE);
@@ -124,10 +134,10 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     auto a_full = [&](int s) { return bar_base + (uint32_t)s * 8; };
     auto a_empty = [&](int s) { return bar_base + (uint32_t)(SA_MAX + s) * 8; };
     auto b_full = [&](int s) { return bar_base + (uint32_t)(2 * SA_MAX + s) * 8; };
-    auto b_empty = [&](int s) { return bar_base + (uint32_t)(2 * SA_MAX + SB + s) * 8; };
-    auto acc_full = [&](int b) { return bar_base + (uint32_t)(2 * SA_MAX + 2 * SB + b) * 8; };
-    auto acc_empty = [&](int b) { return bar_base + (uint32_t)(2 * SA_MAX + 2 * SB + 2 + b) * 8; };
-    constexpr int NBARS = 2 * SA_MAX + 2 * SB + 4;
+    auto b_empty = [&](int s) { return bar_base + (uint32_t)(2 * SA_MAX + SB_MAX + s) * 8; };
+    auto acc_full = [&](int b) { return bar_base + (uint32_t)(2 * SA_MAX + 2 * SB_MAX + b) * 8; };
+    auto acc_empty = [&](int b) { return bar_base + (uint32_t)(2 * SA_MAX + 2 * SB_MAX + 2 + b) * 8; };
+    constexpr int NBARS = 2 * SA_MAX + 2 * SB_MAX + 4;
     uint8_t *after = smem + SA * a_stage + SB * B_STAGE + NBARS * 8;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(after);
     int32_t *sbias = reinterpret_cast<int32_t *>(after + 16);
@@ -142,7 +152,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     if (warp == MMA_WARP) {
         if (lane == 0) {
             for (int s = 0; s < SA; ++s) { mbar_init(a_full(s), TMA ? 1 : LOADERS); mbar_init(a_empty(s), 1); }
-            if (TMA) tma_prefetch_desc(&tmap);
+            for (int p = 0; p < PLANES; ++p) tma_prefetch_desc(&tmaps.m[p]);
             for (int s = 0; s < SB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
             for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), EPI_THREADS); }
             fence_barrier_init();
@@ -180,13 +190,26 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                 for (int cg = 0; cg < ncg; ++cg) {
                     F8_TIMED_WAIT(w_empty, mbar_wait(a_empty(slot), phase ^ 1));
                     if (lane == 0) {
-                        mbar_expect_tx(a_full(slot), (uint32_t)(nbox * BS * 64));
+                        mbar_expect_tx(a_full(slot), (uint32_t)(PLANES * nbox * BS * 64));
                         mbar_arrive(a_full(slot));
                     }
                     __syncwarp();
-                    if (lane < nbox)
-                        tma_load_4d(smem_base + slot * a_stage + lane * BS * 64, &tmap, (cg0 + cg) * 64, -1, yy - 1, img,
-                                    a_full(slot));
+                    if (PLANES == 1) {
+                        if (lane < nbox)
+                            tma_load_4d(smem_base + slot * a_stage + lane * BS * 64, &tmaps.m[0], (cg0 + cg) * 64, -1,
+                                        yy - 1, img, a_full(slot));
+                    } else {
+                        // box b of plane p: the same padded rows of every parity plane
+                        for (int b = lane; b < PLANES * nbox; b += 32) {
+                            int p = 0, bb = b;
+                            while (bb >= nbox) { bb -= nbox; ++p; }
+                            const int Ybb = Yb0 + bb * BY;
+                            const int im = (int)__umulhi((uint32_t)Ybb, g.mHP);
+                            const int y0 = Ybb - im * HP;
+                            tma_load_4d(smem_base + slot * a_stage + (p * g.pps + bb * BS) * 64, &tmaps.m[p],
+                                        (cg0 + cg) * 64, -1, y0 - 1, im, a_full(slot));
+                        }
+                    }
                     if (++slot == SA) { slot = 0; phase ^= 1; }
                 }
             }
@@ -194,107 +217,6 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                 g.stats[blockIdx.x * 16 + 0] = clock64() - t_begin;
                 g.stats[blockIdx.x * 16 + 1] = w_empty;
             }
-        }
-    } else if (warp >= LOADER_WARP0 && warp < MMA_WARP) {
-        // =========================== patch loaders (cp.async) =====================
-        const int lt = tid - LOADER_WARP0 * 32;
-        int slot = 0, phase = 0;
-        long long w_empty = 0, w_cp = 0;
-        const long long t_begin = clock64();
-        // Row-wise staging.  A batch is 8 "items" of 8 slots x 64 B (one warp instruction each:
-        // four consecutive lanes fetch the four 16-byte chunks of a slot, so an instruction reads
-        // 8 pixels x 64 contiguous bytes = whole sectors, and writes four 128-byte runs of shared
-        // memory).  A padded row holds XI = 2^LX items, so a batch covers 8 >> LX rows; the row
-        // is decoded once (warp uniform) and the 8 cp.async of a batch are issued back to back
-        // from 8 distinct address registers (cp.async holds its address registers until the
-        // request drains: reusing one stalls the warp).
-        constexpr int PLANES = STRIDE == 2 ? 4 : 1;
-        const int lw = lt >> 5;
-        const int jc = lane & 3, xl = lane >> 2;
-        const int PW = g.PW, Hin = g.Hin, Win = g.Win, C = g.C, NI = g.N, plane_slots = g.plane_slots;
-        const uint32_t mPW = g.mPW, mHP = g.mHP;
-        const uint8_t *const in = g.in + jc * 16;
-        const int lx = g.lx;                               // log2(items per row), 0..3
-        const int rows_per_batch = 8 >> lx;
-        int issued = 0, aslot = 0;
-        auto stage_rows = [&](auto lx_tag, uint32_t sa, int cg, int Y0, int pi0, int nrows) {
-            constexpr int LX = decltype(lx_tag)::value;
-            constexpr int RB = 8 >> LX, XI = 1 << LX;
-            const int nb = (nrows + RB - 1) / RB;                    // batches per plane
-#pragma unroll 1
-            for (int q = lw; q < nb * PLANES; q += 4) {
-                int plane = 0, bq = q;
-                if (STRIDE == 2) { while (bq >= nb) { bq -= nb; ++plane; } }
-                const uint8_t *src[8];
-                uint32_t dst[8];
-                uint32_t live = 0, ok = 0;
-#pragma unroll
-                for (int rr = 0; rr < RB; ++rr) {
-                    const int r = bq * RB + rr;
-                    const int Yp = Y0 + r;
-                    const int img = (int)__umulhi((uint32_t)Yp, mHP);
-                    const int yy = Yp - img * HP;
-                    const int y = STRIDE == 2 ? 2 * (yy - 1) + (plane >> 1) : yy - 1;
-                    const bool rowok = r < nrows && yy >= 1 && img < NI && y < Hin;
-                    const int p0 = Yp * PW - pi0;                    // in-plane slot of xs = 0
-                    const int x0 = STRIDE == 2 ? 2 * (xl - 1) + (plane & 1) : xl - 1;
-                    const uint8_t *rowbase = in + ((size_t)(img * Hin + y) * Win + x0) * C + cg * 64;
-                    const uint32_t d0 = sa + (uint32_t)((plane * plane_slots + p0 + xl) * 16);
-#pragma unroll
-                    for (int xi = 0; xi < XI; ++xi) {
-                        const int b = rr * XI + xi;
-                        const int xs = xi * 8 + xl;
-                        const int pin = p0 + xs;
-                        const int x = x0 + (STRIDE == 2 ? 16 : 8) * xi;
-                        const bool lv = r < nrows && xs < PW && pin >= 0 && pin < plane_slots;
-                        const bool k = lv && rowok && xs >= 1 && x < Win;
-                        live |= lv ? (1u << b) : 0u;
-                        ok |= k ? (1u << b) : 0u;
-                        src[b] = k ? rowbase + (size_t)((STRIDE == 2 ? 16 : 8) * xi) * C : g.in;
-                        dst[b] = d0 + (uint32_t)(xi * 128);
-                    }
-                }
-#pragma unroll
-                for (int b = 0; b < 8; ++b)
-                    if (live & (1u << b)) cp_async16(dst[b], src[b], (ok >> b) & 1u);
-            }
-        };
-        for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
-            const int st = it / g.ntiles_n;
-            const int pi0 = st * TM;
-            const int Y0 = (int)__umulhi((uint32_t)pi0, mPW);
-            const int nrows = (int)__umulhi((uint32_t)(pi0 + plane_slots - 1), mPW) - Y0 + 1;
-            for (int cg = 0; cg < ncg; ++cg) {
-                F8_TIMED_WAIT(w_empty, mbar_wait(a_empty(slot), phase ^ 1));
-                const uint32_t sa = smem_base + slot * a_stage + jc * lbo_a;
-                if (lx == 3) stage_rows(std::integral_constant<int, 3>{}, sa, cg, Y0, pi0, nrows);
-                else if (lx == 2) stage_rows(std::integral_constant<int, 2>{}, sa, cg, Y0, pi0, nrows);
-                else if (lx == 1) stage_rows(std::integral_constant<int, 1>{}, sa, cg, Y0, pi0, nrows);
-                else stage_rows(std::integral_constant<int, 0>{}, sa, cg, Y0, pi0, nrows);
-                cp_async_commit();
-                if (++slot == SA) { slot = 0; phase ^= 1; }
-                // signal a stage as soon as its bytes have landed, WITHOUT first needing a free
-                // slot for a much younger stage (that would chain MMA(k) behind MMA(k-1))
-                if (++issued > A_LAG) {
-                    F8_TIMED_WAIT(w_cp, cp_async_wait<A_LAG>());
-                    fence_proxy_async();
-                    mbar_arrive(a_full(aslot));
-                    if (++aslot == SA) aslot = 0;
-                    --issued;
-                }
-            }
-        }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        for (; issued > 0; --issued) {
-            mbar_arrive(a_full(aslot));
-            if (++aslot == SA) aslot = 0;
-        }
-        (void)rows_per_batch;
-        if (g.stats && lt == 0) {
-            g.stats[blockIdx.x * 16 + 0] = clock64() - t_begin;
-            g.stats[blockIdx.x * 16 + 1] = w_empty;
-            g.stats[blockIdx.x * 16 + 2] = w_cp;
         }
     } else if (warp == WLOAD_WARP) {
         // =========================== weight-tile loader ===========================
@@ -346,8 +268,8 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
         if (STRIDE == 2) {
             // row fr: plane bit (fr != 1) * 2, plus one padded row for fr > 0; column fs: plane bit
             // (fs != 1), plus one padded column for fs > 0
-            tap_row[0] = 2u * g.plane_slots; tap_row[1] = (uint32_t)g.PW; tap_row[2] = 2u * g.plane_slots + g.PW;
-            tap_col[0] = (uint32_t)g.plane_slots; tap_col[1] = (uint32_t)g.plane_slots + 1u;
+            tap_row[0] = SLOT16 * 2u * g.pps; tap_row[1] = SLOT16 * (uint32_t)g.PW; tap_row[2] = SLOT16 * (2u * g.pps + g.PW);
+            tap_col[0] = SLOT16 * (uint32_t)g.pps; tap_col[1] = SLOT16 * ((uint32_t)g.pps + 1u);
         } else {
             tap_row[0] = 0u; tap_row[1] = SLOT16 * (uint32_t)g.PW; tap_row[2] = SLOT16 * 2u * g.PW;
             tap_col[0] = tap_col[1] = 0u;
@@ -386,7 +308,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                             if (g.probe & 32) continue;
                             // slot offset of tap (fr, fs): stride 1: fr*PW + fs; stride 2: parity plane
                             // ((fr != 1), (fs != 1)) and a one-row / one-column step for fr > 0 / fs > 0
-                            const uint32_t a_lo0 = a_row + (STRIDE == 2 ? (fs == 0 ? tap_col[0] : (fs == 1 ? 1u : tap_col[1]))
+                            const uint32_t a_lo0 = a_row + (STRIDE == 2 ? (fs == 0 ? tap_col[0] : (fs == 1 ? SLOT16 : tap_col[1]))
                                                                         : SLOT16 * (uint32_t)fs);
                             const uint32_t b_lo0 = b_row + (uint32_t)(fs * (B_TILE >> 4));
                             if constexpr (DW) {
@@ -605,26 +527,32 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     constexpr int MB = mb_for(BN);
     constexpr int TM = 128 * MB;
     constexpr int B_TILE = BN * 64;
-    constexpr bool TMA = STRIDE == 1;
-    // TMA path: an even pitch keeps every box (one padded row of PW slots x 64 B) 128-byte aligned
-    const int PW = TMA ? ((a.wout + 2) & ~1) : a.wout + 1;
+    constexpr bool TMA = true;
+    constexpr int PLANES = STRIDE == 2 ? 4 : 1;
+    // an even pitch keeps every box (one padded row of PW slots x 64 B) 128-byte aligned
+    const int PW = (a.wout + 2) & ~1;
     const int plane_slots = TM + (STRIDE == 2 ? PW : 2 * PW) + 2;
     const int slots = (STRIDE == 2 ? 4 : 1) * plane_slots;
     const int HPh = a.hout + 1;
-    // rows per TMA box: a whole padded image when that is at most 64 slots, else one row -- or the
-    // smallest divisor of H + 1 that keeps a stage within 32 boxes (one per lane of the TMA warp)
-    int BY = (TMA && HPh * PW <= 64) ? HPh : 1;
-    if (TMA)
-        for (int d = BY; d <= HPh; ++d)
+    // rows per TMA box (a divisor of H + 1, so that boxes never straddle images).  Stride 1: a whole
+    // padded image when that is at most 64 slots, else one row.  Otherwise (too many boxes for the
+    // TMA warp, or four parity planes): the smallest divisor that keeps a stage within the box budget,
+    // which is also the one that wastes the least shared memory on box alignment.
+    const int box_budget = PLANES == 1 ? 32 : 64;
+    auto boxes_for = [&](int d) { return PLANES * ((plane_slots + d * PW - 1) / (d * PW) + 1); };
+    int BY = (PLANES == 1 && HPh * PW <= 64) ? HPh : 1;
+    if (boxes_for(BY) > box_budget)
+        for (int d = 1; d <= HPh; ++d)
             if (HPh % d == 0 && d * PW <= 256) {
                 BY = d;
-                if ((plane_slots + d * PW - 1) / (d * PW) + 1 <= 32) break;
+                if (boxes_for(d) <= box_budget) break;
             }
     const int box_slots = BY * PW;
     // a stage holds the boxes covering any tile's slot range: at most (range / box) + 2 boxes
     const int max_boxes = (plane_slots + box_slots - 1) / box_slots + 1;
-    if (TMA && max_boxes > 32) return F8_ERR_UNSUPPORTED;
-    const int slots_pad = TMA ? (max_boxes * box_slots + 15) / 16 * 16 : (slots + 7) / 8 * 8;
+    if (PLANES * max_boxes > box_budget) return F8_ERR_UNSUPPORTED;
+    const int pps = (max_boxes * box_slots + 7) / 8 * 8;                 // slots of one plane's region
+    const int slots_pad = (PLANES * pps + 15) / 16 * 16;
     f8::Epilogue ep{};
     ep.bias = a.bias;
     ep.carry_in = a.carry_in;
@@ -647,14 +575,16 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     }
     const bool plain = f8::epilogue_is_plain_u8(ep);
     constexpr int SA_MAX = sa_for(STRIDE);
-    const int SB = sb_for(BN, plain);
-    int SA = SA_MAX;
-    auto smem_for = [&](int sa) {
-        return (size_t)sa * slots_pad * 64 + (size_t)SB * 3 * B_TILE + (2 * SA_MAX + 2 * SB + 4) * 8 + 16 +
+    const int SB_MAX = sb_for(BN, plain);
+    int SA = SA_MAX, SB = SB_MAX;
+    auto smem_for = [&](int sa, int sb) {
+        return (size_t)sa * slots_pad * 64 + (size_t)sb * 3 * B_TILE + (2 * SA_MAX + 2 * SB_MAX + 4) * 8 + 16 +
                2 * BN * 4 + 1024;                                                      // + base alignment slack
     };
-    while (SA > 2 && smem_for(SA) > 227 * 1024) --SA;          // wide images: a shallower patch ring
-    const size_t smem_bytes = smem_for(SA);
+    // wide images / four parity planes: shallower rings
+    while (SA > 2 && smem_for(SA, SB) > 227 * 1024) --SA;
+    while (SB > 2 && smem_for(SA, SB) > 227 * 1024) --SB;
+    const size_t smem_bytes = smem_for(SA, SB);
     if (smem_bytes > 227 * 1024) return F8_ERR_UNSUPPORTED;
     // the kernel owns all 512 TMEM columns: keep a second CTA off the SM
     const size_t smem_launch = smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes;
@@ -678,8 +608,9 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     g.lx = PW <= 8 ? 0 : (PW <= 16 ? 1 : (PW <= 32 ? 2 : 3));
     g.BY = BY;
     g.box_slots = box_slots;
-    if (!TMA && PW > 64) return F8_ERR_UNSUPPORTED;
     g.sa = SA;
+    g.sb = SB;
+    g.pps = pps;
     g.dw = dw ? 1 : 0;
     g.mPW = (uint32_t)(0x100000000ULL / (uint32_t)PW) + 1u;
     g.mHP = (uint32_t)(0x100000000ULL / (uint32_t)(a.hout + 1)) + 1u;
@@ -711,23 +642,27 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
         g.stats = stats_dev;
     }
     const unsigned gr = (unsigned)grid;
-    CUtensorMap tmap;
-    memset(&tmap, 0, sizeof(tmap));
-    if (TMA) {
-        // the NHWC activation as (C, W, H, N); box = 64 channels x PW pixels x BY rows of one image
-        const uint64_t dims[4] = {(uint64_t)a.cin_pad, (uint64_t)a.win, (uint64_t)a.hin, (uint64_t)a.n};
-        const uint64_t strides[3] = {(uint64_t)a.cin_pad, (uint64_t)a.win * a.cin_pad,
+    TMaps tmaps;
+    memset(&tmaps, 0, sizeof(tmaps));
+    for (int p = 0; p < PLANES; ++p) {
+        // stride 1: the NHWC activation as (C, W, H, N).  stride 2: parity plane p = (row parity pr,
+        // column parity pc): every second pixel of every second row, an (C, W/2, H/2, N) view whose
+        // base is pixel (pr, pc).  Box = 64 channels x PW pixels x BY rows of one image.
+        const int pr = p >> 1, pc = p & 1;
+        const uint8_t *base = static_cast<const uint8_t *>(a.in) + ((size_t)pr * a.win + pc) * a.cin_pad;
+        const uint64_t dims[4] = {(uint64_t)a.cin_pad, (uint64_t)a.wout, (uint64_t)a.hout, (uint64_t)a.n};
+        const uint64_t strides[3] = {(uint64_t)STRIDE * a.cin_pad, (uint64_t)STRIDE * a.win * a.cin_pad,
                                      (uint64_t)a.hin * a.win * a.cin_pad};
         const uint32_t box[4] = {64u, (uint32_t)PW, (uint32_t)BY, 1u};
-        const int rc = f8host::encode_tmap_u8_4d(&tmap, a.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+        const int rc = f8host::encode_tmap_u8_4d(&tmaps.m[p], base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc != F8_OK) return rc;
     }
     if (a.in_signed) {
-        if (plain) conv3x3_umma_kernel<BN, true, true, STRIDE, DW><<<gr, (epi_warps_for(true) + 6) * 32, smem_launch, s>>>(g, ep, tmap);
-        else conv3x3_umma_kernel<BN, true, false, STRIDE, DW><<<gr, (epi_warps_for(false) + 6) * 32, smem_launch, s>>>(g, ep, tmap);
+        if (plain) conv3x3_umma_kernel<BN, true, true, STRIDE, DW><<<gr, (epi_warps_for(true) + 6) * 32, smem_launch, s>>>(g, ep, tmaps);
+        else conv3x3_umma_kernel<BN, true, false, STRIDE, DW><<<gr, (epi_warps_for(false) + 6) * 32, smem_launch, s>>>(g, ep, tmaps);
     } else {
-        if (plain) conv3x3_umma_kernel<BN, false, true, STRIDE, DW><<<gr, (epi_warps_for(true) + 6) * 32, smem_launch, s>>>(g, ep, tmap);
-        else conv3x3_umma_kernel<BN, false, false, STRIDE, DW><<<gr, (epi_warps_for(false) + 6) * 32, smem_launch, s>>>(g, ep, tmap);
+        if (plain) conv3x3_umma_kernel<BN, false, true, STRIDE, DW><<<gr, (epi_warps_for(true) + 6) * 32, smem_launch, s>>>(g, ep, tmaps);
+        else conv3x3_umma_kernel<BN, false, false, STRIDE, DW><<<gr, (epi_warps_for(false) + 6) * 32, smem_launch, s>>>(g, ep, tmaps);
     }
     F8_CUDA(cudaGetLastError());
     if (want_stats) {
