@@ -122,7 +122,8 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     constexpr int SA_MAX = sa_for(STRIDE);
     const int SA = g.sa;
     constexpr int A_LAG = a_lag_for(STRIDE);
-    constexpr int B_TILE = BN * 64;                       // one tap
+    constexpr int BROWS = DW ? 64 : BN;                   // weight rows of a tile (depthwise: one 64-channel group)
+    constexpr int B_TILE = BROWS * 64;                    // one tap
     constexpr int B_STAGE = 3 * B_TILE;                   // one filter row
     constexpr int CW = BN / (EPI_WARPS / 4);               // columns per epilogue warp slice (plain path)
     const int a_stage = g.slots_pad * 64;                 // bytes of one patch stage
@@ -146,7 +147,16 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int total_items = g.n_super * g.ntiles_n;
-    const int ncg = DW ? 1 : g.C >> 6;          // 64-channel groups in the K loop
+    // K loop: dense = every 64-channel group of the input; depthwise = the BN / 64 channel groups
+    // of the output tile itself (each through its own diagonal weight block, on its own columns)
+    constexpr int GPT = BN / 64;
+    const int ngroups = (ep.cout_pad + 63) >> 6;
+    auto tile_group0 = [&](int it) { return DW ? (it - (it / g.ntiles_n) * g.ntiles_n) * GPT : 0; };
+    auto tile_ncg = [&](int it) {
+        if (!DW) return g.C >> 6;
+        const int left = ngroups - tile_group0(it);
+        return left < GPT ? left : GPT;
+    };
     const int HP = g.H + 1;
 
     if (warp == MMA_WARP) {
@@ -178,7 +188,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
             const int PW = g.PW, BY = g.BY, BS = g.box_slots;
             for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
                 const int st = it / g.ntiles_n;
-                const int cg0 = DW ? it - st * g.ntiles_n : 0;
+                const int cg0 = tile_group0(it), ncg = tile_ncg(it);
                 const int pi0 = st * TM;
                 const int Y0 = (int)__umulhi((uint32_t)pi0, g.mPW);
                 const int Ylast = (int)__umulhi((uint32_t)(pi0 + g.plane_slots - 1), g.mPW);
@@ -228,23 +238,28 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                 const int st = it / g.ntiles_n;
                 const int n0 = DW ? 0 : (it - st * g.ntiles_n) * BN;
                 const int Ck = DW ? 64 : g.C;
-                const uint8_t *wsrc = g.wpack + (DW ? (size_t)(it - st * g.ntiles_n) * (36 * 64 * 16) : 0);
-                for (int cg = 0; cg < ncg; ++cg)
+                const int ncg = tile_ncg(it);
+                // depthwise: 64 weight rows per group image, dense: BN rows of the shared image
+                constexpr uint32_t ROWS_B = DW ? 64u : (uint32_t)BN;
+                for (int cg = 0; cg < ncg; ++cg) {
+                    const uint8_t *wsrc = g.wpack + (DW ? (size_t)(tile_group0(it) + cg) * (36 * 64 * 16) : 0);
+                    const int kcg = DW ? 0 : cg;
                     for (int fr = 0; fr < 3; ++fr) {
                         F8_TIMED_WAIT(w_bempty, mbar_wait(b_empty(slot), phase ^ 1));
                         const uint32_t sb = sb_base + slot * B_STAGE;
-                        mbar_expect_tx(b_full(slot), B_STAGE);
+                        mbar_expect_tx(b_full(slot), 12u * ROWS_B * 16u);
                         mbar_arrive(b_full(slot));
 #pragma unroll
                         for (int fs = 0; fs < 3; ++fs) {
-                            const size_t kc = (size_t)((fr * 3 + fs) * Ck + cg * 64) >> 4;
+                            const size_t kc = (size_t)((fr * 3 + fs) * Ck + kcg * 64) >> 4;
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
-                                bulk_g2s(sb + fs * B_TILE + j * (BN * 16), wsrc + ((kc + j) * g.wrows + n0) * 16,
-                                         BN * 16, b_full(slot));
+                                bulk_g2s(sb + fs * B_TILE + j * (BROWS * 16), wsrc + ((kc + j) * g.wrows + n0) * 16,
+                                         ROWS_B * 16u, b_full(slot));
                         }
                         if (++slot == SB) { slot = 0; phase ^= 1; }
                     }
+                }
             }
             if (g.stats) {
                 g.stats[blockIdx.x * 16 + 3] = clock64() - t_begin;
@@ -261,7 +276,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
         constexpr uint32_t desc_hi_a = TMA ? ((512u >> 4) | (1u << 14) | (4u << 29)) : desc_hi;
         constexpr uint32_t SLOT16 = TMA ? 4u : 1u;                      // one slot in descriptor units of 16 B
         const uint32_t a_lbo_field = TMA ? (1u << 16) : ((lbo_a >> 4) << 16);
-        constexpr uint32_t b_lbo_field = ((uint32_t)(BN * 16) >> 4) << 16;
+        constexpr uint32_t b_lbo_field = ((uint32_t)(BROWS * 16) >> 4) << 16;
         int aslot = 0, aphase = 0, bslot = 0, bphase = 0, buf = 0, acc_phase = 0;
         // start-address offsets of the taps in descriptor units (16 B = one slot)
         uint32_t tap_row[3], tap_col[2];
@@ -282,8 +297,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(buf * MB * BN);
             int tile_soff = 0;                           // TMA: first slot of the tile inside its box-aligned patch
-            // depthwise: does this tile's channel group have channels 32..63?
-            const int dw_halves = (DW && ep.cout_pad - (it - (it / g.ntiles_n) * g.ntiles_n) * BN <= 32) ? 1 : 2;
+            const int ncg = tile_ncg(it);
             if (TMA) {
                 const int pi0 = (it / g.ntiles_n) * TM;
                 const int Y0 = (int)__umulhi((uint32_t)pi0, g.mPW);
@@ -295,6 +309,8 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                 if (g.stats && t_first_a == 0) t_first_a = clock64();
                 const uint32_t sa = smem_base + aslot * a_stage + (TMA ? (uint32_t)tile_soff * 64u : 0u);
                 const uint32_t first = (uint32_t)(cg != 0);
+                // depthwise: does this channel group have channels 32..63?
+                const int dw_halves = (DW && ep.cout_pad - (tile_group0(it) + cg) * 64 <= 32) ? 1 : 2;
 #pragma unroll
                 for (int fr = 0; fr < 3; ++fr) {
                     F8_TIMED_WAIT(w_b, mbar_wait(b_full(bslot), bphase));
@@ -321,10 +337,10 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
 #pragma unroll
                                     for (int h = 0; h < 2; ++h)
                                         if (h < dw_halves)
-                                            umma_i8_lohi(tacc + (uint32_t)(i * BN + 32 * h),
+                                            umma_i8_lohi(tacc + (uint32_t)(i * BN + 64 * cg + 32 * h),
                                                          a_lo0 + (uint32_t)(i * 512 + h * 2), desc_hi_a,
-                                                         b_lo0 + (uint32_t)h * (((2 * BN * 16) >> 4) + 32u), desc_hi, idesc32,
-                                                         (fs | fr) ? 1u : first);
+                                                         b_lo0 + (uint32_t)h * (((2 * BROWS * 16) >> 4) + 32u), desc_hi, idesc32,
+                                                         (fs | fr) ? 1u : 0u);
                                 }
                             } else {
 #pragma unroll
@@ -526,7 +542,7 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     constexpr bool dw = DW;
     constexpr int MB = mb_for(BN);
     constexpr int TM = 128 * MB;
-    constexpr int B_TILE = BN * 64;
+    constexpr int B_TILE = (DW ? 64 : BN) * 64;
     constexpr bool TMA = true;
     constexpr int PLANES = STRIDE == 2 ? 4 : 1;
     // an even pitch keeps every box (one padded row of PW slots x 64 B) 128-byte aligned
@@ -695,13 +711,21 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
 
 namespace f8host {
 
-// depthwise 3x3 stride 1 on the tensor core: every 64-channel group is a dense 64 -> 64 conv
+// depthwise 3x3 (stride 1, stride 2 for even input sizes) on the tensor core: every 64-channel group is a dense 64 -> 64 conv
 // with a diagonal weight matrix (F8_ERR_UNSUPPORTED => the CUDA-core kernel of dw_conv.cu)
 int launch_conv3x3_dw(const f8_conv_args &a, cudaStream_t s) {
-    if (a.kh != 3 || a.kw != 3 || a.pad != 1 || a.stride != 1 || a.cin_pad != a.cout_pad || a.cin_pad % 16 != 0 ||
-        a.hin != a.hout || a.win != a.wout || a.out_f32 != nullptr)
+    if (a.kh != 3 || a.kw != 3 || a.pad != 1 || a.cin_pad != a.cout_pad || a.cin_pad % 16 != 0 || a.out_f32 != nullptr)
         return F8_ERR_UNSUPPORTED;
-    return launch_bn<64, 1, true>(a, s);
+    if (a.stride == 1 && a.hin == a.hout && a.win == a.wout) return launch_bn<64, 1, true>(a, s);
+    // stride 2: four parity planes per stage -> 256-pixel tiles, two channel groups per tile
+    // (a partial last channel group costs a full one here: measured slower than the CUDA-core kernel
+    // for MobileNetV2's 96- and 144-channel stride-2 layers, so those stay there)
+    if (a.stride == 2 && a.hin == 2 * a.hout && a.win == 2 * a.wout && a.cout_pad % 64 == 0) {
+        const int rc = launch_bn<128, 2, true>(a, s);
+        // wide images: 128-pixel tiles, four channel groups per tile
+        return rc == F8_ERR_UNSUPPORTED ? launch_bn<256, 2, true>(a, s) : rc;
+    }
+    return F8_ERR_UNSUPPORTED;
 }
 
 // F8_ERR_UNSUPPORTED => the caller falls back to the gather kernel (conv_umma.cu)

@@ -174,9 +174,10 @@ namespace f8host {
 
 int launch_dw3x3(const f8_conv_args &a, cudaStream_t s) {
 #ifdef F8_WITH_UMMA
-    // stride 1: the tensor-core kernel (diagonal 64 x 64 weight blocks over the TMA-staged patch)
+    // the tensor-core kernel (diagonal 64 x 64 weight blocks over the TMA-staged patch); odd input
+    // sizes at stride 2 stay on the CUDA cores
     static const bool cuda_core_only = getenv("F8_DW_CUDA_CORE") != nullptr;
-    if (!cuda_core_only && a.stride == 1) {
+    if (!cuda_core_only) {
         const int rc = launch_conv3x3_dw(a, s);
         if (rc != F8_ERR_UNSUPPORTED) return rc;
     }
