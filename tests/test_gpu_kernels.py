@@ -149,8 +149,11 @@ def test_linear_float_logits(G, f8lib, backend):
     assert np.array_equal(f.reshape(2, 1000), yf)
 
 
+# (channels, stride, input size).  Stride 1 and full-group even-size stride 2 run on the tensor core
+# (diagonal weight blocks: conv3x3_umma.cu), the others on the CUDA-core kernel (dw_conv.cu).
 DW_SHAPES = [(32, 1, 16), (96, 2, 16), (144, 1, 9), (144, 2, 14), (24, 1, 7), (960, 1, 7),
-             (64, 2, 15)]
+             (64, 2, 15), (128, 2, 28), (192, 2, 14), (64, 2, 112), (32, 1, 112), (576, 2, 14),
+             (160, 1, 14)]
 
 
 @pytest.mark.parametrize("shape", DW_SHAPES, ids=lambda s: "x".join(map(str, s)))
