@@ -41,7 +41,9 @@ constexpr int BK = 64;
 // per SM with 16 of them, BN <= 128 two CTAs per SM with 8 each: 16 epilogue warps per SM.
 __host__ __device__ constexpr int epi_warps_for(int bn) { return bn == 256 ? 16 : 8; }
 constexpr int PRODUCERS = 128;
-__host__ __device__ constexpr int threads_for(int bn) { return (epi_warps_for(bn) + 5) * 32; }
+// gather path: 4 producer warps + the MMA warp; TMA path: one producer warp + the MMA warp (fewer
+// threads = a higher register cap for the epilogue: 96 instead of 72 / 80)
+__host__ __device__ constexpr int threads_for(int bn, bool tma_a) { return (epi_warps_for(bn) + (tma_a ? 2 : 5)) * 32; }
 // ring depth per tile width: ~96-120 KB of operand bytes in flight per CTA
 __host__ __device__ constexpr int stages_for(int bn) { return bn <= 64 ? 8 : (bn <= 128 ? 6 : 5); }
 constexpr int A_STAGE = BM * BK;          // 8192 B: [4 chunks][128 rows][16 B]
@@ -68,7 +70,7 @@ using namespace f8u;
 // TMA box {64 channels, 128 pixels} of the activation seen as a (C, M) matrix, landing in the
 // 64-byte-swizzled K-major layout; rows past M are the out-of-bounds zero fill.
 template <int BN, bool A_SIGNED, bool SMALL_C, bool TMA_A>
-__global__ void __launch_bounds__(threads_for(BN), (BN <= 128) ? 2 : 1)
+__global__ void __launch_bounds__(threads_for(BN, TMA_A), (BN <= 128) ? 2 : 1)
 conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const int ntiles_n,
                  const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -76,8 +78,8 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
     constexpr int EPI_WARPS = epi_warps_for(BN);
     constexpr int EPI_THREADS = EPI_WARPS * 32;
     constexpr int PRODUCER_WARP0 = EPI_WARPS;     // 4 warps: A gather (+ its thread 0: B bulk copies)
-    constexpr int MMA_WARP = EPI_WARPS + 4;       // TMEM alloc, one elected lane issues tcgen05.mma
-    constexpr int THREADS = threads_for(BN);
+    constexpr int MMA_WARP = EPI_WARPS + (TMA_A ? 1 : 4);   // TMEM alloc, one elected lane issues tcgen05.mma
+    constexpr int THREADS = threads_for(BN, TMA_A);
     constexpr int S = stages_for(BN);
     constexpr int B_STAGE = BN * BK;
     constexpr int B_CHUNK = BN * 16;
@@ -402,7 +404,7 @@ int launch_t(const UGeom &g, const f8::Epilogue &ep, cudaStream_t s) {
     const int per_sm = (BN <= 128) ? 2 : 1;
     long long grid = (long long)num_sms * per_sm;
     if (grid > total) grid = total;
-    kern<<<(unsigned)grid, threads_for(BN), smem_bytes, s>>>(g, ep, mtiles, ntn, tmap);
+    kern<<<(unsigned)grid, threads_for(BN, TMA_A), smem_bytes, s>>>(g, ep, mtiles, ntn, tmap);
     F8_CUDA(cudaGetLastError());
     return F8_OK;
 }
