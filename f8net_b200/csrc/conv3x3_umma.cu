@@ -102,7 +102,7 @@ struct PGeom {
     } while (0)
 
 template <int BN, bool A_SIGNED, bool PLAIN_U8, int STRIDE, bool DW>
-__global__ void __launch_bounds__((epi_warps_for(PLAIN_U8) + 6) * 32, 1)
+__global__ void __launch_bounds__((epi_warps_for(PLAIN_U8) + 3) * 32, 1)
 conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant__ TMaps tmaps) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // stride 1: the patch arrives by TMA in the 64-byte-swizzled K-major layout [slot][64 B]
@@ -113,8 +113,8 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     constexpr int EPI_WARPS = epi_warps_for(PLAIN_U8);
     constexpr int EPI_THREADS = EPI_WARPS * 32;
     constexpr int LOADER_WARP0 = EPI_WARPS;
-    constexpr int MMA_WARP = EPI_WARPS + 4;
-    constexpr int WLOAD_WARP = EPI_WARPS + 5;
+    constexpr int MMA_WARP = EPI_WARPS + 1;       // one TMA warp, one MMA warp, one weight loader:
+    constexpr int WLOAD_WARP = EPI_WARPS + 2;     // 19 warps leave the epilogue a 96-register cap
     constexpr int MB = mb_for(BN);
     constexpr int TM = 128 * MB;
     constexpr int SB_MAX = sb_for(BN, PLAIN_U8);
@@ -674,11 +674,11 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
         if (rc != F8_OK) return rc;
     }
     if (a.in_signed) {
-        if (plain) conv3x3_umma_kernel<BN, true, true, STRIDE, DW><<<gr, (epi_warps_for(true) + 6) * 32, smem_launch, s>>>(g, ep, tmaps);
-        else conv3x3_umma_kernel<BN, true, false, STRIDE, DW><<<gr, (epi_warps_for(false) + 6) * 32, smem_launch, s>>>(g, ep, tmaps);
+        if (plain) conv3x3_umma_kernel<BN, true, true, STRIDE, DW><<<gr, (epi_warps_for(true) + 3) * 32, smem_launch, s>>>(g, ep, tmaps);
+        else conv3x3_umma_kernel<BN, true, false, STRIDE, DW><<<gr, (epi_warps_for(false) + 3) * 32, smem_launch, s>>>(g, ep, tmaps);
     } else {
-        if (plain) conv3x3_umma_kernel<BN, false, true, STRIDE, DW><<<gr, (epi_warps_for(true) + 6) * 32, smem_launch, s>>>(g, ep, tmaps);
-        else conv3x3_umma_kernel<BN, false, false, STRIDE, DW><<<gr, (epi_warps_for(false) + 6) * 32, smem_launch, s>>>(g, ep, tmaps);
+        if (plain) conv3x3_umma_kernel<BN, false, true, STRIDE, DW><<<gr, (epi_warps_for(true) + 3) * 32, smem_launch, s>>>(g, ep, tmaps);
+        else conv3x3_umma_kernel<BN, false, false, STRIDE, DW><<<gr, (epi_warps_for(false) + 3) * 32, smem_launch, s>>>(g, ep, tmaps);
     }
     F8_CUDA(cudaGetLastError());
     if (want_stats) {
