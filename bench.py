@@ -370,7 +370,8 @@ def gpu_arm(args):
         d = fam[dom_kind]
         kind_names = {C.F8_OP_CONVERT_INPUT: "convert_input", C.F8_OP_CONV_DENSE: "conv_dense",
                       C.F8_OP_CONV_DW: "conv_dw3x3", C.F8_OP_MAXPOOL: "maxpool",
-                      C.F8_OP_POOL_REQUANT: "pool_requant", C.F8_OP_HEAD_POOL: "head_conv_pool"}
+                      C.F8_OP_POOL_REQUANT: "pool_requant", C.F8_OP_HEAD_POOL: "head_conv_pool",
+                      C.F8_OP_POOL_FC: "pool_fc"}
         achieved = d["bytes"] / (d["ms"] / 1e3) / 1e9 if d["ms"] > 0 else 0.0
         # DRAM bytes per launch of this kernel family from the committed `ncu --set full` capture
         traffic = None

@@ -13,7 +13,7 @@ F8_ABI_VERSION = 1
 F8_OK, F8_ERR_ARG, F8_ERR_CUDA, F8_ERR_UNSUPPORTED, F8_ERR_NOMEM = 0, -1, -2, -3, -4
 F8_IN_NCHW_I32, F8_IN_NHWC4_8, F8_IN_NCHW_F32, F8_IN_NHWC3_U8 = 0, 1, 2, 3
 F8_OP_CONVERT_INPUT, F8_OP_CONV_DENSE, F8_OP_CONV_DW, F8_OP_MAXPOOL, F8_OP_POOL_REQUANT, \
-    F8_OP_HEAD_POOL = range(6)
+    F8_OP_HEAD_POOL, F8_OP_POOL_FC = range(7)
 
 _i32 = ctypes.c_int32
 _i32p = ctypes.POINTER(ctypes.c_int32)
@@ -82,6 +82,7 @@ SYMBOLS = {
     "f8_maxpool3x3s2": (ctypes.c_int, [ctypes.POINTER(f8_conv_args), _vp]),
     "f8_pool_requant": (ctypes.c_int, [ctypes.POINTER(f8_conv_args), _vp]),
     "f8_head_pool": (ctypes.c_int, [ctypes.POINTER(f8_conv_args), _vp]),
+    "f8_pool_fc": (ctypes.c_int, [ctypes.POINTER(f8_conv_args), _vp]),
     "f8_convert_input": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
     "f8_requant_i32": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_int, _vp]),

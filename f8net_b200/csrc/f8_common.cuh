@@ -324,6 +324,7 @@ inline size_t dw_dense_offset(int cpad) { return ((size_t)12 * (size_t)cpad + 25
 inline size_t dw_pack_bytes(int cpad) { return dw_dense_offset(cpad) + (size_t)((cpad + 63) / 64) * 36 * 64 * 16; }
 int launch_maxpool(const f8_conv_args &a, cudaStream_t s);
 int launch_pool_requant(const f8_conv_args &a, cudaStream_t s);
+int launch_pool_fc(const f8_conv_args &a, cudaStream_t s);
 int launch_convert_input(const int32_t *x, void *out, int n, int h, int w, int is_signed,
                          cudaStream_t s);
 int launch_requant_i32(const int32_t *x, int32_t *y, size_t count, int shift, int is_signed,

@@ -248,14 +248,16 @@ extern "C" int f8_plan_create(const f8_model_desc *desc, int device, f8_plan **o
         if (!rc) rc = check_shift(o.carry_shift, "residual");
         if (!rc) rc = check_shift(o.out_shift[0], "requant");
         if (!rc) rc = check_shift(o.out_shift[1], "requant");
-        if (!rc && (o.kind == F8_OP_CONV_DENSE || o.kind == F8_OP_CONV_DW || o.kind == F8_OP_HEAD_POOL)) {
+        if (!rc && (o.kind == F8_OP_CONV_DENSE || o.kind == F8_OP_CONV_DW || o.kind == F8_OP_HEAD_POOL ||
+                    o.kind == F8_OP_POOL_FC)) {
             if (!o.weight || !o.bias) {
                 set_error("plan_create: op %d has no weight / bias", i);
                 rc = F8_ERR_ARG;
             } else {
                 po.w_off = blob;
-                blob += align_up(f8_pack_weights_bytes(o.kind == F8_OP_HEAD_POOL ? F8_OP_CONV_DENSE : o.kind,
-                                                       o.cin, o.cout, o.cin_pad, o.cout_pad, o.kh, o.kw),
+                const bool fc = o.kind == F8_OP_POOL_FC;       // the classifier: a 1x1 dense pack
+                blob += align_up(f8_pack_weights_bytes(o.kind == F8_OP_CONV_DW ? o.kind : F8_OP_CONV_DENSE, o.cin,
+                                                       o.cout, o.cin_pad, o.cout_pad, fc ? 1 : o.kh, fc ? 1 : o.kw),
                                  kAlign);
                 po.b_off = blob;
                 blob += align_up((size_t)o.cout_pad * sizeof(int32_t), kAlign);
@@ -274,9 +276,12 @@ extern "C" int f8_plan_create(const f8_model_desc *desc, int device, f8_plan **o
     std::vector<uint8_t> host(blob ? blob : 1, 0);
     for (PlanOp &po : p->ops) {
         const f8_op &o = po.op;
-        if (o.kind != F8_OP_CONV_DENSE && o.kind != F8_OP_CONV_DW && o.kind != F8_OP_HEAD_POOL) continue;
-        int rc = f8_pack_weights(o.kind == F8_OP_HEAD_POOL ? F8_OP_CONV_DENSE : o.kind, o.weight, o.cin,
-                                 o.cout, o.cin_pad, o.cout_pad, o.kh, o.kw, host.data() + po.w_off);
+        if (o.kind != F8_OP_CONV_DENSE && o.kind != F8_OP_CONV_DW && o.kind != F8_OP_HEAD_POOL &&
+            o.kind != F8_OP_POOL_FC)
+            continue;
+        const bool fc = o.kind == F8_OP_POOL_FC;
+        int rc = f8_pack_weights(o.kind == F8_OP_CONV_DW ? o.kind : F8_OP_CONV_DENSE, o.weight, o.cin, o.cout,
+                                 o.cin_pad, o.cout_pad, fc ? 1 : o.kh, fc ? 1 : o.kw, host.data() + po.w_off);
         if (rc) { delete p; return rc; }
         std::memcpy(host.data() + po.b_off, o.bias, (size_t)o.cout * sizeof(int32_t));
         po.op.weight = nullptr;   // host pointers are not kept: the caller owns them
@@ -430,6 +435,7 @@ static int run_op(const f8_plan *p, const PlanOp &po, int n, const uint8_t *x, i
         case F8_OP_CONV_DW: return f8host::launch_dw3x3(a, s);
         case F8_OP_MAXPOOL: return f8host::launch_maxpool(a, s);
         case F8_OP_POOL_REQUANT: return f8host::launch_pool_requant(a, s);
+        case F8_OP_POOL_FC: return f8host::launch_pool_fc(a, s);
         case F8_OP_HEAD_POOL: {
             if (p->backend != 1) {
                 set_error("plan_run: the plan fuses head conv + max-pool (tcgen05 backend); rebuild it "
@@ -606,6 +612,13 @@ extern "C" int f8_maxpool3x3s2(const f8_conv_args *a, void *stream) {
     int rc = check_args(a, "maxpool3x3s2");
     if (rc) return rc;
     return f8host::launch_maxpool(*a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int f8_pool_fc(const f8_conv_args *a, void *stream) {
+    int rc = check_args(a, "pool_fc");
+    if (rc) return rc;
+    if (!a->wpack || !a->bias || !a->out_f32) { set_error("pool_fc: no weights / bias / output"); return F8_ERR_ARG; }
+    return f8host::launch_pool_fc(*a, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int f8_head_pool(const f8_conv_args *a, void *stream) {

@@ -104,6 +104,85 @@ pool_requant_kernel(const int32_t *__restrict__ in, int n, int hw, int cpad,
     }
 }
 
+// The network tail in one launch: FXQAvgPool2d (sum over the hw pixels, wrapping) + requant to
+// 8 bit + the classifier nn.Linear + .float()  (fix_quant_ops.py:126-134, fix_resnet.py:367-383).
+// One CTA = TAIL_IMGS images (2, or 4 when the weight matrix is large: fewer re-reads from L2): phase 1 pools and requantises their channel vectors into shared
+// memory, phase 2 gives every thread output neurons o = tid, tid + THREADS, ... for all the images
+// of the CTA: a weight chunk (16 K bytes of row o, from the dense pack [K/16][rows][16]) is loaded
+// once and multiplied with the matching 16 bytes of every image (dp4a, int32 wrap == the reference's
+// int32 addmm).  Consecutive threads read consecutive 16-byte weight pieces.
+constexpr int TAIL_THREADS = 512;
+
+template <bool Q_SIGNED, int TAIL_IMGS>
+__global__ void __launch_bounds__(TAIL_THREADS)
+pool_fc_kernel(const int32_t *__restrict__ in, int n, int hw, int cpad, const uint4 *__restrict__ w, int wrows,
+               const int32_t *__restrict__ bias, int cout, int shift, float *__restrict__ out, int out_ld) {
+    extern __shared__ __align__(16) uint8_t q[];            // [TAIL_IMGS][cpad]
+    const int img0 = blockIdx.x * TAIL_IMGS;
+    const int nimg = min(TAIL_IMGS, n - img0);
+    const int c4n = cpad >> 2;
+    // phase 1: four adjacent lanes share one (image, channel quad): lane part p sums pixels p, p+4, ...
+    // (consecutive pixels of a quad are 16 B apart in the carry layout: the four lanes read 64
+    // contiguous bytes), then two shuffles finish the sum
+    for (int idx = threadIdx.x; idx < TAIL_IMGS * c4n * 4; idx += TAIL_THREADS) {
+        const int item = idx >> 2, part = idx & 3;
+        const int li = item / c4n, c4 = item - li * c4n;
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        if (li < nimg) {
+#pragma unroll 4
+            for (int i = part; i < hw; i += 4) {
+                const int4 v = __ldg(reinterpret_cast<const int4 *>(
+                    in + f8::carry_off((size_t)(img0 + li) * hw + i, c4 * 4, cpad)));
+                a0 += (uint32_t)v.x; a1 += (uint32_t)v.y; a2 += (uint32_t)v.z; a3 += (uint32_t)v.w;
+            }
+        }
+#pragma unroll
+        for (int d = 1; d < 4; d <<= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, d); a1 += __shfl_xor_sync(0xffffffffu, a1, d);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, d); a3 += __shfl_xor_sync(0xffffffffu, a3, d);
+        }
+        if (part == 0) {
+            uint32_t pk = 0;
+            if (li < nimg)
+                pk = ((uint32_t)f8::requant((int32_t)a0, shift, Q_SIGNED) & 0xffu) |
+                     (((uint32_t)f8::requant((int32_t)a1, shift, Q_SIGNED) & 0xffu) << 8) |
+                     (((uint32_t)f8::requant((int32_t)a2, shift, Q_SIGNED) & 0xffu) << 16) |
+                     (((uint32_t)f8::requant((int32_t)a3, shift, Q_SIGNED) & 0xffu) << 24);
+            reinterpret_cast<uint32_t *>(q)[item] = pk;
+        }
+    }
+    __syncthreads();
+    const int kchunks = cpad >> 4;
+    for (int o = threadIdx.x; o < cout; o += TAIL_THREADS) {
+        int32_t acc[TAIL_IMGS];
+#pragma unroll
+        for (int i = 0; i < TAIL_IMGS; ++i) acc[i] = 0;
+#pragma unroll 4
+        for (int kc = 0; kc < kchunks; ++kc) {
+            const uint4 wv = __ldg(w + (size_t)kc * wrows + o);
+#pragma unroll
+            for (int i = 0; i < TAIL_IMGS; ++i) {
+                const uint4 x = *reinterpret_cast<const uint4 *>(q + i * cpad + kc * 16);     // broadcast
+                if (Q_SIGNED) {
+                    asm("dp4a.s32.s32 %0, %1, %2, %0;" : "+r"(acc[i]) : "r"(x.x), "r"(wv.x));
+                    asm("dp4a.s32.s32 %0, %1, %2, %0;" : "+r"(acc[i]) : "r"(x.y), "r"(wv.y));
+                    asm("dp4a.s32.s32 %0, %1, %2, %0;" : "+r"(acc[i]) : "r"(x.z), "r"(wv.z));
+                    asm("dp4a.s32.s32 %0, %1, %2, %0;" : "+r"(acc[i]) : "r"(x.w), "r"(wv.w));
+                } else {
+                    asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(acc[i]) : "r"(x.x), "r"(wv.x));
+                    asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(acc[i]) : "r"(x.y), "r"(wv.y));
+                    asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(acc[i]) : "r"(x.z), "r"(wv.z));
+                    asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(acc[i]) : "r"(x.w), "r"(wv.w));
+                }
+            }
+        }
+        const uint32_t b = (uint32_t)__ldg(bias + o);
+#pragma unroll
+        for (int i = 0; i < TAIL_IMGS; ++i)
+            if (i < nimg) out[(size_t)(img0 + i) * out_ld + o] = (float)(int32_t)((uint32_t)acc[i] + b);
+    }
+}
+
 // x int32 [n,3,h,w] -> out 8-bit [n,h,w,4]; channel 3 = 0.  Keeps the low byte: u8 0..255
 // and s8 -127..127 both survive the truncation unchanged.
 __global__ void __launch_bounds__(THREADS)
@@ -229,6 +308,26 @@ int launch_pool_requant(const f8_conv_args &a, cudaStream_t s) {
     pool_requant_kernel<<<grid_for(total), THREADS, 0, s>>>(static_cast<const int32_t *>(a.in),
                                                             a.n, a.hin * a.win, a.cin_pad,
                                                             make_ep(a));
+    F8_CUDA(cudaGetLastError());
+    return F8_OK;
+}
+
+int launch_pool_fc(const f8_conv_args &a, cudaStream_t s) {
+    const DensePack pk = dense_pack_geometry(a.cin_pad, a.cout_pad, 1, 1);
+    if (pk.mode != 0 || a.cin_pad % 16 != 0 || !a.out_f32 || a.out[0] != nullptr || a.carry_in != nullptr ||
+        (size_t)4 * a.cin_pad > 96 * 1024) {
+        set_error("pool_fc: unsupported geometry (cin_pad %d)", a.cin_pad);
+        return F8_ERR_UNSUPPORTED;
+    }
+    const int imgs = 2;        // (4 per CTA halves the weight re-reads but measured slower: fewer CTAs)
+    const unsigned grid = (unsigned)((a.n + imgs - 1) / imgs);
+    const size_t smem = (size_t)imgs * a.cin_pad;
+    auto kern = imgs == 4 ? (a.out_signed[0] ? pool_fc_kernel<true, 4> : pool_fc_kernel<false, 4>)
+                          : (a.out_signed[0] ? pool_fc_kernel<true, 2> : pool_fc_kernel<false, 2>);
+    if (smem > 48 * 1024) F8_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, TAIL_THREADS, smem, s>>>(static_cast<const int32_t *>(a.in), a.n, a.hin * a.win, a.cin_pad,
+                                         static_cast<const uint4 *>(a.wpack), pk.rows, a.bias, a.cout,
+                                         a.out_shift[0], a.out_f32, a.out_f32_ld);
     F8_CUDA(cudaGetLastError());
     return F8_OK;
 }

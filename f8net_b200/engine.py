@@ -64,7 +64,9 @@ class Engine:
         if backend is None:
             backend = 1 if self.lib.f8_has_umma(self.device.index) else 0
         # the fused head conv + max-pool launch exists on the tcgen05 backend only
-        self.plan: Plan = build_plan(net, _to_numpy_sd(state_dict), fuse_head=(int(backend) == 1))
+        # (the fused tail launch -- pool + requant + classifier -- likewise)
+        self.plan: Plan = build_plan(net, _to_numpy_sd(state_dict), fuse_head=(int(backend) == 1),
+                                     fuse_tail=(int(backend) == 1))
         self.chunk = int(chunk)
         desc, keep = self.plan.to_desc()
         handle = ctypes.c_void_p()

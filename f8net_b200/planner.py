@@ -220,7 +220,8 @@ def _out_hw(h, k, s, p):
     return (h + 2 * p - k) // s + 1
 
 
-def build_plan(net: NetSpec, sd: Dict[str, np.ndarray], fuse_head: bool = False) -> Plan:
+def build_plan(net: NetSpec, sd: Dict[str, np.ndarray], fuse_head: bool = False,
+               fuse_tail: bool = False) -> Plan:
     """Lower the integer graph to fused launches.  ``sd`` maps the reference state_dict keys
     to integer arrays (numpy or anything np.asarray accepts).  ``fuse_head``: emit the ResNet
     head conv + ReLU + max-pool as one F8_OP_HEAD_POOL launch (tcgen05 backend)."""
@@ -307,7 +308,17 @@ def build_plan(net: NetSpec, sd: Dict[str, np.ndarray], fuse_head: bool = False)
     fa_pool = fa + 6                       # shiftnum = round(log2(49)), fix_quant_ops.py:121-122
     if fa_pool > 32:                       # the reference's own assert, fix_quant_ops.py:129
         raise AssertionError("FXQAvgPool2d: output_fraclen <= 32 violated")
-    _, _, fw_fc, fi_fc = _layer(sd, net.fc)
+    w_fc, b_fc, fw_fc, fi_fc = _layer(sd, net.fc)
+    if fuse_tail:
+        # FXQAvgPool2d + int_op_only_fix_quant + classifier + .float() in one launch
+        # (fix_quant_ops.py:126-134, fix_resnet.py:367-383): the pooled 8-bit vector stays on the SM
+        tail = Op(C.F8_OP_POOL_FC, "avgpool+" + net.fc.prefix, cin=net.fc.cin, cout=net.fc.cout,
+                  cin_pad=cur.cout_pad, cout_pad=cpad(net.fc.cout), k=hw, stride=1, pad=0, hin=hw, win=hw,
+                  hout=1, wout=1, in_signed=int(net.fc.sym), in_buf=P.carry(cur), weight=w_fc, bias=b_fc,
+                  fa=fw_fc + fi_fc, out_f32=1)
+        tail.outs.append((-1, fa_pool - fi_fc, int(net.fc.sym)))      # requant of the pooled sum, no buffer
+        P.emit(tail)
+        return P.finalize()
     pool = Op(C.F8_OP_POOL_REQUANT, "avgpool", cin=cur.cout, cout=cur.cout, cin_pad=cur.cout_pad,
               cout_pad=cur.cout_pad, k=hw, stride=1, pad=0, hin=hw, win=hw, hout=1, wout=1,
               in_buf=P.carry(cur), fa=fa_pool)

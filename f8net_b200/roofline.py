@@ -69,12 +69,17 @@ def op_work(plan):
         elif op.kind == C.F8_OP_CONV_DW:
             macs = el_out * 9
             wb = op.cout * 9
+        elif op.kind == C.F8_OP_POOL_FC:
+            macs = op.cout * op.cin
+            wb = op.cout * op.cin
         else:
             macs = wb = 0
         b = 0
         if op.kind == C.F8_OP_HEAD_POOL:
             hc = _hw(op.hin, op.k, op.stride, op.pad)
             b = el_in + hc * hc * op.cout       # SURVEY definition: conv in + conv out, pool excluded
+        elif op.kind == C.F8_OP_POOL_FC:
+            b = op.cin + op.cout              # the classifier's 8-bit input + its outputs (pooling excluded)
         elif op.kind in (C.F8_OP_CONV_DENSE, C.F8_OP_CONV_DW):
             b = el_in + el_out
             if op.carry_in_buf >= 0:

@@ -68,8 +68,11 @@ typedef enum f8_op_kind {
     F8_OP_CONV_DW = 2,        /* depthwise 3x3, CUDA-core int MAC, fused epilogue               */
     F8_OP_MAXPOOL = 3,        /* ResNet head 3x3 s2 p1 max-pool with float32 round trip         */
     F8_OP_POOL_REQUANT = 4,   /* FXQAvgPool2d sum over HxW + requant for the classifier         */
-    F8_OP_HEAD_POOL = 5       /* ResNet head fused: 7x7 s2 conv + ReLU + float round trip +
+    F8_OP_HEAD_POOL = 5,      /* ResNet head fused: 7x7 s2 conv + ReLU + float round trip +
                                  3x3 s2 max-pool (tcgen05 backend only); hout/wout = pooled size  */
+    F8_OP_POOL_FC = 6         /* network tail fused: FXQAvgPool2d sum over hin x win + requant
+                                 (out_shift[0] / out_signed[0], no buffer) + nn.Linear + .float()
+                                 (fix_quant_ops.py:126-134, fix_resnet.py:367-383)                */
 } f8_op_kind;
 
 /*
@@ -235,6 +238,10 @@ F8_API int f8_head_pool(const f8_conv_args *a, void *stream);
  * (fix_quant_ops.py:126-134, fix_resnet.py:367-374). in = int32 carry layout, n*h*w pixels,
  * out[0] = 8-bit [n,c_pad]; carry_out (tests) = plain int32 [n,c_pad]. */
 F8_API int f8_pool_requant(const f8_conv_args *a, void *stream);
+/* Replaces: the same + the classifier nn.Linear + .float() (fix_resnet.py:367-383) in one launch.
+ * in = int32 carry layout [n*h*w pixels, cin_pad]; wpack = dense pack of the [cout, cin] weight;
+ * out_shift[0] / out_signed[0] = requant of the pooled sum; out_f32 = float32 [n, out_f32_ld]. */
+F8_API int f8_pool_fc(const f8_conv_args *a, void *stream);
 /* Replaces: the int32 NCHW tensor hand-over at model(x): repack to NHWC4 8 bit.
  * x int32 [n,3,h,w] -> out 8-bit [n,h,w,4]. */
 F8_API int f8_convert_input(const int32_t *x, void *out, int n, int h, int w, void *stream);

@@ -263,6 +263,36 @@ def test_pool_requant(G, f8lib):
     assert np.array_equal(q0.cpu().numpy()[:, :c].astype(np.int32), O.requant(want, 0, 12, False))
 
 
+@pytest.mark.parametrize("shape", [(5, 512, 1000, False), (19, 1280, 1000, False), (3, 2048, 1000, True),
+                                   (9, 48, 37, False)], ids=str)
+def test_pool_fc_fused_tail(G, f8lib, shape):
+    """FXQAvgPool2d + requant + classifier + .float() in one launch (fix_quant_ops.py:126-134,
+    fix_resnet.py:367-383): ragged image counts (CTAs own 8 images), wrap of the pooled sum, both
+    signednesses of the requantised vector, bias near INT_MAX (wrapping add, float rounding)."""
+    n, c, classes, signed = shape
+    rng = np.random.default_rng(n * c)
+    x = rng.integers(-2 ** 20, 2 ** 22, (n, c, 7, 7)).astype(np.int32)
+    x[0, 0] = 2 ** 26                                       # 49 * 2^26 wraps negative as int32
+    w = rng.integers(-127, 128, (classes, c)).astype(np.int32)
+    b = rng.integers(-2 ** 20, 2 ** 20, classes).astype(np.int32)
+    b[1], b[2] = 2 ** 31 - 5, 2 ** 24 + 3
+    shift = 15
+    q = O.requant(O.avgpool_sum(x), 0, shift, signed)
+    _, want = O.linear(q, w, b)
+    a = _args_for_pool(n, c, 7, 1, 7, 1, 0)
+    a.cout, a.cout_pad = classes, cpad(classes)
+    xd = G.dev(nchw_to_carry(x))
+    wd = G.dev(G.pack(f8lib, C.F8_OP_CONV_DENSE, w.reshape(classes, c, 1, 1), cpad(c), cpad(classes)))
+    bd = G.dev(b)
+    out = torch.full((n, classes), -1.0, dtype=torch.float32, device="cuda:0")
+    a.in_, a.wpack, a.bias = xd.data_ptr(), wd.data_ptr(), bd.data_ptr()
+    a.out_shift[0], a.out_signed[0] = shift, int(signed)
+    a.out_f32, a.out_f32_ld = out.data_ptr(), classes
+    C.check(f8lib.f8_pool_fc(ctypes.byref(a), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
 def test_convert_input(G, f8lib):
     rng = np.random.default_rng(11)
     for signed in (False, True):

@@ -129,3 +129,21 @@ def test_planner_rejects_wrong_shapes():
     sd["stage_1_layer_0.body.0.weight"] = np.zeros((128, 64, 1, 1), np.int32)
     with pytest.raises(ValueError, match="stage_1_layer_0.body.0.weight"):
         build_plan(graph_for("resnet18"), sd)
+
+
+def test_fused_tail_plan_keeps_the_algorithmic_work():
+    """fuse_tail folds FXQAvgPool2d + requant + classifier into one POOL_FC launch; the roofline
+    accounting must not change."""
+    from f8net_b200.roofline import network_work, op_work
+    for arch in ("resnet18", "mobilenet_v2"):
+        hs = synth.HEAD_SIGNED[arch]
+        sd = synth.make_state_dict(arch, hs)
+        net = graph_for(arch, hs)
+        a = build_plan(net, sd, fuse_head=True)
+        b = build_plan(net, sd, fuse_head=True, fuse_tail=True)
+        assert len(b.ops) == len(a.ops) - 1 and b.ops[-1].kind == C.F8_OP_POOL_FC and b.ops[-1].out_f32 == 1
+        assert b.ops[-1].outs[0][1:] == a.ops[-2].outs[0][1:]          # same requant of the pooled sum
+        wa, wb = op_work(a), op_work(b)
+        assert sum(r["bytes_per_image"] for r in wa) == sum(r["bytes_per_image"] for r in wb)
+        assert sum(r["ops"] for r in wa) == sum(r["ops"] for r in wb)
+        assert network_work(net)[1] == sum(r["bytes_per_image"] for r in wb)

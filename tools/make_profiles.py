@@ -33,7 +33,9 @@ def family(name):
         return "conv_dw3x3"
     if "umma_kernel" in name or "conv_mma" in name:
         return "conv_dense"
-    if "pool_requant" in name or "pool_fc" in name:
+    if "pool_fc" in name:
+        return "pool_fc"
+    if "pool_requant" in name:
         return "pool_requant"
     if "convert_input" in name:
         return "convert_input"
