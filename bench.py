@@ -239,9 +239,15 @@ def gpu_arm(args):
 
     logits = torch.empty((B, eng.net.num_classes), dtype=torch.float32, device=device)
 
-    # CUDA graphs of the R step variants (launch-bound inner loop); N>1 keeps eager launches
+    # CUDA graphs of the R step variants (launch-bound inner loop).  N>1: the graph holds this
+    # rank's forward pass, writing into its slice of the gather buffer; the NCCL all-gather of the
+    # logits follows it every step
     graphs = None
-    if not args.no_graph and world == 1:
+    full = mine = None
+    if runner is not None:
+        full = runner.gather_buffer(B, xs[0])
+        mine = full[rank]
+    if not args.no_graph:
         for i in range(min(R, 2)):
             step(i)                       # warm every kernel (cudaFuncSetAttribute) before capture
         torch.cuda.synchronize()
@@ -251,13 +257,15 @@ def gpu_arm(args):
             for i in range(R):
                 gr = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gr, stream=cs):
-                    eng.run_device(xs[i], out=logits, stream=cs)
+                    eng.run_device(xs[i], out=logits if mine is None else mine, stream=cs)
                 graphs.append(gr)
         torch.cuda.synchronize()
 
     def do_step(i):
         if graphs is not None:
             graphs[i % R].replay()
+            if runner is not None:
+                dist.all_gather_into_tensor(full.view(-1), mine.reshape(-1))
         else:
             step(i)
 
