@@ -63,7 +63,7 @@ dw3x3_kernel(const DwGeom g, const f8::Epilogue ep, const long long total, const
     const int c16n = g.cpad >> 4;                      // 16-channel groups per pixel
     long long idx = blockIdx.x * (long long)THREADS + threadIdx.x;
     if (idx >= total) return;
-    const int c16 = (int)(idx % c16n);
+    const int c16 = (int)((uint32_t)idx % (uint32_t)c16n);
     const int c4n = g.cpad >> 2;
     // weights of this thread's 16 channels: word j of channel quad c4 at w[j * c4n + c4]
     uint32_t wv[4][12];
@@ -86,11 +86,13 @@ dw3x3_kernel(const DwGeom g, const f8::Epilogue ep, const long long total, const
     }
     const uint4 *in16 = reinterpret_cast<const uint4 *>(g.in);
     for (; idx < total; idx += stride_items) {
-        const long long pix = idx / c16n;              // output pixel (image-major)
-        const int q = (int)(pix % g.wout);
-        const long long t = pix / g.wout;
-        const int p = (int)(t % g.hout);
-        const int img = (int)(t / g.hout);
+        // 32-bit index arithmetic (the launcher guarantees total < 2^31): 64-bit divisions cost
+        // ~100 instructions each
+        const uint32_t pix = (uint32_t)idx / (uint32_t)c16n;      // output pixel (image-major)
+        const uint32_t t = pix / (uint32_t)g.wout;
+        const int q = (int)(pix - t * (uint32_t)g.wout);
+        const int img = (int)(t / (uint32_t)g.hout);
+        const int p = (int)(t - (uint32_t)img * (uint32_t)g.hout);
         const int ih0 = p * STRIDE - 1, iw0 = q * STRIDE - 1;
         uint4 x[9];
 #pragma unroll
@@ -205,6 +207,10 @@ int launch_dw3x3(const f8_conv_args &a, cudaStream_t s) {
     ep.cout = a.cout; ep.cout_pad = a.cout_pad;
     const int c16n = g.cpad >> 4;
     const long long total = (long long)g.n * g.hout * g.wout * c16n;
+    if (total >= 0x7fffffffLL) {
+        set_error("conv_dw3x3: %lld items exceed the 32-bit index range", total);
+        return F8_ERR_UNSUPPORTED;
+    }
     // grid: ~2 blocks per SM x 8 waves, rounded so that the thread count is a multiple of the
     // number of channel groups (every thread then keeps one channel group)
     long long blocks = (total + THREADS - 1) / THREADS;
