@@ -14,7 +14,7 @@ for a in resnet18 resnet50 mobilenet_v1 mobilenet_v2; do
 done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $out/${tag}_resnet18_launches.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > $out/${tag}_ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"umma_kernel|head_pool|pool_requant" -s 66 -c 22 \
+ncu --set full --clock-control none --import-source on -k regex:"umma_kernel|head_pool|pool_fc" -s 63 -c 21 \
   -o $out/${tag}_dense python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph > $out/${tag}_ncu_full.log 2>&1
 cat $out/${tag}_tests.log
 cat $out/${tag}_bench_resnet18.json

@@ -10,6 +10,7 @@ and optionally the DRAM bytes per launch per kernel family for bench.py's roofli
 """
 import csv
 import json
+import os
 import re
 import subprocess
 import sys
@@ -66,6 +67,8 @@ def full(rep, out, title, traffic=None):
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     hdr, data = rows[0], rows[2:]
+    if os.environ.get("F8_ROWS"):          # keep exactly one forward pass when the capture window overlaps two
+        data = data[:int(os.environ["F8_ROWS"])]
     ix = {h: i for i, h in enumerate(hdr)}
 
     def col(r, name, scale=1.0, fmt="{:.1f}"):
