@@ -30,6 +30,7 @@
 //   warps 0-15 epilogue (the exact integer requantisation is instruction-bound: 16 warps)
 //   | warps 16-19 patch loaders (cp.async, zero fill) | warp 20: one elected lane issues the MMAs
 //   | warp 21 lane 0 weight-tile loader (cp.async.bulk).
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -144,6 +145,11 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     int32_t *sbias = reinterpret_cast<int32_t *>(after + 16);
 
     const long long t_entry = clock64();
+    if (g.stats && threadIdx.x == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        g.stats[blockIdx.x * 16 + 2] = (long long)gt;
+    }
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int total_items = g.n_super * g.ntiles_n;
@@ -174,6 +180,12 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // The next layer's launch may begin its own prologue as this grid's CTAs retire; everything
+    // that touches the previous layer's output (patch TMA, residual carry) waits for that layer
+    // here.  The weight loader does not: weights and biases are plan constants, so it fills
+    // its ring while the previous launch drains.
+    f8::pdl_trigger();
+    if (warp != WLOAD_WARP) f8::pdl_wait();
 
     if (TMA && warp >= LOADER_WARP0 && warp < MMA_WARP) {
         // =========================== patch loader (TMA) ===========================
@@ -530,7 +542,12 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
-    if (g.stats && tid == 0) g.stats[blockIdx.x * 16 + 11] = clock64() - t_entry;
+    if (g.stats && tid == 0) {
+        g.stats[blockIdx.x * 16 + 11] = clock64() - t_entry;
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        g.stats[blockIdx.x * 16 + 13] = (long long)gt;
+    }
 }
 
 }  // namespace
@@ -673,12 +690,13 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
         const int rc = f8host::encode_tmap_u8_4d(&tmaps.m[p], base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc != F8_OK) return rc;
     }
+    const unsigned th = (epi_warps_for(plain) + 3) * 32;
     if (a.in_signed) {
-        if (plain) conv3x3_umma_kernel<BN, true, true, STRIDE, DW><<<gr, (epi_warps_for(true) + 3) * 32, smem_launch, s>>>(g, ep, tmaps);
-        else conv3x3_umma_kernel<BN, true, false, STRIDE, DW><<<gr, (epi_warps_for(false) + 3) * 32, smem_launch, s>>>(g, ep, tmaps);
+        if (plain) F8_CUDA(f8host::launch_pdl(conv3x3_umma_kernel<BN, true, true, STRIDE, DW>, gr, th, smem_launch, s, g, ep, tmaps));
+        else F8_CUDA(f8host::launch_pdl(conv3x3_umma_kernel<BN, true, false, STRIDE, DW>, gr, th, smem_launch, s, g, ep, tmaps));
     } else {
-        if (plain) conv3x3_umma_kernel<BN, false, true, STRIDE, DW><<<gr, (epi_warps_for(true) + 3) * 32, smem_launch, s>>>(g, ep, tmaps);
-        else conv3x3_umma_kernel<BN, false, false, STRIDE, DW><<<gr, (epi_warps_for(false) + 3) * 32, smem_launch, s>>>(g, ep, tmaps);
+        if (plain) F8_CUDA(f8host::launch_pdl(conv3x3_umma_kernel<BN, false, true, STRIDE, DW>, gr, th, smem_launch, s, g, ep, tmaps));
+        else F8_CUDA(f8host::launch_pdl(conv3x3_umma_kernel<BN, false, false, STRIDE, DW>, gr, th, smem_launch, s, g, ep, tmaps));
     }
     F8_CUDA(cudaGetLastError());
     if (want_stats) {
@@ -701,6 +719,13 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
                 pro += (double)(host[b * 16 + 15] >> 32) / (double)grid;
                 fa += (double)(host[b * 16 + 15] & 0xffffffffll) / (double)grid;
             }
+            long long e0 = host[2], e1 = host[2], x0 = host[13], x1 = host[13];
+            for (long long b = 0; b < grid; ++b) {
+                e0 = std::min(e0, host[b * 16 + 2]); e1 = std::max(e1, host[b * 16 + 2]);
+                x0 = std::min(x0, host[b * 16 + 13]); x1 = std::max(x1, host[b * 16 + 13]);
+            }
+            fprintf(stderr, "[f8 stats]   globaltimer: CTA entries spread %lld ns, first entry -> first exit %lld ns, -> last exit %lld ns; mean CTA life %.0f cycles\n",
+                    e1 - e0, x0 - e0, x1 - e0, acc[11]);
             fprintf(stderr, "[f8 stats]   timeline: prologue done @%.0f, first patch landed @%.0f, kernel end @%.0f cycles (acc[11])\n", pro, fa, acc[11]);
         }
     }

@@ -117,6 +117,10 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // programmatic dependent launch: the prologue above overlaps the previous layer's tail; the
+    // trigger comes after this CTA holds its TMEM columns (a dependent CTA must never take them first)
+    f8::pdl_trigger();
+    f8::pdl_wait();
 
     if (TMA_A && warp >= PRODUCER_WARP0 && warp < MMA_WARP) {
         // =========================== producer: one thread, A by TMA + B bulk copies =====
@@ -404,7 +408,7 @@ int launch_t(const UGeom &g, const f8::Epilogue &ep, cudaStream_t s) {
     const int per_sm = (BN <= 128) ? 2 : 1;
     long long grid = (long long)num_sms * per_sm;
     if (grid > total) grid = total;
-    kern<<<(unsigned)grid, threads_for(BN, TMA_A), smem_bytes, s>>>(g, ep, mtiles, ntn, tmap);
+    F8_CUDA(f8host::launch_pdl(kern, (unsigned)grid, threads_for(BN, TMA_A), smem_bytes, s, g, ep, mtiles, ntn, tmap));
     F8_CUDA(cudaGetLastError());
     return F8_OK;
 }

@@ -80,6 +80,10 @@ dw3x3_kernel(const DwGeom g, const f8::Epilogue ep, const long long total, const
     const bool has_carry = ep.carry_in != nullptr;
     const bool plain = f8::epilogue_is_plain_u8(ep);
     const f8::EpiConst kc = f8::epi_const(ep, has_carry);
+    // programmatic dependent launch: weights and bias (plan constants) are in registers before
+    // the previous layer has finished; its output is only touched below
+    f8::pdl_trigger();
+    f8::pdl_wait();
     if (plain) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) bias[i] = (int32_t)((uint32_t)bias[i] + (1u << (ep.shift0 - 1)));
@@ -222,11 +226,11 @@ int launch_dw3x3(const f8_conv_args &a, cudaStream_t s) {
     const long long stride_items = blocks * THREADS;
     const bool sgn = a.in_signed != 0;
     if (a.stride == 1) {
-        if (sgn) dw3x3_kernel<true, 1><<<(unsigned)blocks, THREADS, 0, s>>>(g, ep, total, stride_items);
-        else dw3x3_kernel<false, 1><<<(unsigned)blocks, THREADS, 0, s>>>(g, ep, total, stride_items);
+        if (sgn) F8_CUDA(f8host::launch_pdl(dw3x3_kernel<true, 1>, (unsigned)blocks, THREADS, 0, s, g, ep, total, stride_items));
+        else F8_CUDA(f8host::launch_pdl(dw3x3_kernel<false, 1>, (unsigned)blocks, THREADS, 0, s, g, ep, total, stride_items));
     } else {
-        if (sgn) dw3x3_kernel<true, 2><<<(unsigned)blocks, THREADS, 0, s>>>(g, ep, total, stride_items);
-        else dw3x3_kernel<false, 2><<<(unsigned)blocks, THREADS, 0, s>>>(g, ep, total, stride_items);
+        if (sgn) F8_CUDA(f8host::launch_pdl(dw3x3_kernel<true, 2>, (unsigned)blocks, THREADS, 0, s, g, ep, total, stride_items));
+        else F8_CUDA(f8host::launch_pdl(dw3x3_kernel<false, 2>, (unsigned)blocks, THREADS, 0, s, g, ep, total, stride_items));
     }
     F8_CUDA(cudaGetLastError());
     return F8_OK;

@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/f8b200.h"
 
@@ -296,6 +297,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched through f8host::launch_pdl may
+// start -- barrier init, TMEM allocation, tensor-map prefetch, weight-ring fill -- while the
+// previous layer's launch is still draining; pdl_wait() returns once that launch has completed
+// and its writes are visible, so it must precede the first access to any activation / carry /
+// logits buffer.  Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() {
+#ifdef F8_PDL_EARLY_TRIGGER
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
 }  // namespace f8
 
 // host-side error plumbing (plan.cu)
@@ -312,6 +325,28 @@ int cuda_fail(cudaError_t e, const char *what);
 
 // kernel launchers implemented in the .cu files, called by plan.cu
 namespace f8host {
+// F8_PDL=0 turns programmatic dependent launch off (plain stream order between layers)
+inline bool pdl_enabled() {
+    static const bool on = [] { const char *e = getenv("F8_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+// Launch with the programmatic-stream-serialization attribute: only for kernels whose every
+// access to the previous launch's output comes after f8::pdl_wait().
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 int launch_conv_mma(const f8_conv_args &a, cudaStream_t s);
 int launch_conv_umma(const f8_conv_args &a, cudaStream_t s);
 int launch_conv3x3_umma(const f8_conv_args &a, cudaStream_t s);

@@ -166,6 +166,10 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // programmatic dependent launch: weights, bias and TMEM are in place before the input
+    // conversion launch (or the previous pass) has finished
+    f8::pdl_trigger();
+    f8::pdl_wait();
 
     if (warp == LOAD_WARP) {
         // =========================== image loader (TMA) ===========================
@@ -429,8 +433,8 @@ int launch_head_pool(const f8_conv_args &a, cudaStream_t s) {
         F8_CUDA(cudaMemsetAsync(stats_dev, 0, 16 * 1024 * sizeof(long long), s));
         g.stats = stats_dev;
     }
-    if (a.in_signed) head_pool2_kernel<true><<<(unsigned)grid, THREADS, SMEM_BYTES, s>>>(g, ep, tmap);
-    else head_pool2_kernel<false><<<(unsigned)grid, THREADS, SMEM_BYTES, s>>>(g, ep, tmap);
+    if (a.in_signed) F8_CUDA(f8host::launch_pdl(head_pool2_kernel<true>, (unsigned)grid, THREADS, SMEM_BYTES, s, g, ep, tmap));
+    else F8_CUDA(f8host::launch_pdl(head_pool2_kernel<false>, (unsigned)grid, THREADS, SMEM_BYTES, s, g, ep, tmap));
     F8_CUDA(cudaGetLastError());
     if (want_stats) {
         static long long host[16 * 1024];

@@ -118,6 +118,8 @@ __global__ void __launch_bounds__(TAIL_THREADS)
 pool_fc_kernel(const int32_t *__restrict__ in, int n, int hw, int cpad, const uint4 *__restrict__ w, int wrows,
                const int32_t *__restrict__ bias, int cout, int shift, float *__restrict__ out, int out_ld) {
     extern __shared__ __align__(16) uint8_t q[];            // [TAIL_IMGS][cpad]
+    f8::pdl_trigger();                                      // programmatic dependent launch:
+    f8::pdl_wait();                                         // the last conv's carry is read below
     const int img0 = blockIdx.x * TAIL_IMGS;
     const int nimg = min(TAIL_IMGS, n - img0);
     const int c4n = cpad >> 2;
@@ -188,6 +190,10 @@ pool_fc_kernel(const int32_t *__restrict__ in, int n, int hw, int cpad, const ui
 __global__ void __launch_bounds__(THREADS)
 convert_input_kernel(const int32_t *__restrict__ x, uint32_t *__restrict__ out, int n, int hw) {
     const long long total = (long long)n * hw;
+    // programmatic dependent launch: the NHWC4 buffer written here may still be read by the
+    // head conv of the previous chunk / pass
+    f8::pdl_trigger();
+    f8::pdl_wait();
     for (long long idx = blockIdx.x * (long long)THREADS + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * THREADS) {
         const int img = (int)(idx / hw);
@@ -325,17 +331,16 @@ int launch_pool_fc(const f8_conv_args &a, cudaStream_t s) {
     auto kern = imgs == 4 ? (a.out_signed[0] ? pool_fc_kernel<true, 4> : pool_fc_kernel<false, 4>)
                           : (a.out_signed[0] ? pool_fc_kernel<true, 2> : pool_fc_kernel<false, 2>);
     if (smem > 48 * 1024) F8_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TAIL_THREADS, smem, s>>>(static_cast<const int32_t *>(a.in), a.n, a.hin * a.win, a.cin_pad,
-                                         static_cast<const uint4 *>(a.wpack), pk.rows, a.bias, a.cout,
-                                         a.out_shift[0], a.out_f32, a.out_f32_ld);
+    F8_CUDA(launch_pdl(kern, grid, TAIL_THREADS, smem, s, static_cast<const int32_t *>(a.in), a.n, a.hin * a.win,
+                       a.cin_pad, static_cast<const uint4 *>(a.wpack), pk.rows, a.bias, a.cout, a.out_shift[0],
+                       a.out_f32, a.out_f32_ld));
     F8_CUDA(cudaGetLastError());
     return F8_OK;
 }
 
 int launch_convert_input(const int32_t *x, void *out, int n, int h, int w, int, cudaStream_t s) {
     const long long total = (long long)n * h * w;
-    convert_input_kernel<<<grid_for(total), THREADS, 0, s>>>(x, static_cast<uint32_t *>(out), n,
-                                                             h * w);
+    F8_CUDA(launch_pdl(convert_input_kernel, grid_for(total), THREADS, 0, s, x, static_cast<uint32_t *>(out), n, h * w));
     F8_CUDA(cudaGetLastError());
     return F8_OK;
 }
