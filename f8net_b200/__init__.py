@@ -16,3 +16,14 @@ def compile(*args, **kwargs):
 def build(force=False):
     from .build import build as _build
     return _build(force=force)
+
+
+def export_int_state_dict(*args, **kwargs):
+    """Float-simulation checkpoint -> IntModel state_dict (Model.int_model())."""
+    from .export import export_int_state_dict as _e
+    return _e(*args, **kwargs)
+
+
+def compile_float(*args, **kwargs):
+    from .export import compile_float as _c
+    return _c(*args, **kwargs)

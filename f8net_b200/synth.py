@@ -150,3 +150,38 @@ def to_torch_state_dict(sd):
     import torch
     return {k: torch.from_numpy(np.ascontiguousarray(v)).to(torch.int32).reshape(v.shape)
             for k, v in sd.items()}
+
+
+def make_float_state_dict(arch, seed=77, flags=None):
+    """A seeded synthetic FLOAT-simulation checkpoint (the ``best_model.pt`` layout of the
+    reference's ``Model.state_dict()``: ``<p>.conv.weight``, ``<p>.bn.*``, ``<p>.alpha``,
+    ``<p>.input_fraclen``; classifier ``weight`` / ``bias`` / ``alpha`` / ``input_fraclen``) for the
+    export tests (f8net_b200/export.py).  Per-layer gains spread the folded weights over
+    several weight fraclens; input fraclens carry fractional noise so the export's round()
+    and clamp() are exercised."""
+    import torch
+    from .export import ExportFlags, float_layers
+    flags = flags or ExportFlags()
+    net = graph_for(arch, bool(flags.normalize))
+    g = torch.Generator().manual_seed(seed)
+    by_int = {c.prefix: c for c in net.convs()}
+    sd = {}
+    for i, L in enumerate(float_layers(net, flags)):
+        c = by_int[L.iprefix]
+        p = L.fprefix
+        if L.kind == "fc":
+            sd[p + ".weight"] = torch.randn(c.weight_shape(), generator=g) * (0.01 * (1 + i % 3))
+            sd[p + ".bias"] = torch.randn(c.cout, generator=g) * 0.2
+        else:
+            shape = c.weight_shape()
+            K = shape[1] * shape[2] * shape[3]
+            gain = (0.3, 1.0, 3.0, 0.6, 8.0)[i % 5]
+            sd[p + ".conv.weight"] = torch.randn(shape, generator=g) * (gain * math.sqrt(2.0 / K))
+            sd[p + ".bn.weight"] = torch.rand(c.cout, generator=g) + 0.5
+            sd[p + ".bn.bias"] = torch.randn(c.cout, generator=g) * 0.3
+            sd[p + ".bn.running_mean"] = torch.randn(c.cout, generator=g) * 0.2
+            sd[p + ".bn.running_var"] = torch.rand(c.cout, generator=g) * 1.5 + 0.5
+        sd[p + ".alpha"] = torch.rand((), generator=g) * 8.0 + 2.0
+        fl = float(torch.randint(3, 10, (1,), generator=g)) + float(torch.rand((), generator=g)) * 0.8 - 0.4
+        sd[p + ".input_fraclen"] = torch.ones(1) * fl
+    return sd

@@ -39,8 +39,10 @@ def available():
     return os.path.isdir(os.path.join(REF_ROOT, "models"))
 
 
-def build_int_model(arch):
-    """Return (IntModel, FLAGS) built the way fix_train.py:258-296 + :930-934 does, on CPU."""
+def build_int_model(arch, float_state_dict=None, keep_grid_search=False):
+    """Return (IntModel, FLAGS) built the way fix_train.py:258-296 + :930-934 does, on CPU.
+    ``float_state_dict``: loaded into the float-sim Model before ``int_model()`` converts it (the
+    export golden vectors, tests/golden/make_export_golden.py)."""
     import torch
     import torch.nn as nn
 
@@ -73,7 +75,7 @@ def build_int_model(arch):
         finally:
             nn.Conv2d, nn.Linear = oc, ol
 
-    if getattr(FLAGS, "format_grid_search", False):
+    if getattr(FLAGS, "format_grid_search", False) and not keep_grid_search:
         # grid search only affects the *values* int_model() exports, which we overwrite
         # with the synthetic state dict; skip its cost (fix_quant_ops.py:17-27).
         FLAGS.format_grid_search = False
@@ -103,6 +105,9 @@ def build_int_model(arch):
         if isinstance(m, ReLUClipFXQLinear):
             m.rescale_forward = getattr(FLAGS, "rescale_forward", True)
     model.eval()
+    if float_state_dict is not None:       # a float-sim checkpoint (fix_train.py:877-891)
+        missing, unexpected = model.load_state_dict(float_state_dict, strict=False)
+        assert not unexpected and all(k.endswith("num_batches_tracked") for k in missing), (missing, unexpected)
     model.apply(lambda m: setattr(m, "int_op_only", True))       # fix_train.py:932
     with nograd_param_shim():
         im = model.int_model().cpu()                             # fix_train.py:933
