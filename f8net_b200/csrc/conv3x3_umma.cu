@@ -170,7 +170,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
             for (int s = 0; s < SA; ++s) { mbar_init(a_full(s), TMA ? 1 : LOADERS); mbar_init(a_empty(s), 1); }
             for (int p = 0; p < PLANES; ++p) tma_prefetch_desc(&tmaps.m[p]);
             for (int s = 0; s < SB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-            for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), EPI_THREADS); }
+            for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), EPI_WARPS); }   // one arrival per epilogue warp (not 512 serialised atomics)
             fence_barrier_init();
         }
         __syncwarp();
@@ -517,12 +517,14 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(acc_empty(buf));     // this thread's accumulator columns are drained
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty(buf));     // this warp's accumulator columns are drained
             }
             if (PLAIN_U8) {
-                // every accumulator column this thread owns is in registers (or consumed)
+                // every accumulator column this warp owns is in registers (or consumed)
                 tc_fence_before();
-                mbar_arrive(acc_empty(buf));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty(buf));
             }
             if (++buf == 2) { buf = 0; acc_phase ^= 1; }
         }

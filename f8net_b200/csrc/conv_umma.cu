@@ -28,6 +28,7 @@
 //              integer epilogue of f8_common.cuh (residual carries prefetched two steps ahead)
 //              and releases the accumulator ("acc_empty").
 // Integer accumulation is associative mod 2^32: tiling and MMA order cannot change results.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -106,7 +107,7 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
             }
             for (int b = 0; b < 2; ++b) {
                 mbar_init(acc_full_bar(b), 1);
-                mbar_init(acc_empty_bar(b), EPI_THREADS);
+                mbar_init(acc_empty_bar(b), EPI_WARPS);        // one arrival per epilogue warp
             }
             fence_barrier_init();
         }
@@ -360,7 +361,8 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
                 }
             }
             tc_fence_before();
-            mbar_arrive(acc_empty_bar(buf));       // this thread's columns are drained
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty_bar(buf));       // this warp's columns are drained
             if (++buf == 2) { buf = 0; acc_phase ^= 1; }
         }
     }
@@ -371,6 +373,347 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
         tc_fence_after();
         tmem_dealloc(tmem_base, 2 * BN);
     }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// conv1x1_res_kernel -- 1x1 stride-1 convolutions with FEW channels and MANY pixels (the early
+// MobileNet point-wise layers, the 56x56 bottleneck 1x1s of ResNet50): per 128-pixel tile the
+// generic kernel above spends more on pipeline hand-overs (a weight re-fetch of 4 bulk copies, two
+// mbarrier round trips, one accumulator hand-over) than on moving its ~6 KB.  Here
+//   * the layer's whole weight image (K_pad x BN bytes, one N tile) is RESIDENT in shared memory,
+//     fetched once per CTA -- before griddepcontrol.wait, i.e. under the previous layer's tail;
+//   * a tile is MSEG = 256 / BN segments of 128 pixels: one ring stage = MSEG TMA boxes of one
+//     64-channel K step, one accumulator set = MSEG x BN TMEM columns (two sets = 512 columns),
+//     so every mbarrier round trip is amortised over 512 (BN = 64) or 256 (BN = 128) pixels;
+//   * 16 epilogue warps: warp (lane group, unit) owns 32 pixels x 64 columns of one segment.
+// One CTA per SM, persistent.  Same operand layouts, descriptors and epilogue as the TMA_A path.
+#define R_TIMED(acc, stmt)                       \
+    do {                                         \
+        if (stats) {                             \
+            const long long _t0 = clock64();     \
+            stmt;                                \
+            acc += clock64() - _t0;              \
+        } else {                                 \
+            stmt;                                \
+        }                                        \
+    } while (0)
+constexpr int R_EPI_WARPS = 16;
+constexpr int R_THREADS = (R_EPI_WARPS + 2) * 32;
+constexpr int R_SMAX = 6;
+
+template <int BN, bool A_SIGNED, bool PLAIN>
+__global__ void __launch_bounds__(R_THREADS, 1)
+conv1x1_res_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const int S,
+                   const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap omap,
+                   long long *stats) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (f8::smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr int MSEG = 256 / BN;
+    constexpr int TM = MSEG * BM;
+    constexpr int EPI_THREADS = R_EPI_WARPS * 32;
+    constexpr int PRODUCER_WARP = R_EPI_WARPS;
+    constexpr int MMA_WARP = R_EPI_WARPS + 1;
+    constexpr int STAGE = MSEG * A_STAGE;
+    constexpr int B_CHUNK = BN * 16;
+    const int w_bytes = g.ktiles * 4 * B_CHUNK;
+    // 8-bit output staging: one 32-pixel x 64-byte box per epilogue warp (64-byte swizzle), written
+    // to global memory by TMA -- a warp's direct stores would be 32 16-byte pieces at a cout_pad
+    // pitch (one L1 wavefront each)
+    constexpr int OSTAGE = 32 * 64;
+    const uint32_t smem_base = f8::smem_u32(smem);
+    const uint32_t o_base = smem_base + S * STAGE;
+    const uint32_t w_base = o_base + R_EPI_WARPS * OSTAGE;
+    const uint32_t bar_base = w_base + w_bytes;
+    auto full_bar = [&](int s) { return bar_base + (uint32_t)s * 8; };
+    auto empty_bar = [&](int s) { return bar_base + (uint32_t)(R_SMAX + s) * 8; };
+    auto acc_full_bar = [&](int b) { return bar_base + (uint32_t)(2 * R_SMAX + b) * 8; };
+    auto acc_empty_bar = [&](int b) { return bar_base + (uint32_t)(2 * R_SMAX + 2 + b) * 8; };
+    const uint32_t w_full = bar_base + (uint32_t)(2 * R_SMAX + 4) * 8;
+    uint8_t *after = smem + S * STAGE + R_EPI_WARPS * OSTAGE + w_bytes + (2 * R_SMAX + 5) * 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(after);
+    int32_t *sbias = reinterpret_cast<int32_t *>(after + 8);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    if (warp == MMA_WARP) {
+        if (lane == 0) {
+            for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+            // acc_empty: one arrival per epilogue WARP (512 per-thread arrivals on one mbarrier are 512
+            // serialised shared-memory atomics per tile)
+            for (int b = 0; b < 2; ++b) { mbar_init(acc_full_bar(b), 1); mbar_init(acc_empty_bar(b), R_EPI_WARPS); }
+            mbar_init(w_full, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(f8::smem_u32(tmem_slot), 512);
+    }
+    constexpr bool plain = PLAIN;       // f8::epilogue_is_plain_u8(ep), decided by the launcher
+    if (tid < BN) {                     // one N tile: the bias copy is loaded once
+        int32_t b = tid < ep.cout_pad ? __ldg(ep.bias + tid) : 0;
+        if (plain) b = (int32_t)((uint32_t)b + (1u << (ep.shift0 - 1)));   // bias + half
+        sbias[tid] = b;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == PRODUCER_WARP) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap);
+            tma_prefetch_desc(&omap);
+            // resident weights: chunk-major image rows [0, BN) of every 16-byte K chunk
+            mbar_expect_tx(w_full, (uint32_t)w_bytes);
+            mbar_arrive(w_full);
+            for (int kc = 0; kc < g.ktiles * 4; ++kc)
+                bulk_g2s(w_base + kc * B_CHUNK, g.wpack + (size_t)kc * g.wrows * 16, B_CHUNK, w_full);
+            f8::pdl_wait();                     // the activation is the previous launch's output
+            int slot = 0, phase = 0;
+            long long st_a = 0;
+            const long long st_t0 = clock64();
+            for (int t = blockIdx.x; t < mtiles; t += gridDim.x) {
+                int nseg = (g.M - t * TM + BM - 1) / BM;       // segments with at least one real pixel
+                if (nseg > MSEG) nseg = MSEG;
+                for (int kt = 0; kt < g.ktiles; ++kt) {
+                    R_TIMED(st_a, mbar_wait(empty_bar(slot), phase ^ 1));
+                    const uint32_t sa = smem_base + slot * STAGE;
+                    mbar_expect_tx(full_bar(slot), (uint32_t)(nseg * A_STAGE));
+                    mbar_arrive(full_bar(slot));
+                    for (int sg = 0; sg < nseg; ++sg)
+                        tma_load_4d(sa + sg * A_STAGE, &tmap, kt * BK, (t * MSEG + sg) * BM, 0, 0, full_bar(slot));
+                    if (++slot == S) { slot = 0; phase ^= 1; }
+                }
+            }
+            if (stats) { stats[blockIdx.x * 8 + 0] = clock64() - st_t0; stats[blockIdx.x * 8 + 1] = st_a; }
+        }
+    } else if (warp == MMA_WARP) {
+        constexpr uint32_t idesc = instr_desc(A_SIGNED, BN);
+        constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);                         // B: SBO = 128 B
+        constexpr uint32_t desc_hi_a = (512u >> 4) | (1u << 14) | (4u << 29);          // A: SWIZZLE_64B
+        constexpr uint32_t a_lbo_field = 1u << 16;
+        constexpr uint32_t b_lbo_field = ((uint32_t)B_CHUNK >> 4) << 16;
+        int slot = 0, phase = 0, buf = 0, acc_phase = 0;
+        mbar_wait(w_full, 0);
+        long long st_acc = 0, st_full = 0;
+        const long long st_t0 = clock64();
+        for (int t = blockIdx.x; t < mtiles; t += gridDim.x) {
+            R_TIMED(st_acc, mbar_wait(acc_empty_bar(buf), acc_phase ^ 1));
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + (uint32_t)(buf * 256);
+            for (int kt = 0; kt < g.ktiles; ++kt) {
+                R_TIMED(st_full, mbar_wait(full_bar(slot), phase));
+                tc_fence_after();
+                const uint32_t sa = smem_base + slot * STAGE;
+                const uint32_t a_lo = ((sa & 0x3ffffu) >> 4) | a_lbo_field;
+                const uint32_t b_lo = (((w_base + kt * 4 * B_CHUNK) & 0x3ffffu) >> 4) | b_lbo_field;
+                if (elect_one()) {
+#pragma unroll
+                    for (int sg = 0; sg < MSEG; ++sg) {
+                        umma_i8_lohi(tacc + (uint32_t)(sg * BN), a_lo + (uint32_t)(sg * (A_STAGE >> 4)), desc_hi_a,
+                                     b_lo, desc_hi, idesc, (uint32_t)(kt != 0));
+                        umma_i8_lohi(tacc + (uint32_t)(sg * BN), a_lo + (uint32_t)(sg * (A_STAGE >> 4)) + 2u, desc_hi_a,
+                                     b_lo + ((2 * B_CHUNK) >> 4), desc_hi, idesc, 1u);
+                    }
+                    umma_commit(empty_bar(slot));
+                }
+                __syncwarp();
+                if (++slot == S) { slot = 0; phase ^= 1; }
+            }
+            if (elect_one()) umma_commit(acc_full_bar(buf));
+            __syncwarp();
+            if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+        }
+        if (stats && lane == 0) {
+            stats[blockIdx.x * 8 + 2] = clock64() - st_t0; stats[blockIdx.x * 8 + 3] = st_acc; stats[blockIdx.x * 8 + 4] = st_full;
+        }
+    } else {
+        // =========================== epilogue (16 warps) =========================
+        f8::pdl_wait();                                  // residual carry = an earlier launch's output
+        constexpr int UPS = BN / 64;                     // 64-column units per segment
+        const int lg = warp & 3;
+        const int u = warp >> 2;
+        const int seg = u / UPS;
+        const int cbase = (u - seg * UPS) * 64;
+        const int row = seg * BM + lg * 32 + lane;       // row inside the tile
+        const bool has_carry = !PLAIN && ep.carry_in != nullptr;
+        const f8::EpiConst kc = f8::epi_const(ep, has_carry);
+        int pf_t = blockIdx.x, pf_s = 0;                 // carry prefetch cursor: one step ahead
+        int4 cq[4] = {};
+        auto request = [&](int4 (&dst)[4]) {
+            if (PLAIN) return;
+            if (has_carry && pf_t < mtiles) {
+                const int col = cbase + 16 * pf_s;
+                const int m = pf_t * TM + row;
+                if (m < g.M && col < ep.cout_pad) {
+                    const int32_t *src = ep.carry_in + f8::carry_off((size_t)m, col, ep.cout_pad);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) dst[k] = __ldg(reinterpret_cast<const int4 *>(src + k * 512));
+                }
+            }
+            if (++pf_s == 4) { pf_s = 0; pf_t += gridDim.x; }
+        };
+        request(cq);
+        // this thread's row of the warp's staging box; 16-byte chunk j of row r sits at chunk
+        // j ^ ((r >> 1) & 3) (SWIZZLE_64B: conflict-free for the 16-byte row-per-lane writes)
+        uint8_t *ostage = smem + S * STAGE + warp * OSTAGE + lane * 64;
+        const int oswz = (lane >> 1) & 3;
+        const bool out_unit = ep.out0 != nullptr && cbase < ep.cout_pad;      // warp-uniform
+        int buf = 0, acc_phase = 0;
+        long long st_w = 0, st_st = 0;
+        const long long st_t0 = clock64();
+        for (int t = blockIdx.x; t < mtiles; t += gridDim.x) {
+            const int m = t * TM + row;
+            const bool valid = m < g.M;
+            R_TIMED(st_w, mbar_wait(acc_full_bar(buf), acc_phase));
+            tc_fence_after();
+            if (out_unit) {            // the previous tile's store has finished reading the staging box
+                if (lane == 0) R_TIMED(st_st, tma_store_wait_read());
+                __syncwarp();
+            }
+            const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * 256 + seg * BN);
+            // the TMEM load of step s + 1 is in flight while step s is computed
+            // (plain path only: the generic path has no registers to spare for a second buffer)
+            int32_t va[16], vb[16];
+            if (PLAIN && cbase < ep.cout_pad) tmem_ld16(trow + (uint32_t)cbase, va);
+#pragma unroll
+            for (int sidx = 0; sidx < 4; ++sidx) {
+                const int c0 = cbase + 16 * sidx;
+                int4 c[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) c[k] = cq[k];
+                request(cq);
+                if (c0 < ep.cout_pad) {                         // warp-uniform
+                    int32_t (&v)[16] = (PLAIN && (sidx & 1)) ? vb : va;
+                    if (!PLAIN) tmem_ld16(trow + (uint32_t)c0, va);
+                    tmem_ld_wait();
+                    if (PLAIN && sidx < 3 && c0 + 16 < ep.cout_pad)
+                        tmem_ld16(trow + (uint32_t)(c0 + 16), (sidx & 1) ? va : vb);
+                    {
+                        const size_t o = (size_t)m * ep.cout_pad + c0;
+                        uint8_t *so = ostage + ((sidx ^ oswz) << 4);
+                        if (plain) {
+                            f8::epilogue16_plain_u8(v, sbias + c0, so, ep.shift0);
+                        } else if (valid) {
+                            f8::epilogue16_math(v, sbias + c0, kc, c, has_carry);
+                            if (ep.carry_out) {
+                                int32_t *dst = ep.carry_out + f8::carry_off((size_t)m, c0, ep.cout_pad);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    *reinterpret_cast<int4 *>(dst + k * 512) =
+                                        make_int4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                            }
+                            if (ep.out0)
+                                *reinterpret_cast<uint4 *>(so) = f8::requant_pack16(v, ep.shift0, ep.signed0);
+                            if (ep.out1)
+                                *reinterpret_cast<uint4 *>(ep.out1 + o) = f8::requant_pack16(v, ep.shift1, ep.signed1);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty_bar(buf));
+            if (out_unit) {
+                // rows past M and columns past cout_pad of the box are clipped by the tensor map
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_4d(&omap, cbase, t * TM + seg * BM + lg * 32, 0, 0,
+                                 o_base + (uint32_t)(warp * OSTAGE));
+                    tma_store_commit();
+                }
+            }
+            if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+        }
+        if (out_unit && lane == 0) tma_store_wait_all();
+        if (stats && tid == 0) {
+            stats[blockIdx.x * 8 + 5] = clock64() - st_t0; stats[blockIdx.x * 8 + 6] = st_w; stats[blockIdx.x * 8 + 7] = st_st;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// Returns F8_ERR_UNSUPPORTED when the layer is not one this kernel is for (the caller then
+// takes the generic path).
+template <int BN, bool A_SIGNED, bool PLAIN>
+int launch_res_p(const UGeom &g, const f8::Epilogue &ep, cudaStream_t s);
+template <int BN, bool A_SIGNED>
+int launch_res_t(const UGeom &g, const f8::Epilogue &ep, cudaStream_t s) {
+    return f8::epilogue_is_plain_u8(ep) ? launch_res_p<BN, A_SIGNED, true>(g, ep, s)
+                                        : launch_res_p<BN, A_SIGNED, false>(g, ep, s);
+}
+template <int BN, bool A_SIGNED, bool PLAIN>
+int launch_res_p(const UGeom &g, const f8::Epilogue &ep, cudaStream_t s) {
+    constexpr int MSEG = 256 / BN;
+    constexpr int TM = MSEG * BM;
+    constexpr int STAGE = MSEG * A_STAGE;
+    const int w_bytes = g.ktiles * BK * BN;
+    static int num_sms = 0;
+    static bool attr_done = false;
+    auto kern = conv1x1_res_kernel<BN, A_SIGNED, PLAIN>;
+    if (!attr_done) {
+        F8_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        int dev = 0;
+        F8_CUDA(cudaGetDevice(&dev));
+        F8_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        attr_done = true;
+    }
+    const int mtiles = (g.M + TM - 1) / TM;
+    if (w_bytes > 64 * 1024 || mtiles < 2 * num_sms) return F8_ERR_UNSUPPORTED;
+    const size_t fixed = (size_t)w_bytes + R_EPI_WARPS * 32 * 64 + (2 * R_SMAX + 5) * 8 + 8 + BN * 4 + 1024;
+    int S = (int)((200 * 1024 - fixed) / STAGE);
+    if (S > R_SMAX) S = R_SMAX;
+    if (S < 2) return F8_ERR_UNSUPPORTED;
+    size_t smem_bytes = fixed + (size_t)S * STAGE;
+    if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;       // all 512 TMEM columns: one CTA per SM
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    const uint64_t dims[4] = {(uint64_t)g.cin_pad, (uint64_t)g.M, 1u, 1u};
+    const uint64_t row = (uint64_t)g.cin_pad, all = (uint64_t)g.cin_pad * (uint64_t)g.M;
+    const uint64_t strides[3] = {row, all, all};
+    const uint32_t box[4] = {(uint32_t)BK, (uint32_t)BM, 1u, 1u};
+    const int rc = f8host::encode_tmap_u8_4d(&tmap, g.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc != F8_OK) return rc;
+    CUtensorMap omap;
+    memset(&omap, 0, sizeof(omap));
+    if (ep.out0) {
+        const uint64_t odims[4] = {(uint64_t)ep.cout_pad, (uint64_t)g.M, 1u, 1u};
+        const uint64_t orow = (uint64_t)ep.cout_pad, oall = (uint64_t)ep.cout_pad * (uint64_t)g.M;
+        const uint64_t ostrides[3] = {orow, oall, oall};
+        const uint32_t obox[4] = {64u, 32u, 1u, 1u};
+        const int orc = f8host::encode_tmap_u8_4d(&omap, ep.out0, odims, ostrides, obox, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (orc != F8_OK) return orc;
+    }
+    const int grid = mtiles < num_sms ? mtiles : num_sms;
+    static const bool want_stats = getenv("F8_STATS") != nullptr;
+    static long long *stats_dev = nullptr;
+    if (want_stats) {
+        if (!stats_dev) F8_CUDA(cudaMalloc(&stats_dev, 8 * 1024 * sizeof(long long)));
+        F8_CUDA(cudaMemsetAsync(stats_dev, 0, 8 * 1024 * sizeof(long long), s));
+    }
+    F8_CUDA(f8host::launch_pdl(kern, (unsigned)grid, (unsigned)R_THREADS, smem_bytes, s, g, ep, mtiles, S, tmap, omap,
+                               want_stats ? stats_dev : (long long *)nullptr));
+    F8_CUDA(cudaGetLastError());
+    if (want_stats) {
+        static long long host[8 * 1024];
+        F8_CUDA(cudaStreamSynchronize(s));
+        F8_CUDA(cudaMemcpy(host, stats_dev, sizeof(host), cudaMemcpyDeviceToHost));
+        double acc[8] = {0};
+        for (int b = 0; b < grid; ++b)
+            for (int k = 0; k < 8; ++k) acc[k] += (double)host[b * 8 + k] / grid;
+        fprintf(stderr, "[f8 stats] conv1x1_res BN=%d cin=%d cout=%d M=%d tiles/cta=%.1f S=%d | producer total %.0f wait_empty %.0f | "
+                "mma total %.0f wait_acc %.0f wait_full %.0f | epi(warp 0) total %.0f wait_full %.0f wait_store %.0f (cycles, mean per CTA)\n",
+                BN, g.cin_pad, ep.cout_pad, g.M, (double)mtiles / grid, S, acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], acc[6], acc[7]);
+    }
+    return F8_OK;
 }
 
 template <int BN>
@@ -466,6 +809,15 @@ int launch_conv_umma(const f8_conv_args &a, cudaStream_t s) {
     static const bool no_tma = getenv("F8_GATHER_NO_TMA") != nullptr;
     const bool tma_a = !no_tma && !small_c && a.kh == 1 && a.kw == 1 && a.stride == 1 && a.pad == 0 &&
                        a.cin_pad % 16 == 0 && (g.M * (long long)a.cin_pad) < (1LL << 40);   // channels past cin_pad: zero fill
+    // few channels, many pixels: resident weights + multi-segment tiles (conv1x1_res_kernel)
+    static const bool no_res = getenv("F8_NO_CONV1X1_RES") != nullptr;
+    if (tma_a && !no_res && a.cout_pad <= 256 && !ep.out_f32) {
+        int rc;
+        if (a.cout_pad <= 64) rc = sgn ? launch_res_t<64, true>(g, ep, s) : launch_res_t<64, false>(g, ep, s);
+        else if (a.cout_pad <= 128) rc = sgn ? launch_res_t<128, true>(g, ep, s) : launch_res_t<128, false>(g, ep, s);
+        else rc = sgn ? launch_res_t<256, true>(g, ep, s) : launch_res_t<256, false>(g, ep, s);
+        if (rc != F8_ERR_UNSUPPORTED) return rc;
+    }
     if (a.cout_pad <= 64) return launch_bn<64>(g, ep, sgn, small_c, tma_a, s);
     if (a.cout_pad <= 128) return launch_bn<128>(g, ep, sgn, small_c, tma_a, s);
     return launch_bn<256>(g, ep, sgn, small_c, tma_a, s);

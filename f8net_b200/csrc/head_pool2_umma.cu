@@ -126,9 +126,9 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
     if (warp == MMA_WARP) {
         if (lane == 0) {
             for (int s = 0; s < NSTAGE; ++s) {
-                mbar_init(stage_full(s), 1); mbar_init(stage_empty(s), 1); mbar_init(stageb_full(s), SHIFT_WARPS * 32);
+                mbar_init(stage_full(s), 1); mbar_init(stage_empty(s), 1); mbar_init(stageb_full(s), SHIFT_WARPS);
             }
-            for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), EPI_THREADS); }
+            for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), EPI_WARPS); }   // one arrival per epilogue warp
             mbar_init(w_full, 1);
             fence_barrier_init();
             tma_prefetch_desc(&tmap);
@@ -216,7 +216,8 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
                 }
             }
             fence_proxy_async();
-            mbar_arrive(stageb_full(slot));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(stageb_full(slot));     // one arrival per shifter warp
             if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
         }
         if (g.stats && tid == SHIFT_WARP0 * 32) {
@@ -314,7 +315,8 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
                 tmem_ld16(trow + 2 * COUT, v2);
                 tmem_ld_wait();
                 tc_fence_before();
-                mbar_arrive(acc_empty(buf));     // this thread's columns are in registers
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty(buf));     // this warp's columns are in registers
                 // the pool's padding row / column: replace the excluded values by the identity of max
                 // (rare: only lanes of the first pooled row / column, so a branch, not 16 selects)
                 const int32_t ident = safe ? (int32_t)0x80000000 : 0;
