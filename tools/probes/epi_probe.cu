@@ -20,7 +20,12 @@ __device__ __forceinline__ uint4 step16(const int32_t (&v)[16], const int32_t *b
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint32_t t = (uint32_t)v[4 * q + j] + (uint32_t)bh[4 * q + j];
-            if (MODE == 3) {
+            if (MODE == 4) {
+                // tie with an odd quotient <=> the low n+1 bits of t are exactly 2^n: step t down by one
+                uint32_t tt = t;
+                if ((t & (2u * mask + 1u)) == mask + 1u) tt = t - 1u;
+                r[j] = (int32_t)tt >> n;
+            } else if (MODE == 3) {
                 const uint32_t b = (t >> n) & 1u;
                 r[j] = (int32_t)(t + (mask >> 1) + b) >> n;
             } else {
@@ -86,7 +91,7 @@ void run(int warps, long long *dev) {
 int main() {
     long long *dev;
     cudaMalloc(&dev, 148 * 16 * sizeof(long long));
-    for (int w : {4, 8, 16}) { run<0>(w, dev); run<1>(w, dev); run<2>(w, dev); run<3>(w, dev); }
+    for (int w : {4, 8, 16}) { run<0>(w, dev); run<1>(w, dev); run<2>(w, dev); run<3>(w, dev); run<4>(w, dev); }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
