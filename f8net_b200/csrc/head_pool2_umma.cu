@@ -347,11 +347,19 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
                 ++ph;
             }
             if (valid) {
+                // .float() max-pool .int() (fix_resnet.py:358-359): the round trip is the identity for
+                // 0 <= x < 2^24, which one OR over the 16 (non-negative) values proves; the conversions
+                // (quarter-rate pipe) run only for a thread that holds a larger value
                 int32_t r[16];
+                uint32_t any = 0;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const int32_t x = safe ? max((int32_t)((uint32_t)m[i] + (uint32_t)b16[i]), 0) : m[i];
-                    r[i] = f8::f2i_x86((float)x);          // .float() max-pool .int()
+                    r[i] = safe ? max((int32_t)((uint32_t)m[i] + (uint32_t)b16[i]), 0) : m[i];
+                    any |= (uint32_t)r[i];
+                }
+                if (any >= (1u << 24)) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r[i] = f8::f2i_x86((float)r[i]);
                 }
                 const size_t opix = ((size_t)img * POOLED + p) * POOLED + q;
                 const int ch0 = cgp * 16;
