@@ -769,6 +769,10 @@ namespace f8host {
 
 int launch_conv_umma(const f8_conv_args &a, cudaStream_t s) {
     if ((a.cin_pad != 4 && a.cin_pad % 16 != 0) || a.cout_pad % 16 != 0) return F8_ERR_UNSUPPORTED;
+    if (a.cin_pad == 4 && a.kh == 3) {          // the MobileNet head: space-to-depth kernel (head3x3_umma.cu)
+        const int rc = launch_head3x3s2(a, s);
+        if (rc != F8_ERR_UNSUPPORTED) return rc;
+    }
     const DensePack pk = dense_pack_geometry(a.cin_pad, a.cout_pad, a.kh, a.kw);
     if (pk.mode == 1 && ((a.stride & 1) || ((a.pad + pk.shift_px) & 1) || (a.win & 1) ||
                          (pk.row_bytes & 7)))

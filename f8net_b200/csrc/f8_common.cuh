@@ -351,6 +351,7 @@ int launch_conv_mma(const f8_conv_args &a, cudaStream_t s);
 int launch_conv_umma(const f8_conv_args &a, cudaStream_t s);
 int launch_conv3x3_umma(const f8_conv_args &a, cudaStream_t s);
 int launch_head_pool(const f8_conv_args &a, cudaStream_t s);
+int launch_head3x3s2(const f8_conv_args &a, cudaStream_t s);
 int launch_dw3x3(const f8_conv_args &a, cudaStream_t s);
 int launch_conv3x3_dw(const f8_conv_args &a, cudaStream_t s);
 // depthwise weight pack = [12][cpad/4] dp4a words, then (256-byte aligned) one block-diagonal

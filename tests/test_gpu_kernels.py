@@ -91,6 +91,32 @@ def test_conv_dense_plain(G, f8lib, shape, signed, backend):
     assert np.array_equal(q[0], eq[0]) and np.array_equal(q[1], eq[1])
 
 
+@pytest.mark.parametrize("signed", [False, True])
+@pytest.mark.parametrize("geom", [(1, 8, 8), (3, 32, 32), (2, 30, 44), (5, 224, 224)],
+                         ids=lambda g: "x".join(map(str, g)))
+def test_mobilenet_head_space_to_depth(G, f8lib, geom, signed):
+    """head[0] of the MobileNets (3 -> 32, k3 s2 p1) + ReLU + one unsigned requant in the
+    space-to-depth kernel (head3x3_umma.cu): ragged batches, non-square even images, every tile
+    boundary of the padded linear space, exact ties; against the generic gather path as well."""
+    if not f8lib.f8_has_umma(0):
+        pytest.skip("tcgen05 backend not available")
+    n, h, wd = geom
+    rng = np.random.default_rng(n * 1000 + h + signed)
+    lo, hi, w, b = _rand_layer(rng, 3, 32, 3, signed)
+    w[:, :, 1, 1] = (w[:, :, 1, 1] // 2) * 2
+    b[:8] = (b[:8] // 16) * 16 + 8                      # ties of the 4-bit shift below
+    x = rng.integers(lo, hi, (n, 3, h, wd)).astype(np.int32)
+    x[0, :, 0, :] = hi - 1                              # first / last rows and columns saturated:
+    x[-1, :, -1, :] = lo                                # the zero halo must not leak in
+    x[:, :, :, 0] = hi - 1
+    for shift in (4, 9):
+        outs = ((shift, False),)
+        _, q, _ = G.run_conv(f8lib, x, w, b, 2, 1, in_signed=signed, relu=True, outs=outs, want_carry=False,
+                             backend=1)
+        _, eq = G.expect_conv(x, w, b, 2, 1, relu=True, outs=outs)
+        assert np.array_equal(q[0], eq[0]), (geom, signed, shift)
+
+
 @pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("carry_shift", [-3, 0, 2, 29])
 def test_conv_dense_residual_epilogue(G, f8lib, carry_shift, backend):
