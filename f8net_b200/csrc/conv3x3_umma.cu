@@ -70,6 +70,7 @@ struct PGeom {
     const uint8_t *wpack;   // [K_pad/16][wrows][16], k = (r*3+s)*C + c
     int wrows;
     int N, H, W, C;         // H x W = OUTPUT size per image, C = cin_pad (multiple of 64)
+    int Nh;                 // pair mode: images of the first batch half (CTA rank 0); else N
     int Hin, Win;           // input size per image (= H, W for stride 1; 2H, 2W for stride 2)
     int plane_slots;        // slots of one parity plane (stride 1: the only plane)
     int PW;                 // W + 1
@@ -102,7 +103,14 @@ struct PGeom {
         }                                        \
     } while (0)
 
-template <int BN, bool A_SIGNED, bool PLAIN_U8, int STRIDE, bool DW>
+// PAIR (dense stride 1, BN = 128): the kernel runs as clusters of two CTAs issuing cta_group::2 MMAs
+// (M = 256).  CTA r of a pair works on batch half r (same tile index, hence identical patch
+// geometry and identical shared-memory offsets in both CTAs), holds its own patch and only rows
+// [64 r, 64 r + 64) of every weight tile: per MMA each SM fetches 4 KB of A + 2 KB of B instead of
+// 4 + 4 (the shared-memory port is the bound of the single-CTA form) and the weight stream from
+// L2 is halved.  The leader (rank 0) issues; the peer's MMA warp forwards its "patch / weights
+// landed" barriers to the leader; tcgen05.commit multicasts every release to both CTAs.
+template <int BN, bool A_SIGNED, bool PLAIN_U8, int STRIDE, bool DW, bool PAIR>
 __global__ void __launch_bounds__((epi_warps_for(PLAIN_U8) + 3) * 32, 1)
 conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant__ TMaps tmaps) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -118,12 +126,12 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     constexpr int WLOAD_WARP = EPI_WARPS + 2;     // 19 warps leave the epilogue a 96-register cap
     constexpr int MB = mb_for(BN);
     constexpr int TM = 128 * MB;
-    constexpr int SB_MAX = sb_for(BN, PLAIN_U8);
+    constexpr int SB_MAX = PAIR ? 6 : sb_for(BN, PLAIN_U8);     // pair: half-size stages, a longer round trip
     const int SB = g.sb;
     constexpr int SA_MAX = sa_for(STRIDE);
     const int SA = g.sa;
     constexpr int A_LAG = a_lag_for(STRIDE);
-    constexpr int BROWS = DW ? 64 : BN;                   // weight rows of a tile (depthwise: one 64-channel group)
+    constexpr int BROWS = DW ? 64 : (PAIR ? BN / 2 : BN); // weight rows of a tile held by this CTA (depthwise: one 64-channel group)
     constexpr int B_TILE = BROWS * 64;                    // one tap
     constexpr int B_STAGE = 3 * B_TILE;                   // one filter row
     constexpr int CW = BN / (EPI_WARPS / 4);               // columns per epilogue warp slice (plain path)
@@ -139,7 +147,10 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     auto b_empty = [&](int s) { return bar_base + (uint32_t)(2 * SA_MAX + SB_MAX + s) * 8; };
     auto acc_full = [&](int b) { return bar_base + (uint32_t)(2 * SA_MAX + 2 * SB_MAX + b) * 8; };
     auto acc_empty = [&](int b) { return bar_base + (uint32_t)(2 * SA_MAX + 2 * SB_MAX + 2 + b) * 8; };
-    constexpr int NBARS = 2 * SA_MAX + 2 * SB_MAX + 4;
+    // pair mode, leader side: "the peer's patch / weight stage has landed"
+    auto a_peer = [&](int s) { return bar_base + (uint32_t)(2 * SA_MAX + 2 * SB_MAX + 4 + s) * 8; };
+    auto b_peer = [&](int s) { return bar_base + (uint32_t)(3 * SA_MAX + 2 * SB_MAX + 4 + s) * 8; };
+    constexpr int NBARS = 2 * SA_MAX + 2 * SB_MAX + 4 + (PAIR ? SA_MAX + SB_MAX : 0);
     uint8_t *after = smem + SA * a_stage + SB * B_STAGE + NBARS * 8;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(after);
     int32_t *sbias = reinterpret_cast<int32_t *>(after + 16);
@@ -153,6 +164,11 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int total_items = g.n_super * g.ntiles_n;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;           // pair mode: batch half of this CTA
+    const int bid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int nb = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_loc = PAIR ? (rank ? g.N - g.Nh : g.Nh) : g.N;     // images of this CTA's half
+    const int pix_off = PAIR ? (int)rank * g.Nh * g.H * g.W : 0;   // first output pixel of the half
     // K loop: dense = every 64-channel group of the input; depthwise = the BN / 64 channel groups
     // of the output tile itself (each through its own diagonal weight block, on its own columns)
     constexpr int GPT = BN / 64;
@@ -170,14 +186,21 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
             for (int s = 0; s < SA; ++s) { mbar_init(a_full(s), TMA ? 1 : LOADERS); mbar_init(a_empty(s), 1); }
             for (int p = 0; p < PLANES; ++p) tma_prefetch_desc(&tmaps.m[p]);
             for (int s = 0; s < SB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-            for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), EPI_WARPS); }   // one arrival per epilogue warp (not 512 serialised atomics)
+            // one arrival per epilogue warp (not 512 serialised atomics); pair mode: both CTAs' warps
+            for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
+            if (PAIR) {
+                for (int s = 0; s < SA; ++s) mbar_init(a_peer(s), 1);
+                for (int s = 0; s < SB; ++s) mbar_init(b_peer(s), 1);
+            }
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc(f8::smem_u32(tmem_slot), 512);
+        if (PAIR) tmem_alloc2(f8::smem_u32(tmem_slot), 512);
+        else tmem_alloc(f8::smem_u32(tmem_slot), 512);
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();       // the peer's barriers exist before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // The next layer's launch may begin its own prologue as this grid's CTAs retire; everything
@@ -198,7 +221,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
             long long w_empty = 0;
             const long long t_begin = clock64();
             const int PW = g.PW, BY = g.BY, BS = g.box_slots;
-            for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+            for (int it = bid; it < total_items; it += nb) {
                 const int st = it / g.ntiles_n;
                 const int cg0 = tile_group0(it), ncg = tile_ncg(it);
                 const int pi0 = st * TM;
@@ -218,7 +241,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                     __syncwarp();
                     if (PLANES == 1) {
                         if (lane < nbox)
-                            tma_load_4d(smem_base + slot * a_stage + lane * BS * 64, &tmaps.m[0], (cg0 + cg) * 64, -1,
+                            tma_load_4d(smem_base + slot * a_stage + lane * BS * 64, &tmaps.m[PAIR ? rank : 0u], (cg0 + cg) * 64, -1,
                                         yy - 1, img, a_full(slot));
                     } else {
                         // box b of plane p: the same padded rows of every parity plane
@@ -246,13 +269,13 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
             int slot = 0, phase = 0;
             long long w_bempty = 0;
             const long long t_begin = clock64();
-            for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+            for (int it = bid; it < total_items; it += nb) {
                 const int st = it / g.ntiles_n;
-                const int n0 = DW ? 0 : (it - st * g.ntiles_n) * BN;
+                const int n0 = DW ? 0 : (it - st * g.ntiles_n) * BN + (PAIR ? (int)rank * (BN / 2) : 0);
                 const int Ck = DW ? 64 : g.C;
                 const int ncg = tile_ncg(it);
-                // depthwise: 64 weight rows per group image, dense: BN rows of the shared image
-                constexpr uint32_t ROWS_B = DW ? 64u : (uint32_t)BN;
+                // depthwise: 64 weight rows per group image, dense: BN rows of the shared image (pair: this CTA's half)
+                constexpr uint32_t ROWS_B = (uint32_t)BROWS;
                 for (int cg = 0; cg < ncg; ++cg) {
                     const uint8_t *wsrc = g.wpack + (DW ? (size_t)(tile_group0(it) + cg) * (36 * 64 * 16) : 0);
                     const int kcg = DW ? 0 : cg;
@@ -304,8 +327,25 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
         long long w_acc = 0, w_a = 0, w_b = 0;
         const long long t_begin = clock64();
         long long t_first_a = 0;
-        for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
-            F8_TIMED_WAIT(w_acc, mbar_wait(acc_empty(buf), acc_phase ^ 1));
+        if (PAIR && rank != 0) {
+            // peer of a pair: no MMAs to issue; tell the leader when this CTA's patch / weight stages land
+            for (int it = bid; it < total_items; it += nb) {
+                const int ncg = tile_ncg(it);
+                for (int cg = 0; cg < ncg; ++cg) {
+                    mbar_wait(a_full(aslot), aphase);
+                    if (lane == 0) mbar_arrive_cluster(mapa_rank(a_peer(aslot), 0u));
+                    for (int fr = 0; fr < 3; ++fr) {
+                        mbar_wait(b_full(bslot), bphase);
+                        if (lane == 0) mbar_arrive_cluster(mapa_rank(b_peer(bslot), 0u));
+                        if (++bslot == SB) { bslot = 0; bphase ^= 1; }
+                    }
+                    if (++aslot == SA) { aslot = 0; aphase ^= 1; }
+                }
+            }
+        } else
+        for (int it = bid; it < total_items; it += nb) {
+            if (PAIR) F8_TIMED_WAIT(w_acc, mbar_wait_cluster(acc_empty(buf), acc_phase ^ 1));
+            else F8_TIMED_WAIT(w_acc, mbar_wait(acc_empty(buf), acc_phase ^ 1));
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(buf * MB * BN);
             int tile_soff = 0;                           // TMA: first slot of the tile inside its box-aligned patch
@@ -318,6 +358,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
             }
             for (int cg = 0; cg < ncg; ++cg) {
                 F8_TIMED_WAIT(w_a, mbar_wait(a_full(aslot), aphase));
+                if (PAIR) F8_TIMED_WAIT(w_a, mbar_wait_cluster(a_peer(aslot), aphase));
                 if (g.stats && t_first_a == 0) t_first_a = clock64();
                 const uint32_t sa = smem_base + aslot * a_stage + (TMA ? (uint32_t)tile_soff * 64u : 0u);
                 const uint32_t first = (uint32_t)(cg != 0);
@@ -326,6 +367,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
 #pragma unroll
                 for (int fr = 0; fr < 3; ++fr) {
                     F8_TIMED_WAIT(w_b, mbar_wait(b_full(bslot), bphase));
+                    if (PAIR) F8_TIMED_WAIT(w_b, mbar_wait_cluster(b_peer(bslot), bphase));
                     tc_fence_after();
                     const uint32_t sb = sb_base + bslot * B_STAGE;
                     const uint32_t a_row = (((sa & 0x3ffffu) >> 4) | a_lbo_field) + tap_row[fr];
@@ -358,26 +400,29 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
 #pragma unroll
                             for (int i = 0; i < MB; ++i) {
 #pragma unroll
-                                for (int h = 0; h < 2; ++h)
-                                    umma_i8_lohi(tacc + (uint32_t)(i * BN),
-                                                 a_lo0 + (TMA ? (uint32_t)(i * 512 + h * 2)
-                                                              : (uint32_t)((i * 2048) >> 4) + (uint32_t)h * ((2 * lbo_a) >> 4)),
-                                                 desc_hi_a,
-                                                 b_lo0 + (uint32_t)h * ((2 * BN * 16) >> 4), desc_hi, idesc,
-                                                 (h | fs | fr) ? 1u : first);
+                                for (int h = 0; h < 2; ++h) {
+                                    const uint32_t a_lo1 = a_lo0 + (TMA ? (uint32_t)(i * 512 + h * 2)
+                                                                        : (uint32_t)((i * 2048) >> 4) + (uint32_t)h * ((2 * lbo_a) >> 4));
+                                    const uint32_t b_lo1 = b_lo0 + (uint32_t)h * ((2 * BROWS * 16) >> 4);
+                                    if (PAIR) umma_i8_lohi2(tacc + (uint32_t)(i * BN), a_lo1, desc_hi_a, b_lo1, desc_hi,
+                                                            instr_desc_m(A_SIGNED, BN, 256), (h | fs | fr) ? 1u : first);
+                                    else umma_i8_lohi(tacc + (uint32_t)(i * BN), a_lo1, desc_hi_a, b_lo1, desc_hi, idesc,
+                                                      (h | fs | fr) ? 1u : first);
+                                }
                             }
                             }
                         }
-                        umma_commit(b_empty(bslot));
+                        if (PAIR) umma_commit2(b_empty(bslot));
+                        else umma_commit(b_empty(bslot));
                     }
                     __syncwarp();
                     if (++bslot == SB) { bslot = 0; bphase ^= 1; }
                 }
-                if (elect_one()) umma_commit(a_empty(aslot));
+                if (elect_one()) { if (PAIR) umma_commit2(a_empty(aslot)); else umma_commit(a_empty(aslot)); }
                 __syncwarp();
                 if (++aslot == SA) { aslot = 0; aphase ^= 1; }
             }
-            if (elect_one()) umma_commit(acc_full(buf));
+            if (elect_one()) { if (PAIR) umma_commit2(acc_full(buf)); else umma_commit(acc_full(buf)); }
             __syncwarp();
             if (++buf == 2) { buf = 0; acc_phase ^= 1; }
         }
@@ -399,7 +444,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
         int4 cnext[4] = {};            // prefetched residual carry of the next 16-column step
         long long w_full = 0, t_issue = 0, t_wait = 0, t_math = 0, t_store = 0;
         const long long t_begin = clock64();
-        for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+        for (int it = bid; it < total_items; it += nb) {
             const int st = it / g.ntiles_n;
             const int n0 = (it - st * g.ntiles_n) * BN;
             int ncols = ep.cout_pad - n0;
@@ -427,8 +472,8 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                         const int xo = m - Yo * g.PW;
                         const int img = (int)__umulhi((uint32_t)Yo, g.mHP);
                         const int y = Yo - img * HP;
-                        const bool valid = xo < g.W && y < g.H && img < g.N;
-                        const size_t opix = ((size_t)(img * g.H + y) * g.W + xo);
+                        const bool valid = xo < g.W && y < g.H && img < n_loc;
+                        const size_t opix = ((size_t)(img * g.H + y) * g.W + xo) + (size_t)pix_off;
                         const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) +
                                               (uint32_t)((buf * MB + i) * BN);
 #pragma unroll
@@ -463,7 +508,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                     const int xo = m - Yo * g.PW;
                     const int img = (int)__umulhi((uint32_t)Yo, g.mHP);
                     const int y = Yo - img * HP;
-                    return (xo < g.W && y < g.H && img < g.N) ? (img * g.H + y) * g.W + xo : -1;
+                    return (xo < g.W && y < g.H && img < n_loc) ? (img * g.H + y) * g.W + xo + pix_off : -1;
                 };
                 auto load_carry = [&](int pix_, int col, int4 (&c)[4]) {
                     if (has_carry && pix_ >= 0 && col < ep.cout_pad) {
@@ -487,7 +532,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                     if (q < 3) {
                         load_carry(pix, n0 + cbase + 16 * (q + 1), cnext);
                     } else {
-                        const int it2 = it + gridDim.x;
+                        const int it2 = it + nb;
                         if (it2 < total_items) {
                             const int st2 = it2 / g.ntiles_n;
                             load_carry(unit_pixel(st2), (it2 - st2 * g.ntiles_n) * BN + cbase, cnext);
@@ -518,13 +563,19 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty(buf));     // this warp's accumulator columns are drained
+                if (lane == 0) {            // this warp's accumulator columns are drained (pair: tell the leader)
+                    if (PAIR && rank != 0) mbar_arrive_cluster(mapa_rank(acc_empty(buf), 0u));
+                    else mbar_arrive(acc_empty(buf));
+                }
             }
             if (PLAIN_U8) {
                 // every accumulator column this warp owns is in registers (or consumed)
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty(buf));
+                if (lane == 0) {
+                    if (PAIR && rank != 0) mbar_arrive_cluster(mapa_rank(acc_empty(buf), 0u));
+                    else mbar_arrive(acc_empty(buf));
+                }
             }
             if (++buf == 2) { buf = 0; acc_phase ^= 1; }
         }
@@ -540,9 +591,11 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
 
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();       // neither CTA leaves while the pair's MMAs may still read its memory
     if (warp == MMA_WARP) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (PAIR) tmem_dealloc2(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
     if (g.stats && tid == 0) {
         g.stats[blockIdx.x * 16 + 11] = clock64() - t_entry;
@@ -556,12 +609,14 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
 
 namespace {
 
-template <int BN, int STRIDE, bool DW = false>
+template <int BN, int STRIDE, bool DW = false, bool PAIR = false>
 int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     constexpr bool dw = DW;
     constexpr int MB = mb_for(BN);
     constexpr int TM = 128 * MB;
-    constexpr int B_TILE = (DW ? 64 : BN) * 64;
+    constexpr int B_TILE = (DW ? 64 : (PAIR ? BN / 2 : BN)) * 64;
+    const int Nh = PAIR ? (a.n + 1) / 2 : a.n;          // pair mode: each CTA of a pair takes one batch half
+    if (PAIR && a.n < 2) return F8_ERR_UNSUPPORTED;
     constexpr bool TMA = true;
     constexpr int PLANES = STRIDE == 2 ? 4 : 1;
     // an even pitch keeps every box (one padded row of PW slots x 64 B) 128-byte aligned
@@ -610,10 +665,10 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     }
     const bool plain = f8::epilogue_is_plain_u8(ep);
     constexpr int SA_MAX = sa_for(STRIDE);
-    const int SB_MAX = sb_for(BN, plain);
+    const int SB_MAX = PAIR ? 6 : sb_for(BN, plain);
     int SA = SA_MAX, SB = SB_MAX;
     auto smem_for = [&](int sa, int sb) {
-        return (size_t)sa * slots_pad * 64 + (size_t)sb * 3 * B_TILE + (2 * SA_MAX + 2 * SB_MAX + 4) * 8 + 16 +
+        return (size_t)sa * slots_pad * 64 + (size_t)sb * 3 * B_TILE + (3 * SA_MAX + 3 * SB_MAX + 4) * 8 + 16 +
                2 * BN * 4 + 1024;                                                      // + base alignment slack
     };
     // wide images / four parity planes: shallower rings
@@ -623,7 +678,7 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     if (smem_bytes > 227 * 1024) return F8_ERR_UNSUPPORTED;
     // the kernel owns all 512 TMEM columns: keep a second CTA off the SM
     const size_t smem_launch = smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes;
-    const long long lin = (long long)a.n * (a.hout + 1) * PW;     // padded linear output space
+    const long long lin = (long long)Nh * (a.hout + 1) * PW;      // padded linear output space (of one batch half)
     // (the magic-number divisions need (lin + TM) * PW < 2^32)
     if ((lin + TM) * (long long)(PW > a.hout + 1 ? PW : a.hout + 1) >= 0xffffffffLL) return F8_ERR_UNSUPPORTED;
     const f8host::DensePack pk = f8host::dense_pack_geometry(a.cin_pad, a.cout_pad, 3, 3);
@@ -636,6 +691,7 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
         g.wrows = 64;
     }
     g.N = a.n; g.H = a.hout; g.W = a.wout; g.C = a.cin_pad;
+    g.Nh = Nh;
     g.Hin = a.hin; g.Win = a.win;
     g.plane_slots = plane_slots;
     g.PW = PW;
@@ -658,17 +714,19 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     static bool attr_done = false;
     static int num_sms = 0;
     if (!attr_done) {
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, false, STRIDE, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, false, STRIDE, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, true, STRIDE, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, true, STRIDE, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, false, STRIDE, DW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, false, STRIDE, DW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, true, STRIDE, DW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, true, STRIDE, DW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         int dev = 0;
         F8_CUDA(cudaGetDevice(&dev));
         F8_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         attr_done = true;
     }
     long long grid = (long long)g.n_super * g.ntiles_n;
+    if (PAIR) grid *= 2;                                  // two CTAs per item
     if (grid > num_sms) grid = num_sms;
+    if (PAIR) grid &= ~1LL;
     static const bool want_stats = getenv("F8_STATS") != nullptr;
     static long long *stats_dev = nullptr;
     if (want_stats) {
@@ -692,13 +750,22 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
         const int rc = f8host::encode_tmap_u8_4d(&tmaps.m[p], base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc != F8_OK) return rc;
     }
+    if (PAIR) {     // the second batch half: the same view starting at image Nh
+        const uint8_t *base = static_cast<const uint8_t *>(a.in) + (size_t)Nh * a.hin * a.win * a.cin_pad;
+        const uint64_t dims[4] = {(uint64_t)a.cin_pad, (uint64_t)a.wout, (uint64_t)a.hout, (uint64_t)(a.n - Nh)};
+        const uint64_t strides[3] = {(uint64_t)a.cin_pad, (uint64_t)a.win * a.cin_pad, (uint64_t)a.hin * a.win * a.cin_pad};
+        const uint32_t box[4] = {64u, (uint32_t)PW, (uint32_t)BY, 1u};
+        const int rc = f8host::encode_tmap_u8_4d(&tmaps.m[1], base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc != F8_OK) return rc;
+    }
     const unsigned th = (epi_warps_for(plain) + 3) * 32;
+    constexpr int CL = PAIR ? 2 : 1;
     if (a.in_signed) {
-        if (plain) F8_CUDA(f8host::launch_pdl(conv3x3_umma_kernel<BN, true, true, STRIDE, DW>, gr, th, smem_launch, s, g, ep, tmaps));
-        else F8_CUDA(f8host::launch_pdl(conv3x3_umma_kernel<BN, true, false, STRIDE, DW>, gr, th, smem_launch, s, g, ep, tmaps));
+        if (plain) F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, true, true, STRIDE, DW, PAIR>, gr, th, smem_launch, s, CL, g, ep, tmaps));
+        else F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, true, false, STRIDE, DW, PAIR>, gr, th, smem_launch, s, CL, g, ep, tmaps));
     } else {
-        if (plain) F8_CUDA(f8host::launch_pdl(conv3x3_umma_kernel<BN, false, true, STRIDE, DW>, gr, th, smem_launch, s, g, ep, tmaps));
-        else F8_CUDA(f8host::launch_pdl(conv3x3_umma_kernel<BN, false, false, STRIDE, DW>, gr, th, smem_launch, s, g, ep, tmaps));
+        if (plain) F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, false, true, STRIDE, DW, PAIR>, gr, th, smem_launch, s, CL, g, ep, tmaps));
+        else F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, false, false, STRIDE, DW, PAIR>, gr, th, smem_launch, s, CL, g, ep, tmaps));
     }
     F8_CUDA(cudaGetLastError());
     if (want_stats) {
@@ -761,7 +828,15 @@ int launch_conv3x3_umma(const f8_conv_args &a, cudaStream_t s) {
         a.out_f32 != nullptr)
         return F8_ERR_UNSUPPORTED;
     if (a.stride == 1 && a.hin == a.hout && a.win == a.wout) {
-        if (a.cout_pad > 64) return launch_bn<128, 1>(a, s);
+        if (a.cout_pad > 64) {
+            // CTA pairs (cta_group::2, M = 256): half the weight stream and 3/4 of the operand fetch per SM
+            static const bool pair = getenv("F8_PAIR") != nullptr && atoi(getenv("F8_PAIR")) != 0;
+            if (pair) {
+                const int rc = launch_bn<128, 1, false, true>(a, s);
+                if (rc != F8_ERR_UNSUPPORTED) return rc;
+            }
+            return launch_bn<128, 1>(a, s);
+        }
         return launch_bn<64, 1>(a, s);
     }
     // stride 2: four parity planes of the input; even input sizes only (every F8Net stage)
