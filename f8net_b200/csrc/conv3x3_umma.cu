@@ -151,7 +151,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     auto a_peer = [&](int s) { return bar_base + (uint32_t)(2 * SA_MAX + 2 * SB_MAX + 4 + s) * 8; };
     auto b_peer = [&](int s) { return bar_base + (uint32_t)(3 * SA_MAX + 2 * SB_MAX + 4 + s) * 8; };
     constexpr int NBARS = 2 * SA_MAX + 2 * SB_MAX + 4 + (PAIR ? SA_MAX + SB_MAX : 0);
-    uint8_t *after = smem + SA * a_stage + SB * B_STAGE + NBARS * 8;
+    uint8_t *after = smem + SA * a_stage + SB * B_STAGE + ((NBARS * 8 + 15) & ~15);   // bias copy: 16-byte aligned
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(after);
     int32_t *sbias = reinterpret_cast<int32_t *>(after + 16);
 
