@@ -406,7 +406,7 @@ template <int BN, bool A_SIGNED, bool PLAIN>
 __global__ void __launch_bounds__(R_THREADS, 1)
 conv1x1_res_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const int S,
                    const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap omap,
-                   long long *stats) {
+                   long long *stats, const int probe) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (f8::smem_u32(smem_raw) & 1023u)) & 1023u);
     constexpr int MSEG = 256 / BN;
@@ -594,7 +594,8 @@ conv1x1_res_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const
                         const size_t o = (size_t)m * ep.cout_pad + c0;
                         uint8_t *so = ostage + ((sidx ^ oswz) << 4);
                         if (plain) {
-                            f8::epilogue16_plain_u8(v, sbias + c0, so, ep.shift0);
+                            if (probe & 1) *reinterpret_cast<uint4 *>(so) = make_uint4(v[0], v[5], v[10], v[15]);   // timing probe: WRONG results
+                            else f8::epilogue16_plain_u8(v, sbias + c0, so, ep.shift0);
                         } else if (valid) {
                             f8::epilogue16_math(v, sbias + c0, kc, c, has_carry);
                             if (ep.carry_out) {
@@ -619,7 +620,7 @@ conv1x1_res_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const
                 // rows past M and columns past cout_pad of the box are clipped by the tensor map
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) {
+                if (lane == 0 && !(probe & 2)) {
                     tma_store_4d(&omap, cbase, t * TM + seg * BM + lg * 32, 0, 0,
                                  o_base + (uint32_t)(warp * OSTAGE));
                     tma_store_commit();
@@ -694,13 +695,14 @@ int launch_res_p(const UGeom &g, const f8::Epilogue &ep, cudaStream_t s) {
     }
     const int grid = mtiles < num_sms ? mtiles : num_sms;
     static const bool want_stats = getenv("F8_STATS") != nullptr;
+    static const int rprobe = getenv("F8_RPROBE") ? atoi(getenv("F8_RPROBE")) : 0;   // timing probes: WRONG results
     static long long *stats_dev = nullptr;
     if (want_stats) {
         if (!stats_dev) F8_CUDA(cudaMalloc(&stats_dev, 8 * 1024 * sizeof(long long)));
         F8_CUDA(cudaMemsetAsync(stats_dev, 0, 8 * 1024 * sizeof(long long), s));
     }
     F8_CUDA(f8host::launch_pdl(kern, (unsigned)grid, (unsigned)R_THREADS, smem_bytes, s, g, ep, mtiles, S, tmap, omap,
-                               want_stats ? stats_dev : (long long *)nullptr));
+                               want_stats ? stats_dev : (long long *)nullptr, rprobe));
     F8_CUDA(cudaGetLastError());
     if (want_stats) {
         static long long host[8 * 1024];
