@@ -406,7 +406,7 @@ template <int BN, bool A_SIGNED, bool PLAIN>
 __global__ void __launch_bounds__(R_THREADS, 1)
 conv1x1_res_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const int S,
                    const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap omap,
-                   long long *stats, const int probe) {
+                   long long *stats, const int probe, const int cpa) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (f8::smem_u32(smem_raw) & 1023u)) & 1023u);
     constexpr int MSEG = 256 / BN;
@@ -460,7 +460,48 @@ conv1x1_res_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == PRODUCER_WARP) {
+    if (warp == PRODUCER_WARP && cpa) {
+        // ---- inputs of 16 / 32 channels: a TMA box over such narrow rows costs ~5 cycles per row, so the
+        // warp copies the pixels with 16-byte cp.async straight into the canonical no-swizzle K-major
+        // layout [chunk][TM rows][16 B] (cpa = chunks per pixel); the K = 64 stage becomes ONE K = 32 MMA
+        if (lane == 0) {
+            tma_prefetch_desc(&omap);
+            mbar_expect_tx(w_full, (uint32_t)w_bytes);
+            mbar_arrive(w_full);
+            for (int kc = 0; kc < g.ktiles * 4; ++kc)
+                bulk_g2s(w_base + kc * B_CHUNK, g.wpack + (size_t)kc * g.wrows * 16, B_CHUNK, w_full);
+        }
+        f8::pdl_wait();                         // the activation is the previous launch's output
+        constexpr int LAG = 2;                  // a stage is signalled once LAG younger ones are issued
+        int slot = 0, phase = 0, aslot = 0, issued = 0;
+        for (int t = blockIdx.x; t < mtiles; t += gridDim.x) {
+            mbar_wait(empty_bar(slot), phase ^ 1);
+            const uint32_t sa = smem_base + slot * STAGE;
+            for (int idx = lane; idx < TM * cpa; idx += 32) {
+                const int r = cpa == 2 ? idx >> 1 : idx, ch = cpa == 2 ? idx & 1 : 0;
+                const int m = t * TM + r;
+                const bool ok = m < g.M;
+                cp_async16(sa + ch * (TM * 16) + r * 16, g.in + (size_t)(ok ? m : 0) * g.cin_pad + ch * 16, ok);
+            }
+            cp_async_commit();
+            if (++slot == S) { slot = 0; phase ^= 1; }
+            if (++issued > LAG) {
+                cp_async_wait<LAG>();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar(aslot));
+                if (++aslot == S) aslot = 0;
+                --issued;
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        __syncwarp();
+        for (; issued > 0; --issued) {
+            if (lane == 0) mbar_arrive(full_bar(aslot));
+            if (++aslot == S) aslot = 0;
+        }
+    } else if (warp == PRODUCER_WARP) {
         if (lane == 0) {
             tma_prefetch_desc(&tmap);
             tma_prefetch_desc(&omap);
@@ -486,7 +527,7 @@ conv1x1_res_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const
                     if (++slot == S) { slot = 0; phase ^= 1; }
                 }
             }
-            if (stats) { stats[blockIdx.x * 8 + 0] = clock64() - st_t0; stats[blockIdx.x * 8 + 1] = st_a; }
+            if (stats) { stats[blockIdx.x * 16 + 0] = clock64() - st_t0; stats[blockIdx.x * 16 + 1] = st_a; }
         }
     } else if (warp == MMA_WARP) {
         constexpr uint32_t idesc = instr_desc(A_SIGNED, BN);
@@ -508,7 +549,17 @@ conv1x1_res_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const
                 const uint32_t sa = smem_base + slot * STAGE;
                 const uint32_t a_lo = ((sa & 0x3ffffu) >> 4) | a_lbo_field;
                 const uint32_t b_lo = (((w_base + kt * 4 * B_CHUNK) & 0x3ffffu) >> 4) | b_lbo_field;
-                if (elect_one()) {
+                if (cpa) {
+                    // no-swizzle operand: K chunk 1 sits TM rows behind chunk 0 (16-channel inputs: its weights are zero)
+                    const uint32_t a_lo_c = ((sa & 0x3ffffu) >> 4) | ((uint32_t)((TM * 16) >> 4) << 16);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int sg = 0; sg < MSEG; ++sg)
+                            umma_i8_lohi(tacc + (uint32_t)(sg * BN), a_lo_c + (uint32_t)(sg * ((BM * 16) >> 4)), desc_hi,
+                                         b_lo, desc_hi, idesc, 0u);
+                        umma_commit(empty_bar(slot));
+                    }
+                } else if (elect_one()) {
 #pragma unroll
                     for (int sg = 0; sg < MSEG; ++sg) {
                         umma_i8_lohi(tacc + (uint32_t)(sg * BN), a_lo + (uint32_t)(sg * (A_STAGE >> 4)), desc_hi_a,
@@ -526,7 +577,7 @@ conv1x1_res_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const
             if (++buf == 2) { buf = 0; acc_phase ^= 1; }
         }
         if (stats && lane == 0) {
-            stats[blockIdx.x * 8 + 2] = clock64() - st_t0; stats[blockIdx.x * 8 + 3] = st_acc; stats[blockIdx.x * 8 + 4] = st_full;
+            stats[blockIdx.x * 16 + 2] = clock64() - st_t0; stats[blockIdx.x * 16 + 3] = st_acc; stats[blockIdx.x * 16 + 4] = st_full;
         }
     } else {
         // =========================== epilogue (16 warps) =========================
@@ -561,17 +612,19 @@ conv1x1_res_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const
         const int oswz = (lane >> 1) & 3;
         const bool out_unit = ep.out0 != nullptr && cbase < ep.cout_pad;      // warp-uniform
         int buf = 0, acc_phase = 0;
-        long long st_w = 0, st_st = 0;
+        long long st_w = 0, st_st = 0, st_p[4] = {0, 0, 0, 0};
         const long long st_t0 = clock64();
         for (int t = blockIdx.x; t < mtiles; t += gridDim.x) {
             const int m = t * TM + row;
             const bool valid = m < g.M;
             R_TIMED(st_w, mbar_wait(acc_full_bar(buf), acc_phase));
             tc_fence_after();
+            long long ph0 = stats ? clock64() : 0;
             if (out_unit) {            // the previous tile's store has finished reading the staging box
                 if (lane == 0) R_TIMED(st_st, tma_store_wait_read());
                 __syncwarp();
             }
+            if (stats) { const long long n = clock64(); st_p[0] += n - ph0; ph0 = n; }
             const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * 256 + seg * BN);
             // the TMEM load of step s + 1 is in flight while step s is computed
             // (plain path only: the generic path has no registers to spare for a second buffer)
@@ -613,9 +666,11 @@ conv1x1_res_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const
                     }
                 }
             }
+            if (stats) { const long long n = clock64(); st_p[1] += n - ph0; ph0 = n; }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty_bar(buf));
+            if (stats) { const long long n = clock64(); st_p[2] += n - ph0; ph0 = n; }
             if (out_unit) {
                 // rows past M and columns past cout_pad of the box are clipped by the tensor map
                 fence_proxy_async();
@@ -626,11 +681,14 @@ conv1x1_res_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const
                     tma_store_commit();
                 }
             }
+            if (stats) { const long long n = clock64(); st_p[3] += n - ph0; ph0 = n; }
             if (++buf == 2) { buf = 0; acc_phase ^= 1; }
         }
         if (out_unit && lane == 0) tma_store_wait_all();
+        if (stats && tid == 0)
+            for (int k = 0; k < 4; ++k) stats[blockIdx.x * 16 + 8 + k] = st_p[k];
         if (stats && tid == 0) {
-            stats[blockIdx.x * 8 + 5] = clock64() - st_t0; stats[blockIdx.x * 8 + 6] = st_w; stats[blockIdx.x * 8 + 7] = st_st;
+            stats[blockIdx.x * 16 + 5] = clock64() - st_t0; stats[blockIdx.x * 16 + 6] = st_w; stats[blockIdx.x * 16 + 7] = st_st;
         }
     }
 
@@ -694,26 +752,33 @@ int launch_res_p(const UGeom &g, const f8::Epilogue &ep, cudaStream_t s) {
         if (orc != F8_OK) return orc;
     }
     const int grid = mtiles < num_sms ? mtiles : num_sms;
+    // 16 / 32 input channels: cp.async operand loader (chunks per pixel), see the kernel
+    // (measured neutral: these layers are bound by the TMEM read rate of the epilogue, not by the loader;
+    // kept behind F8_CPA=1)
+    static const bool use_cpa = getenv("F8_CPA") != nullptr && atoi(getenv("F8_CPA")) != 0;
+    const int cpa = (use_cpa && S >= 4 && g.ktiles == 1 && (g.cin_pad == 16 || g.cin_pad == 32)) ? g.cin_pad / 16 : 0;
     static const bool want_stats = getenv("F8_STATS") != nullptr;
     static const int rprobe = getenv("F8_RPROBE") ? atoi(getenv("F8_RPROBE")) : 0;   // timing probes: WRONG results
     static long long *stats_dev = nullptr;
     if (want_stats) {
-        if (!stats_dev) F8_CUDA(cudaMalloc(&stats_dev, 8 * 1024 * sizeof(long long)));
-        F8_CUDA(cudaMemsetAsync(stats_dev, 0, 8 * 1024 * sizeof(long long), s));
+        if (!stats_dev) F8_CUDA(cudaMalloc(&stats_dev, 16 * 1024 * sizeof(long long)));
+        F8_CUDA(cudaMemsetAsync(stats_dev, 0, 16 * 1024 * sizeof(long long), s));
     }
     F8_CUDA(f8host::launch_pdl(kern, (unsigned)grid, (unsigned)R_THREADS, smem_bytes, s, g, ep, mtiles, S, tmap, omap,
-                               want_stats ? stats_dev : (long long *)nullptr, rprobe));
+                               want_stats ? stats_dev : (long long *)nullptr, rprobe, cpa));
     F8_CUDA(cudaGetLastError());
     if (want_stats) {
-        static long long host[8 * 1024];
+        static long long host[16 * 1024];
         F8_CUDA(cudaStreamSynchronize(s));
         F8_CUDA(cudaMemcpy(host, stats_dev, sizeof(host), cudaMemcpyDeviceToHost));
-        double acc[8] = {0};
+        double acc[16] = {0};
         for (int b = 0; b < grid; ++b)
-            for (int k = 0; k < 8; ++k) acc[k] += (double)host[b * 8 + k] / grid;
+            for (int k = 0; k < 16; ++k) acc[k] += (double)host[b * 16 + k] / grid;
         fprintf(stderr, "[f8 stats] conv1x1_res BN=%d cin=%d cout=%d M=%d tiles/cta=%.1f S=%d | producer total %.0f wait_empty %.0f | "
                 "mma total %.0f wait_acc %.0f wait_full %.0f | epi(warp 0) total %.0f wait_full %.0f wait_store %.0f (cycles, mean per CTA)\n",
                 BN, g.cin_pad, ep.cout_pad, g.M, (double)mtiles / grid, S, acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], acc[6], acc[7]);
+        fprintf(stderr, "[f8 stats]   epilogue warp 0 phases: store-wait+sync %.0f | tmem loads + math + staging %.0f | fence+sync+arrive %.0f | "
+                "proxy fence+sync+store issue %.0f\n", acc[8], acc[9], acc[10], acc[11]);
     }
     return F8_OK;
 }
