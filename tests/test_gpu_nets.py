@@ -135,3 +135,30 @@ def test_input_validation(cuda, f8lib):
     bad = torch.full((1, 3, 224, 224), 300, dtype=torch.int32)
     with pytest.raises(ValueError, match="outside"):
         eng(bad, strict=True)
+
+
+@pytest.mark.parametrize("switch,arch", [("F8_PAIR", "resnet18"), ("F8_CPA", "mobilenet_v2"), ("F8_PDL", "resnet18")])
+def test_switchable_kernel_paths_stay_exact(cuda, f8lib, switch, arch):
+    """Kernel variants kept behind environment switches: the CTA-pair form of the 3x3
+    kernel (F8_PAIR=1), the cp.async operand loader of the point-wise kernel (F8_CPA=1) and plain
+    stream order instead of programmatic dependent launch (F8_PDL=0).  The library reads the switches
+    once, so each runs in its own process: odd batch (ragged halves / tiles) against the oracle."""
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, torch, f8net_b200\n"
+        "from f8net_b200 import synth\n"
+        "from oracle import nets\n"
+        f"arch = {arch!r}\n"
+        "hs = synth.HEAD_SIGNED[arch]\n"
+        "sd = synth.make_state_dict(arch, hs)\n"
+        "x = synth.make_input(arch, 5, hs, seed=11)\n"
+        "eng = f8net_b200.compile(sd, arch=arch, head_signed=hs, chunk=5)\n"
+        "y = eng(torch.from_numpy(x).cuda()).cpu().numpy()\n"
+        "assert np.array_equal(y, nets.forward(arch, sd, x, hs)), 'logits differ'\n"
+        "print('exact')\n")
+    env = dict(os.environ)
+    env[switch] = "0" if switch == "F8_PDL" else "1"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "exact" in r.stdout, r.stderr[-2000:]
