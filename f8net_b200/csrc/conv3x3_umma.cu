@@ -20,16 +20,20 @@
 // on the zero column / zero row are computed and dropped (W/(W+1) * H/(H+1) of the MMA rows are
 // real pixels: 96 % at 56x56, 77 % at 7x7).
 //
-// Shared-memory operand layout (K-major, SWIZZLE_NONE): [16-byte channel chunk][slot][16 B],
-// i.e. core matrices of 8 consecutive slots x 16 B, SBO = 128 B, LBO = slots*16 B.  A tap shift
-// of d slots is "start address += 16*d".  K order: for each 64-channel group, for each tap:
-// two K=32 MMAs per M segment.  The 64-column weight tile of a (channel group, tap) is
-// fetched once (4 bulk copies of 1 KB) and used by all four M segments.
+// Shared-memory operand layout: the patch of one 64-channel group arrives by TMA as [slot][64 B] in
+// the 64-byte-swizzled K-major layout (SBO = 8 slots x 64 B); the swizzle XOR acts on absolute
+// address bits, so a tap shift of d slots is still "start address += 64*d" of the descriptor.
+// K order: for each 64-channel group, for each tap: two K=32 MMAs per M segment.  The weight ring
+// stage is one filter row (3 taps x 64 channels x BN columns, 12 bulk copies), shared by every
+// M segment of the tile.
 //
-// Persistent CTA, 1 per SM, 512 TMEM columns = 2 (double buffer) x 4 segments x 64 columns:
-//   warps 0-15 epilogue (the exact integer requantisation is instruction-bound: 16 warps)
-//   | warps 16-19 patch loaders (cp.async, zero fill) | warp 20: one elected lane issues the MMAs
-//   | warp 21 lane 0 weight-tile loader (cp.async.bulk).
+// Persistent CTA, 1 per SM, 512 TMEM columns = 2 accumulator sets x MB segments x BN columns
+// (BN = 64: 4 segments, BN = 128: 2):
+//   warps 0-15 epilogue (TMEM read rate and the exact integer requantisation bound it: 16 warps)
+//   | warp 16 patch loader (TMA, one lane per box) | warp 17: one elected lane issues the MMAs
+//   | warp 18 lane 0 weight-stage loader (cp.async.bulk).
+// Variants: STRIDE = 2 (four parity-plane tensor maps), DW (depthwise: diagonal 64 x 64 weight
+// blocks, two N = 32 MMAs per tap), PAIR (CTA pairs, cta_group::2; see the kernel).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
