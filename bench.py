@@ -12,8 +12,9 @@ scaling, no data-path collective) and the logits are all-gathered once per step 
 One JSON line on stdout (rank 0).  ``value``: inputs resident in HBM as the engine-native
 NHWC u8 tensor, rotating over several distinct batches so that every step's input comes from
 HBM, not L2.  ``e2e``: the same metric through the reference-facing call with HOST buffers --
-pinned int32 NCHW input (the reference's tensor), H2D copy, run, D2H copy of the logits, all
-inside the timed region (two engines on two streams overlap copy and compute).
+pinned int32 NCHW input (the reference's tensor), host-side narrowing to the engine's 8-bit
+layout, H2D copy, run, D2H copy of the logits, all inside the timed region (two engines on two
+streams overlap copy and compute).
 ``roofline``: the dominant kernel family (dense conv implicit GEMM), algorithmic bytes of its
 launches / their device time measured with CUDA events around every launch.  ``cpu_baseline``:
 the CPU oracle port (oracle/) on the host cores, a bounded sample of the same workload.
@@ -318,9 +319,15 @@ def gpu_arm(args):
         t = torch.tensor([e2e_dt], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
+    # run_host repacks the int32 tensor to NHWC4 bytes with the host cores (inside the timed region)
+    # and ships those; F8_HOST_PACK_THREADS=0 ships the int32 tensor itself
+    host_pack = os.environ.get("F8_HOST_PACK_THREADS", "") != "0"
     e2e = {"value": world * B * args.steps / e2e_dt, "unit": UNIT,
-           "h2d_bytes_per_step": B * 3 * S * S * 4, "d2h_bytes_per_step": B * eng.net.num_classes * 4,
-           "input": "pinned int32 NCHW (the reference's tensor), two engines on two streams",
+           "h2d_bytes_per_step": B * S * S * 4 if host_pack else B * 3 * S * S * 4,
+           "host_tensor_bytes_per_step": B * 3 * S * S * 4,
+           "d2h_bytes_per_step": B * eng.net.num_classes * 4,
+           "input": "pinned int32 NCHW (the reference's tensor), two engines on two streams"
+                    + ("; run_host narrows it to NHWC4 bytes on the host cores (timed) before the copy" if host_pack else ""),
            "timer": "host perf_counter around the loop, stream syncs inside"}
 
     # ---- the same call fed with decoded uint8 pixels [B,H,W,3]: ToTensor +

@@ -11,6 +11,10 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <thread>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <vector>
 
 #include "f8_common.cuh"
@@ -111,6 +115,10 @@ struct f8_plan {
     // forward_loss's input integerisation (f8_plan_set_input_prep)
     int prep_normalize = 0, prep_fraclen = 8;
     uint8_t *lut_dev = nullptr; // [3][256] table for F8_IN_NHWC3_U8
+    // f8_plan_run_host, int32 NCHW input: pinned staging of the host-side 8-bit repack
+    uint8_t *host_stage = nullptr;
+    size_t host_stage_bytes = 0;
+    cudaEvent_t host_stage_free = nullptr;   // recorded after the H2D copy that reads the staging
 };
 
 // ---------------------------------------------------------------------------------------
@@ -304,6 +312,8 @@ extern "C" void f8_plan_destroy(f8_plan *plan) {
     if (!plan) return;
     if (plan->blob) cudaFree(plan->blob);
     if (plan->lut_dev) cudaFree(plan->lut_dev);
+    if (plan->host_stage) cudaFreeHost(plan->host_stage);
+    if (plan->host_stage_free) cudaEventDestroy(plan->host_stage_free);
     delete plan;
 }
 
@@ -548,6 +558,49 @@ static int plan_run_impl(f8_plan *plan, const void *x_dev, int x_layout, int n,
     return F8_OK;
 }
 
+// int32 NCHW [n,3,hw] -> NHWC4 bytes (channel 3 = 0) on the host, rows [r0, r1) of the n*h image rows.
+// Keeps the low byte of every value, exactly what convert_input_kernel does on the device: the
+// reference's tensor holds 8-bit-range integers (fix_train.py:682-692), so 3 of every 4 bytes that
+// would cross PCIe carry nothing.
+static void pack_rows_nchw_i32(const int32_t *x, uint8_t *dst, int h, int w, long long r0, long long r1) {
+    const size_t hw = (size_t)h * w;
+    for (long long r = r0; r < r1; ++r) {
+        const long long img = r / h;
+        const int y = (int)(r - img * h);
+        const int32_t *c0 = x + (size_t)img * 3 * hw + (size_t)y * w;
+        const int32_t *c1 = c0 + hw, *c2 = c1 + hw;
+        uint32_t *o = reinterpret_cast<uint32_t *>(dst) + (size_t)r * w;
+        int i = 0;
+#if defined(__SSE2__)
+        // streaming stores: the staging is written once and read by the DMA engine, never by this core
+        if ((reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
+            const __m128i m = _mm_set1_epi32(0xff);
+            for (; i + 4 <= w; i += 4) {
+                const __m128i a = _mm_and_si128(_mm_loadu_si128(reinterpret_cast<const __m128i *>(c0 + i)), m);
+                const __m128i b = _mm_and_si128(_mm_loadu_si128(reinterpret_cast<const __m128i *>(c1 + i)), m);
+                const __m128i c = _mm_and_si128(_mm_loadu_si128(reinterpret_cast<const __m128i *>(c2 + i)), m);
+                _mm_stream_si128(reinterpret_cast<__m128i *>(o + i),
+                                 _mm_or_si128(a, _mm_or_si128(_mm_slli_epi32(b, 8), _mm_slli_epi32(c, 16))));
+            }
+        }
+#endif
+        for (; i < w; ++i)
+            o[i] = ((uint32_t)c0[i] & 0xffu) | (((uint32_t)c1[i] & 0xffu) << 8) | (((uint32_t)c2[i] & 0xffu) << 16);
+    }
+#if defined(__SSE2__)
+    _mm_sfence();
+#endif
+}
+
+static int host_pack_threads() {
+    static const int t = [] {
+        if (const char *e = getenv("F8_HOST_PACK_THREADS")) return std::max(0, atoi(e));   // 0 = ship the int32 tensor as is
+        const unsigned hc = std::thread::hardware_concurrency();
+        return (int)std::min(16u, std::max(1u, hc));
+    }();
+    return t;
+}
+
 extern "C" int f8_plan_run_host(f8_plan *plan, const void *x_host, int x_layout, int n,
                                 float *logits_host, void *x_stage_dev, float *logits_dev,
                                 void *workspace_dev, size_t workspace_bytes, int chunk,
@@ -561,7 +614,34 @@ extern "C" int f8_plan_run_host(f8_plan *plan, const void *x_host, int x_layout,
     int cur = -1;
     F8_CUDA(cudaGetDevice(&cur));
     if (cur != plan->device) F8_CUDA(cudaSetDevice(plan->device));
-    F8_CUDA(cudaMemcpyAsync(x_stage_dev, x_host, x_img * (size_t)n, cudaMemcpyHostToDevice, s));
+    const int nthreads = host_pack_threads();
+    if (x_layout == F8_IN_NCHW_I32 && nthreads > 0) {
+        // repack to the engine-native NHWC4 bytes with the host cores, ship a third of the bytes
+        const size_t bytes = (size_t)n * plan->image_h * plan->image_w * 4;
+        if (plan->host_stage_bytes < bytes) {
+            if (plan->host_stage) { F8_CUDA(cudaStreamSynchronize(s)); F8_CUDA(cudaFreeHost(plan->host_stage)); }
+            plan->host_stage = nullptr;
+            plan->host_stage_bytes = 0;
+            F8_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&plan->host_stage), bytes, cudaHostAllocDefault));
+            plan->host_stage_bytes = bytes;
+        }
+        if (!plan->host_stage_free) F8_CUDA(cudaEventCreateWithFlags(&plan->host_stage_free, cudaEventDisableTiming));
+        else F8_CUDA(cudaEventSynchronize(plan->host_stage_free));      // the previous copy has read the staging
+        const long long rows = (long long)n * plan->image_h;
+        const int T = (int)std::min<long long>(nthreads, std::max<long long>(1, rows / 64));
+        const int32_t *xi = static_cast<const int32_t *>(x_host);
+        std::vector<std::thread> pool;
+        for (int t = 1; t < T; ++t)
+            pool.emplace_back(pack_rows_nchw_i32, xi, plan->host_stage, plan->image_h, plan->image_w, rows * t / T,
+                              rows * (t + 1) / T);
+        pack_rows_nchw_i32(xi, plan->host_stage, plan->image_h, plan->image_w, 0, rows / T);
+        for (auto &th : pool) th.join();
+        F8_CUDA(cudaMemcpyAsync(x_stage_dev, plan->host_stage, bytes, cudaMemcpyHostToDevice, s));
+        F8_CUDA(cudaEventRecord(plan->host_stage_free, s));
+        x_layout = F8_IN_NHWC4_8;
+    } else {
+        F8_CUDA(cudaMemcpyAsync(x_stage_dev, x_host, x_img * (size_t)n, cudaMemcpyHostToDevice, s));
+    }
     int rc = f8_plan_run(plan, x_stage_dev, x_layout, n, logits_dev, workspace_dev,
                          workspace_bytes, chunk, stream);
     if (rc) return rc;
