@@ -172,7 +172,12 @@ F8_API int f8_plan_set_input_prep(f8_plan *plan, int normalize, int fraclen, con
  * input (n * 3*H*W*4 bytes for NCHW_I32 / NCHW_F32, n * H*W*4 for NHWC4_8, n * H*W*3 for NHWC3_U8).  sync = 0 leaves the stream
  * unsynchronised (x_host / logits_host must then be pinned and stay alive) so that a caller
  * can overlap the copies of one batch with the compute of another on a second stream.  This
- * is the entry the reference-facing call surface uses for CPU tensors. */
+ * is the entry the reference-facing call surface uses for CPU tensors.
+ * F8_IN_NCHW_I32: the tensor holds 8-bit-range integers (fix_train.py:682-692), so the call first
+ * narrows it on the host cores to NHWC4 bytes (the low byte of every value, as the device-side
+ * conversion keeps) in a plan-owned pinned staging buffer and copies a third of the bytes; x_host
+ * has been fully read when the call returns.  Environment F8_HOST_PACK_THREADS = number of host
+ * threads (default min(16, cores); 0 = copy the int32 tensor as is).  One call at a time per plan. */
 F8_API int f8_plan_run_host(f8_plan *plan, const void *x_host, int x_layout, int n, float *logits_host,
                      void *x_stage_dev, float *logits_dev, void *workspace_dev,
                      size_t workspace_bytes, int chunk, int sync, void *stream);
