@@ -648,6 +648,19 @@ class PackPool {
     unsigned long long gen_ = 0;
 };
 
+static PackPool &pack_pool() {
+    static PackPool *pool = new PackPool;                   // never destroyed: its threads outlive main()
+    return *pool;
+}
+
+extern "C" int f8_pack_input_host(const int32_t *x, int n, int h, int w, void *dst, int threads) {
+    if (!x || !dst || n <= 0 || h <= 0 || w <= 0) { set_error("pack_input_host: bad arguments"); return F8_ERR_ARG; }
+    const long long rows = (long long)n * h;
+    const int T = (int)std::min<long long>(std::max(1, threads), std::max<long long>(1, rows / 64));
+    pack_pool().run(x, static_cast<uint8_t *>(dst), h, w, rows, T);
+    return F8_OK;
+}
+
 static int host_pack_threads() {
     static const int t = [] {
         if (const char *e = getenv("F8_HOST_PACK_THREADS")) return std::max(0, atoi(e));   // 0 = ship the int32 tensor as is
@@ -685,8 +698,7 @@ extern "C" int f8_plan_run_host(f8_plan *plan, const void *x_host, int x_layout,
         else F8_CUDA(cudaEventSynchronize(plan->host_stage_free));      // the previous copy has read the staging
         const long long rows = (long long)n * plan->image_h;
         const int T = (int)std::min<long long>(nthreads, std::max<long long>(1, rows / 64));
-        static PackPool *pool = new PackPool;               // never destroyed: its threads outlive main()
-        pool->run(static_cast<const int32_t *>(x_host), plan->host_stage, plan->image_h, plan->image_w, rows, T);
+        pack_pool().run(static_cast<const int32_t *>(x_host), plan->host_stage, plan->image_h, plan->image_w, rows, T);
         F8_CUDA(cudaMemcpyAsync(x_stage_dev, plan->host_stage, bytes, cudaMemcpyHostToDevice, s));
         F8_CUDA(cudaEventRecord(plan->host_stage_free, s));
         x_layout = F8_IN_NHWC4_8;

@@ -259,6 +259,10 @@ F8_API int f8_integerize_f32(const float *x, void *out, int n, int h, int w, int
  * f8_make_input_lut fills the (host) table for given normalize / fraclen / mean / std. */
 F8_API int f8_integerize_u8(const uint8_t *x, const uint8_t *lut_dev, void *out, int n, int h, int w,
                      void *stream);
+/* Host-only (no CUDA call): the narrowing f8_plan_run_host applies to an F8_IN_NCHW_I32 host tensor.
+ * x int32 [n,3,h,w] -> dst bytes [n,h,w,4] = the low byte of each channel value, channel 3 = 0 (what
+ * f8_convert_input produces on the device).  threads <= 1: the calling thread only. */
+F8_API int f8_pack_input_host(const int32_t *x, int n, int h, int w, void *dst, int threads);
 F8_API int f8_make_input_lut(int normalize, int fraclen, const float *mean3, const float *std3,
                       uint8_t *lut_host768);
 /* Replaces: int_op_only_fix_quant as a standalone op (fix_quant_ops.py:90-114):

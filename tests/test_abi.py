@@ -164,3 +164,20 @@ def test_input_lut_matches_reference(f8lib):
         want = g[key][0]
         got = got.view(np.int8).astype(np.int32) if normalize else got.astype(np.int32)
         assert np.array_equal(got, want), key
+
+
+def test_pack_input_host_low_bytes_nhwc4(f8lib):
+    """The host-side narrowing of f8_plan_run_host (int32 NCHW -> NHWC4 low bytes), every thread
+    count, ragged shapes (row tails, fewer rows than threads), unsigned and signed ranges; repeated
+    calls reuse the persistent helper threads."""
+    rng = np.random.default_rng(3)
+    for n, h, w in [(1, 1, 1), (2, 5, 7), (3, 64, 30), (5, 224, 224), (9, 33, 18)]:
+        for lo, hi in [(0, 256), (-127, 128)]:
+            x = rng.integers(lo, hi, (n, 3, h, w)).astype(np.int32)
+            want = np.zeros((n, h, w, 4), np.uint8)
+            want[..., :3] = (x.transpose(0, 2, 3, 1) & 0xff).astype(np.uint8)
+            for threads in (0, 1, 3, 16):
+                out = np.full((n, h, w, 4), 0x55, np.uint8)
+                assert f8lib.f8_pack_input_host(x.ctypes.data, n, h, w, out.ctypes.data, threads) == 0
+                assert np.array_equal(out, want), (n, h, w, lo, threads)
+    assert f8lib.f8_pack_input_host(None, 1, 1, 1, None, 1) != 0
