@@ -204,7 +204,11 @@ class _Exporter:
             if self.f.rescale_type == "stddev":
                 ws = t.std(weight)
             elif self.f.rescale_type == "constant":
-                ws = 1.0 / (layer.out_ch * layer.k * layer.k) ** 0.5
+                # the reference cannot export this combination either: float_weight reads
+                # self.out_channels / self.kernel_size, which ReLUClipFXQConvBN does not define
+                # (fix_quant_ops.py:539-541 -> AttributeError inside the int_weight property)
+                raise NotImplementedError("rescale_forward_conv with rescale_type 'constant' is not exportable "
+                                          "in the reference (fix_quant_ops.py:539-541)")
             else:
                 raise NotImplementedError
             ws = ws / t.std(weight)

@@ -39,7 +39,7 @@ def available():
     return os.path.isdir(os.path.join(REF_ROOT, "models"))
 
 
-def build_int_model(arch, float_state_dict=None, keep_grid_search=False):
+def build_int_model(arch, float_state_dict=None, keep_grid_search=False, flag_overrides=None):
     """Return (IntModel, FLAGS) built the way fix_train.py:258-296 + :930-934 does, on CPU.
     ``float_state_dict``: loaded into the float-sim Model before ``int_model()`` converts it (the
     export golden vectors, tests/golden/make_export_golden.py)."""
@@ -75,6 +75,8 @@ def build_int_model(arch, float_state_dict=None, keep_grid_search=False):
         finally:
             nn.Conv2d, nn.Linear = oc, ol
 
+    for k, v in (flag_overrides or {}).items():    # config variants of the export golden vectors
+        setattr(FLAGS, k, v)
     if getattr(FLAGS, "format_grid_search", False) and not keep_grid_search:
         # grid search only affects the *values* int_model() exports, which we overwrite
         # with the synthetic state dict; skip its cost (fix_quant_ops.py:17-27).

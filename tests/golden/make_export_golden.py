@@ -23,11 +23,27 @@ sys.path.insert(0, ROOT)
 SEED = 77
 
 
-def flags_for(arch):
+# config variants beyond the shipped *_int_op_only*.yml files: name -> (ExportFlags fields, FLAGS overrides)
+VARIANTS = {
+    "sharing": (dict(input_fraclen_sharing=True), dict(input_fraclen_sharing=True)),
+    "rms": (dict(metric="rms"), dict(metric="rms")),
+    "mae": (dict(metric="mae"), dict(metric="mae")),
+    "convrescale": (dict(rescale_forward_conv=True, rescale_type="stddev"),
+                    dict(rescale_forward_conv=True, rescale_type="stddev")),
+    "norescale": (dict(rescale_forward=False), dict(rescale_forward=False)),
+}
+
+
+def flags_for(arch, variant=None):
     from f8net_b200.export import ExportFlags
     if arch == "resnet50":      # res50 tiny_finetuning config: normalize, no_clipping, grid search
-        return ExportFlags(normalize=True, no_clipping=True, format_grid_search=True)
-    return ExportFlags()
+        f = ExportFlags(normalize=True, no_clipping=True, format_grid_search=True)
+    else:
+        f = ExportFlags()
+    if variant:
+        for k, v in VARIANTS[variant][0].items():
+            setattr(f, k, v)
+    return f
 
 
 def digest(t):
@@ -36,16 +52,17 @@ def digest(t):
     return hashlib.sha256(a.tobytes()).hexdigest()
 
 
-def one(arch):
+def one(arch, variant=None):
     import numpy as np
     import torch
     from f8net_b200 import synth
     from f8net_b200.export import export_int_state_dict
     from oracle import ref_harness
     torch.set_num_threads(8)
-    flags = flags_for(arch)
+    flags = flags_for(arch, variant)
     fsd = synth.make_float_state_dict(arch, SEED, flags)
-    im, FLAGS = ref_harness.build_int_model(arch, float_state_dict=fsd, keep_grid_search=True)
+    im, FLAGS = ref_harness.build_int_model(arch, float_state_dict=fsd, keep_grid_search=True,
+                                            flag_overrides=VARIANTS[variant][1] if variant else None)
     for k in ("normalize", "no_clipping", "format_grid_search"):
         assert bool(getattr(FLAGS, k, False)) == bool(getattr(flags, k)), (k, getattr(FLAGS, k, None))
     ref = im.state_dict()
@@ -66,17 +83,21 @@ def one(arch):
     for k in ref:
         if not k.endswith(".weight"):
             out[k] = ref[k].numpy()
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"export_{arch}.npz"), **out)
+    tag = f"{arch}_{variant}" if variant else arch
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"export_{tag}.npz"), **out)
     fws = [int(ref[k]) for k in ref if k.endswith("weight_fraclen")]
-    print(f"{arch}: {len(ref)} tensors identical to the reference int_model(); weight fraclens "
+    print(f"{tag}: {len(ref)} tensors identical to the reference int_model(); weight fraclens "
           f"{sorted(set(fws))}")
 
 
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "--one":
-        one(sys.argv[2])
+        one(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
     else:
         archs = sys.argv[1:] or ["resnet18", "resnet50", "mobilenet_v1", "mobilenet_v2"]
         env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
         for a in archs:
             subprocess.check_call([sys.executable, os.path.abspath(__file__), "--one", a], env=env, cwd=ROOT)
+        if not sys.argv[1:]:        # config variants on the two small networks
+            for a, v in [("resnet18", v) for v in VARIANTS] + [("mobilenet_v2", "sharing")]:
+                subprocess.check_call([sys.executable, os.path.abspath(__file__), "--one", a, v], env=env, cwd=ROOT)

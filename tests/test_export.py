@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "gol
 from f8net_b200 import synth  # noqa: E402
 from f8net_b200.arch import graph_for  # noqa: E402
 from f8net_b200.export import ExportFlags, export_int_state_dict, float_layers  # noqa: E402
-from make_export_golden import SEED, flags_for  # noqa: E402
+from make_export_golden import SEED, VARIANTS, flags_for  # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ARCHS = ["resnet18", "resnet50", "mobilenet_v1", "mobilenet_v2"]
@@ -48,6 +48,21 @@ def test_export_equals_reference_int_model(arch):
     assert int(sd["head.0.weight"].abs().max()) <= 127
 
 
+@pytest.mark.parametrize("arch,variant", [("resnet18", v) for v in VARIANTS] + [("mobilenet_v2", "sharing")])
+def test_export_config_variants_equal_reference(arch, variant):
+    """Config switches the shipped int_op_only yml files leave at their defaults -- input_fraclen_sharing
+    (master layers share the buffer, fix_quant_ops.py:462-471), metric rms / mae (metric2fraclen
+    coefficients, :30-37), conv weight rescaling (:306-316, 534-544), no classifier rescaling (:1046-1056) --
+    against vectors the reference produced with the same FLAGS overrides."""
+    gold = np.load(os.path.join(GOLD, f"export_{arch}_{variant}.npz"))
+    flags = flags_for(arch, variant)
+    sd = export_int_state_dict(synth.make_float_state_dict(arch, SEED, flags), arch, flags)
+    keys = [str(k) for k in gold["keys"]]
+    assert list(sd.keys()) == keys
+    for k, want in zip(keys, gold["sha256"]):
+        assert _sha(sd[k]) == str(want), (variant, k)
+
+
 def test_wiring_master_and_following():
     """fix_resnet.py:148-153, 194-199, 456-467: a downsample block's body[0] and shortcut inherit
     the previous identity block's master; block-last convs and shortcuts are followed by the
@@ -71,6 +86,12 @@ def test_wiring_master_and_following():
     V = {l.fprefix: l for l in float_layers(graph_for("mobilenet_v1"), ExportFlags())}
     assert all(l.master is None for l in V.values())
     assert V["stage_4_layer_1.body.1"].avgpool_scale == 64 / 49
+
+
+def test_conv_constant_rescale_fails_like_the_reference():
+    flags = ExportFlags(rescale_forward_conv=True, rescale_type="constant")
+    with pytest.raises(NotImplementedError):
+        export_int_state_dict(synth.make_float_state_dict("resnet18", SEED, flags), "resnet18", flags)
 
 
 def test_rejects_an_int_state_dict():
