@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libf8b200.so")
-SOURCES = ["plan.cu", "conv_mma.cu", "conv_umma.cu", "conv3x3_umma.cu", "head_pool_umma.cu", "head_pool2_umma.cu", "head3x3_umma.cu", "dw_conv.cu", "pool_misc.cu"]
+SOURCES = ["plan.cu", "conv_mma.cu", "conv_umma.cu", "conv3x3_umma.cu", "head_pool2_umma.cu", "head3x3_umma.cu", "dw_conv.cu", "pool_misc.cu"]
 HEADERS = [os.path.join(CSRC, "f8_common.cuh"), os.path.join(CSRC, "umma_common.cuh"), os.path.join(CSRC, "tma_common.cuh"), os.path.join(HERE, "..", "include", "f8b200.h")]
 
 
@@ -45,6 +45,8 @@ def build(force=False, verbose=False):
            "-shared", "-o", LIB]
     if any(s.endswith("conv_umma.cu") for s in srcs):
         cmd += ["-DF8_WITH_UMMA"]
+    if os.environ.get("F8_DEBUG_PROBES"):      # in-kernel wait counters / timing probes (never in the shipping build)
+        cmd += ["-DF8_DEBUG_PROBES"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += srcs

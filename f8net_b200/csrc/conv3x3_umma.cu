@@ -98,7 +98,7 @@ struct PGeom {
 
 #define F8_TIMED_WAIT(acc, stmt)                 \
     do {                                         \
-        if (g.stats) {                           \
+        if (F8_DBG && g.stats) {                 \
             const long long _t0 = clock64();     \
             stmt;                                \
             acc += clock64() - _t0;              \
@@ -160,7 +160,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     int32_t *sbias = reinterpret_cast<int32_t *>(after + 16);
 
     const long long t_entry = clock64();
-    if (g.stats && threadIdx.x == 0) {
+    if (F8_DBG && g.stats && threadIdx.x == 0) {
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         g.stats[blockIdx.x * 16 + 2] = (long long)gt;
@@ -262,7 +262,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                     if (++slot == SA) { slot = 0; phase ^= 1; }
                 }
             }
-            if (g.stats && lane == 0) {
+            if (F8_DBG && g.stats && lane == 0) {
                 g.stats[blockIdx.x * 16 + 0] = clock64() - t_begin;
                 g.stats[blockIdx.x * 16 + 1] = w_empty;
             }
@@ -363,7 +363,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
             for (int cg = 0; cg < ncg; ++cg) {
                 F8_TIMED_WAIT(w_a, mbar_wait(a_full(aslot), aphase));
                 if (PAIR) F8_TIMED_WAIT(w_a, mbar_wait_cluster(a_peer(aslot), aphase));
-                if (g.stats && t_first_a == 0) t_first_a = clock64();
+                if (F8_DBG && g.stats && t_first_a == 0) t_first_a = clock64();
                 const uint32_t sa = smem_base + aslot * a_stage + (TMA ? (uint32_t)tile_soff * 64u : 0u);
                 const uint32_t first = (uint32_t)(cg != 0);
                 // depthwise: does this channel group have channels 32..63?
@@ -379,7 +379,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                     if (elect_one()) {
 #pragma unroll
                         for (int fs = 0; fs < 3; ++fs) {
-                            if (g.probe & 32) continue;
+                            if (F8_DBG && (g.probe & 32)) continue;
                             // slot offset of tap (fr, fs): stride 1: fr*PW + fs; stride 2: parity plane
                             // ((fr != 1), (fs != 1)) and a one-row / one-column step for fr > 0 / fs > 0
                             const uint32_t a_lo0 = a_row + (STRIDE == 2 ? (fs == 0 ? tap_col[0] : (fs == 1 ? SLOT16 : tap_col[1]))
@@ -430,7 +430,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
             __syncwarp();
             if (++buf == 2) { buf = 0; acc_phase ^= 1; }
         }
-        if (g.stats && lane == 0) {
+        if (F8_DBG && g.stats && lane == 0) {
             g.stats[blockIdx.x * 16 + 5] = clock64() - t_begin;
             g.stats[blockIdx.x * 16 + 6] = w_acc;
             g.stats[blockIdx.x * 16 + 7] = w_a;
@@ -468,7 +468,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
             if (PLAIN_U8) {
                 F8_TIMED_WAIT(w_full, mbar_wait(acc_full(buf), acc_phase));
                 tc_fence_after();
-                if (cw0 < ncols && !(g.probe & 16)) {
+                if (cw0 < ncols && !(F8_DBG && (g.probe & 16))) {
 #pragma unroll
                     for (int i = 0; i < MB; ++i) {
                         const int m = st * TM + i * 128 + row;
@@ -583,7 +583,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
             }
             if (++buf == 2) { buf = 0; acc_phase ^= 1; }
         }
-        if (g.stats && tid == 0) {
+        if (F8_DBG && g.stats && tid == 0) {
             g.stats[blockIdx.x * 16 + 9] = clock64() - t_begin;
             g.stats[blockIdx.x * 16 + 10] = w_full;
             g.stats[blockIdx.x * 16 + 11] = t_issue;
@@ -601,7 +601,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
         if (PAIR) tmem_dealloc2(tmem_base, 512);
         else tmem_dealloc(tmem_base, 512);
     }
-    if (g.stats && tid == 0) {
+    if (F8_DBG && g.stats && tid == 0) {
         g.stats[blockIdx.x * 16 + 11] = clock64() - t_entry;
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -660,7 +660,7 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     ep.cout = a.cout;
     ep.cout_pad = a.cout_pad;
     int probe_bits = 0;
-    if (const char *probe = getenv("F8_PROBE")) {   // timing probes only: WRONG results
+    if (const char *probe = f8host::debug_env("F8_PROBE")) {   // timing probes only: WRONG results
         const int pv = atoi(probe);
         if (pv & 1) ep.carry_in = nullptr;
         if (pv & 2) ep.carry_out = nullptr;
@@ -715,23 +715,23 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     g.slots_pad = slots_pad;
     g.n_super = (int)((lin + TM - 1) / TM);
     g.ntiles_n = (a.cout_pad + BN - 1) / BN;
-    static bool attr_done = false;
-    static int num_sms = 0;
-    if (!attr_done) {
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, false, STRIDE, DW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, false, STRIDE, DW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, true, STRIDE, DW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, true, STRIDE, DW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        int dev = 0;
-        F8_CUDA(cudaGetDevice(&dev));
-        F8_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_done = true;
+    static f8host::DeviceOnce once;
+    int num_sms = 0;
+    {
+        const int rc = f8host::device_once(once, &num_sms, []() -> int {
+            F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, false, STRIDE, DW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, false, STRIDE, DW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, true, STRIDE, DW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, true, STRIDE, DW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            return F8_OK;
+        });
+        if (rc) return rc;
     }
     long long grid = (long long)g.n_super * g.ntiles_n;
     if (PAIR) grid *= 2;                                  // two CTAs per item
     if (grid > num_sms) grid = num_sms;
     if (PAIR) grid &= ~1LL;
-    static const bool want_stats = getenv("F8_STATS") != nullptr;
+    static const bool want_stats = f8host::debug_env("F8_STATS") != nullptr;
     static long long *stats_dev = nullptr;
     if (want_stats) {
         if (!stats_dev) F8_CUDA(cudaMalloc(&stats_dev, 16 * 1024 * sizeof(long long)));
@@ -764,6 +764,8 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     }
     const unsigned th = (epi_warps_for(plain) + 3) * 32;
     constexpr int CL = PAIR ? 2 : 1;
+    f8host::note_kernel("conv3x3_umma<BN=%d,s%d,%s%s%s>", BN, STRIDE, DW ? "dw" : "dense", plain ? ",plain" : ",generic",
+                        PAIR ? ",pair" : "");
     if (a.in_signed) {
         if (plain) F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, true, true, STRIDE, DW, PAIR>, gr, th, smem_launch, s, CL, g, ep, tmaps));
         else F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, true, false, STRIDE, DW, PAIR>, gr, th, smem_launch, s, CL, g, ep, tmaps));

@@ -316,12 +316,17 @@ int launch_t(const ConvGeom &g, const f8::Epilogue &ep, int ntiles_n, cudaStream
     constexpr int smem_epi = 2 * BM * (BN + 16);
     constexpr int smem_bytes = smem_pipe > smem_epi ? smem_pipe : smem_epi;
     auto kern = conv_mma_kernel<BN, A_SIGNED, SMALL_C>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        F8_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        attr_done = true;
+    static f8host::DeviceOnce once;
+    int num_sms = 0;
+    {
+        const int rc = f8host::device_once(once, &num_sms, [&]() -> int {
+            F8_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+            return F8_OK;
+        });
+        if (rc) return rc;
     }
     dim3 grid((g.M + BM - 1) / BM, ntiles_n);
+    f8host::note_kernel("conv_mma<BN=%d%s>", BN, SMALL_C ? ",small_c" : "");
     kern<<<grid, THREADS, smem_bytes, s>>>(g, ep);
     F8_CUDA(cudaGetLastError());
     return F8_OK;

@@ -390,7 +390,7 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
 // One CTA per SM, persistent.  Same operand layouts, descriptors and epilogue as the TMA_A path.
 #define R_TIMED(acc, stmt)                       \
     do {                                         \
-        if (stats) {                             \
+        if (F8_DBG && stats) {                   \
             const long long _t0 = clock64();     \
             stmt;                                \
             acc += clock64() - _t0;              \
@@ -527,7 +527,7 @@ conv1x1_res_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const
                     if (++slot == S) { slot = 0; phase ^= 1; }
                 }
             }
-            if (stats) { stats[blockIdx.x * 16 + 0] = clock64() - st_t0; stats[blockIdx.x * 16 + 1] = st_a; }
+            if (F8_DBG && stats) { stats[blockIdx.x * 16 + 0] = clock64() - st_t0; stats[blockIdx.x * 16 + 1] = st_a; }
         }
     } else if (warp == MMA_WARP) {
         constexpr uint32_t idesc = instr_desc(A_SIGNED, BN);
@@ -576,7 +576,7 @@ conv1x1_res_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const
             __syncwarp();
             if (++buf == 2) { buf = 0; acc_phase ^= 1; }
         }
-        if (stats && lane == 0) {
+        if (F8_DBG && stats && lane == 0) {
             stats[blockIdx.x * 16 + 2] = clock64() - st_t0; stats[blockIdx.x * 16 + 3] = st_acc; stats[blockIdx.x * 16 + 4] = st_full;
         }
     } else {
@@ -619,12 +619,12 @@ conv1x1_res_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const
             const bool valid = m < g.M;
             R_TIMED(st_w, mbar_wait(acc_full_bar(buf), acc_phase));
             tc_fence_after();
-            long long ph0 = stats ? clock64() : 0;
+            long long ph0 = (F8_DBG && stats) ? clock64() : 0;
             if (out_unit) {            // the previous tile's store has finished reading the staging box
                 if (lane == 0) R_TIMED(st_st, tma_store_wait_read());
                 __syncwarp();
             }
-            if (stats) { const long long n = clock64(); st_p[0] += n - ph0; ph0 = n; }
+            if (F8_DBG && stats) { const long long n = clock64(); st_p[0] += n - ph0; ph0 = n; }
             const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * 256 + seg * BN);
             // the TMEM load of step s + 1 is in flight while step s is computed
             // (plain path only: the generic path has no registers to spare for a second buffer)
@@ -647,7 +647,7 @@ conv1x1_res_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const
                         const size_t o = (size_t)m * ep.cout_pad + c0;
                         uint8_t *so = ostage + ((sidx ^ oswz) << 4);
                         if (plain) {
-                            if (probe & 1) *reinterpret_cast<uint4 *>(so) = make_uint4(v[0], v[5], v[10], v[15]);   // timing probe: WRONG results
+                            if (F8_DBG && (probe & 1)) *reinterpret_cast<uint4 *>(so) = make_uint4(v[0], v[5], v[10], v[15]);   // timing probe: WRONG results
                             else f8::epilogue16_plain_u8(v, sbias + c0, so, ep.shift0);
                         } else if (valid) {
                             f8::epilogue16_math(v, sbias + c0, kc, c, has_carry);
@@ -666,28 +666,28 @@ conv1x1_res_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const
                     }
                 }
             }
-            if (stats) { const long long n = clock64(); st_p[1] += n - ph0; ph0 = n; }
+            if (F8_DBG && stats) { const long long n = clock64(); st_p[1] += n - ph0; ph0 = n; }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty_bar(buf));
-            if (stats) { const long long n = clock64(); st_p[2] += n - ph0; ph0 = n; }
+            if (F8_DBG && stats) { const long long n = clock64(); st_p[2] += n - ph0; ph0 = n; }
             if (out_unit) {
                 // rows past M and columns past cout_pad of the box are clipped by the tensor map
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0 && !(probe & 2)) {
+                if (lane == 0 && !(F8_DBG && (probe & 2))) {
                     tma_store_4d(&omap, cbase, t * TM + seg * BM + lg * 32, 0, 0,
                                  o_base + (uint32_t)(warp * OSTAGE));
                     tma_store_commit();
                 }
             }
-            if (stats) { const long long n = clock64(); st_p[3] += n - ph0; ph0 = n; }
+            if (F8_DBG && stats) { const long long n = clock64(); st_p[3] += n - ph0; ph0 = n; }
             if (++buf == 2) { buf = 0; acc_phase ^= 1; }
         }
         if (out_unit && lane == 0) tma_store_wait_all();
-        if (stats && tid == 0)
+        if (F8_DBG && stats && tid == 0)
             for (int k = 0; k < 4; ++k) stats[blockIdx.x * 16 + 8 + k] = st_p[k];
-        if (stats && tid == 0) {
+        if (F8_DBG && stats && tid == 0) {
             stats[blockIdx.x * 16 + 5] = clock64() - st_t0; stats[blockIdx.x * 16 + 6] = st_w; stats[blockIdx.x * 16 + 7] = st_st;
         }
     }
@@ -715,15 +715,15 @@ int launch_res_p(const UGeom &g, const f8::Epilogue &ep, cudaStream_t s) {
     constexpr int TM = MSEG * BM;
     constexpr int STAGE = MSEG * A_STAGE;
     const int w_bytes = g.ktiles * BK * BN;
-    static int num_sms = 0;
-    static bool attr_done = false;
     auto kern = conv1x1_res_kernel<BN, A_SIGNED, PLAIN>;
-    if (!attr_done) {
-        F8_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        int dev = 0;
-        F8_CUDA(cudaGetDevice(&dev));
-        F8_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_done = true;
+    static f8host::DeviceOnce once;
+    int num_sms = 0;
+    {
+        const int rc = f8host::device_once(once, &num_sms, [&]() -> int {
+            F8_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            return F8_OK;
+        });
+        if (rc) return rc;
     }
     const int mtiles = (g.M + TM - 1) / TM;
     if (w_bytes > 64 * 1024 || mtiles < 2 * num_sms) return F8_ERR_UNSUPPORTED;
@@ -757,13 +757,14 @@ int launch_res_p(const UGeom &g, const f8::Epilogue &ep, cudaStream_t s) {
     // kept behind F8_CPA=1)
     static const bool use_cpa = getenv("F8_CPA") != nullptr && atoi(getenv("F8_CPA")) != 0;
     const int cpa = (use_cpa && S >= 4 && g.ktiles == 1 && (g.cin_pad == 16 || g.cin_pad == 32)) ? g.cin_pad / 16 : 0;
-    static const bool want_stats = getenv("F8_STATS") != nullptr;
-    static const int rprobe = getenv("F8_RPROBE") ? atoi(getenv("F8_RPROBE")) : 0;   // timing probes: WRONG results
+    static const bool want_stats = f8host::debug_env("F8_STATS") != nullptr;
+    static const int rprobe = f8host::debug_env("F8_RPROBE") ? atoi(f8host::debug_env("F8_RPROBE")) : 0;   // timing probes: WRONG results
     static long long *stats_dev = nullptr;
     if (want_stats) {
         if (!stats_dev) F8_CUDA(cudaMalloc(&stats_dev, 16 * 1024 * sizeof(long long)));
         F8_CUDA(cudaMemsetAsync(stats_dev, 0, 16 * 1024 * sizeof(long long), s));
     }
+    f8host::note_kernel("conv1x1_res<BN=%d,%s>", BN, PLAIN ? "plain" : "generic");
     F8_CUDA(f8host::launch_pdl(kern, (unsigned)grid, (unsigned)R_THREADS, smem_bytes, s, g, ep, mtiles, S, tmap, omap,
                                want_stats ? stats_dev : (long long *)nullptr, rprobe, cpa));
     F8_CUDA(cudaGetLastError());
@@ -802,14 +803,14 @@ int launch_t(const UGeom &g, const f8::Epilogue &ep, cudaStream_t s) {
         const int rc = f8host::encode_tmap_u8_4d(&tmap, g.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc != F8_OK) return rc;
     }
-    static bool attr_done = false;
-    static int num_sms = 0;
-    if (!attr_done) {
-        F8_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        int dev = 0;
-        F8_CUDA(cudaGetDevice(&dev));
-        F8_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_done = true;
+    static f8host::DeviceOnce once;
+    int num_sms = 0;
+    {
+        const int rc = f8host::device_once(once, &num_sms, [&]() -> int {
+            F8_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+            return F8_OK;
+        });
+        if (rc) return rc;
     }
     const int mtiles = (g.M + BM - 1) / BM;
     const int ntn = (ep.cout_pad + BN - 1) / BN;
@@ -818,6 +819,7 @@ int launch_t(const UGeom &g, const f8::Epilogue &ep, cudaStream_t s) {
     const int per_sm = (BN <= 128) ? 2 : 1;
     long long grid = (long long)num_sms * per_sm;
     if (grid > total) grid = total;
+    f8host::note_kernel("conv_umma<BN=%d,%s,k%ds%d>", BN, SMALL_C ? "small_c" : (TMA_A ? "tma_a" : "gather"), g.kh, g.stride);
     F8_CUDA(f8host::launch_pdl(kern, (unsigned)grid, threads_for(BN, TMA_A), smem_bytes, s, g, ep, mtiles, ntn, tmap));
     F8_CUDA(cudaGetLastError());
     return F8_OK;

@@ -225,6 +225,7 @@ int launch_dw3x3(const f8_conv_args &a, cudaStream_t s) {
     blocks = (blocks + mult - 1) / mult * mult;
     const long long stride_items = blocks * THREADS;
     const bool sgn = a.in_signed != 0;
+    note_kernel("dw3x3<s%d>", a.stride);
     if (a.stride == 1) {
         if (sgn) F8_CUDA(f8host::launch_pdl(dw3x3_kernel<true, 1>, (unsigned)blocks, THREADS, 0, s, g, ep, total, stride_items));
         else F8_CUDA(f8host::launch_pdl(dw3x3_kernel<false, 1>, (unsigned)blocks, THREADS, 0, s, g, ep, total, stride_items));

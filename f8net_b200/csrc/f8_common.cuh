@@ -9,6 +9,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "../../include/f8b200.h"
 
 namespace f8 {
@@ -315,6 +317,10 @@ __device__ __forceinline__ void pdl_trigger() {
 namespace f8host {
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
+// every launcher names the kernel template it is about to launch (thread local, printf style);
+// f8_plan_profile keeps the name per op (f8_plan_kernel_name) so that measurements can be
+// attributed to kernel templates instead of op kinds
+void note_kernel(const char *fmt, ...);
 }  // namespace f8host
 
 #define F8_CUDA(call)                                                     \
@@ -323,8 +329,48 @@ int cuda_fail(cudaError_t e, const char *what);
         if (_e != cudaSuccess) return f8host::cuda_fail(_e, #call);       \
     } while (0)
 
+// Debug instrumentation (in-kernel wait counters F8_STATS, timing probes F8_PROBE / F8_RPROBE that
+// skip work and therefore give WRONG results) exists only in a -DF8_DEBUG_PROBES build
+// (F8_DEBUG_PROBES=1 python -m f8net_b200.build --force).  In the shipping library the switches
+// are not read at all and every probe branch is compiled out.
+#ifdef F8_DEBUG_PROBES
+#define F8_DBG 1
+#else
+#define F8_DBG 0
+#endif
+
 // kernel launchers implemented in the .cu files, called by plan.cu
 namespace f8host {
+inline const char *debug_env(const char *name) { return F8_DBG ? getenv(name) : nullptr; }
+
+// One-time setup of a kernel family PER DEVICE: cudaFuncSetAttribute (the > 48 KB dynamic shared
+// memory opt-in) applies to the current device only, and so does the SM count a persistent grid is
+// sized with -- a process may hold plans on several GPUs and launch from several host threads.
+struct DeviceOnce {
+    static constexpr int kMaxDevices = 64;
+    std::mutex m;
+    bool done[kMaxDevices] = {};
+    int sms[kMaxDevices] = {};
+};
+template <typename Setup>
+inline int device_once(DeviceOnce &st, int *num_sms, Setup &&setup) {
+    int dev = 0;
+    F8_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= DeviceOnce::kMaxDevices) {
+        set_error("device index %d outside the supported range", dev);
+        return F8_ERR_UNSUPPORTED;
+    }
+    std::lock_guard<std::mutex> lk(st.m);
+    if (!st.done[dev]) {
+        const int rc = setup();
+        if (rc) return rc;
+        F8_CUDA(cudaDeviceGetAttribute(&st.sms[dev], cudaDevAttrMultiProcessorCount, dev));
+        st.done[dev] = true;
+    }
+    *num_sms = st.sms[dev];
+    return F8_OK;
+}
+
 // F8_PDL=0 turns programmatic dependent launch off (plain stream order between layers)
 inline bool pdl_enabled() {
     static const bool on = [] { const char *e = getenv("F8_PDL"); return !(e && e[0] == '0'); }();

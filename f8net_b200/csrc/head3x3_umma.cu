@@ -258,17 +258,18 @@ int launch_head3x3s2(const f8_conv_args &a, cudaStream_t s) {
     size_t smem = (size_t)SA * g.stage_slots * 16 + B_BYTES + (2 * SA + 4) * 8 + 16 + COUT_PAD * 4 + 128;
     if (smem > 200 * 1024) return F8_ERR_UNSUPPORTED;
     if (smem < 120 * 1024) smem = 120 * 1024;                          // one CTA per SM (register budget)
-    static bool attr_done = false;
-    static int num_sms = 0;
-    if (!attr_done) {
-        F8_CUDA(cudaFuncSetAttribute(head3x3s2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        F8_CUDA(cudaFuncSetAttribute(head3x3s2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        int dev = 0;
-        F8_CUDA(cudaGetDevice(&dev));
-        F8_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_done = true;
+    static DeviceOnce once;
+    int num_sms = 0;
+    {
+        const int rc = device_once(once, &num_sms, []() -> int {
+            F8_CUDA(cudaFuncSetAttribute(head3x3s2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            F8_CUDA(cudaFuncSetAttribute(head3x3s2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            return F8_OK;
+        });
+        if (rc) return rc;
     }
     const unsigned grid = (unsigned)(g.ntiles < num_sms ? g.ntiles : num_sms);
+    note_kernel("head3x3s2");
     if (a.in_signed) F8_CUDA(launch_pdl(head3x3s2_kernel<true>, grid, (unsigned)THREADS, smem, s, g, ep));
     else F8_CUDA(launch_pdl(head3x3s2_kernel<false>, grid, (unsigned)THREADS, smem, s, g, ep));
     F8_CUDA(cudaGetLastError());

@@ -40,10 +40,6 @@
 
 #include "tma_common.cuh"
 
-namespace f8host {
-int launch_head_pool_v1(const f8_conv_args &a, cudaStream_t s);
-}
-
 namespace {
 
 using namespace f8u;
@@ -86,7 +82,7 @@ constexpr int SMEM_BYTES = OFF_MISC + 32 + COUT * 4 + 128;         // + base ali
 
 #define H2_TIMED(acc, stmt)                      \
     do {                                         \
-        if (g.stats) {                           \
+        if (F8_DBG && g.stats) {                 \
             const long long _t0 = clock64();     \
             stmt;                                \
             acc += clock64() - _t0;              \
@@ -220,7 +216,7 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
             if (lane == 0) mbar_arrive(stageb_full(slot));     // one arrival per shifter warp
             if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
         }
-        if (g.stats && tid == SHIFT_WARP0 * 32) {
+        if (F8_DBG && g.stats && tid == SHIFT_WARP0 * 32) {
             g.stats[blockIdx.x * 16 + 6] = clock64() - t_begin;
             g.stats[blockIdx.x * 16 + 7] = w_sa;
         }
@@ -276,7 +272,7 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
             }
             if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
         }
-        if (g.stats && lane == 0) {
+        if (F8_DBG && g.stats && lane == 0) {
             g.stats[blockIdx.x * 16 + 0] = clock64() - t_begin;
             g.stats[blockIdx.x * 16 + 1] = w_stage;
             g.stats[blockIdx.x * 16 + 2] = w_stageb;
@@ -374,7 +370,7 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
                 if (ep.out1) *reinterpret_cast<uint4 *>(ep.out1 + o) = f8::requant_pack16(r, ep.shift1, ep.signed1);
             }
         }
-        if (g.stats && tid == 0) {
+        if (F8_DBG && g.stats && tid == 0) {
             g.stats[blockIdx.x * 16 + 4] = clock64() - t_begin;
             g.stats[blockIdx.x * 16 + 5] = w_full;
         }
@@ -395,8 +391,6 @@ namespace f8host {
 // a = the head convolution's arguments with hout/wout = the POOLED size (56) and the epilogue
 // of the pooled tensor.  F8_ERR_UNSUPPORTED => the caller runs conv + maxpool separately.
 int launch_head_pool(const f8_conv_args &a, cudaStream_t s) {
-    static const bool force_v1 = getenv("F8_HEAD_V1") != nullptr;
-    if (force_v1) return launch_head_pool_v1(a, s);
     if (a.kh != 7 || a.kw != 7 || a.stride != 2 || a.pad != 3 || a.cin_pad != 4 || a.cout != COUT ||
         a.cout_pad != COUT || a.hin != IMG || a.win != IMG || a.hout != POOLED || a.wout != POOLED ||
         a.carry_in != nullptr || a.out_f32 != nullptr)
@@ -416,15 +410,15 @@ int launch_head_pool(const f8_conv_args &a, cudaStream_t s) {
     ep.shift1 = a.out_shift[1]; ep.signed1 = a.out_signed[1];
     ep.cout = a.cout;
     ep.cout_pad = a.cout_pad;
-    static bool attr_done = false;
-    static int num_sms = 0;
-    if (!attr_done) {
-        F8_CUDA(cudaFuncSetAttribute(head_pool2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        F8_CUDA(cudaFuncSetAttribute(head_pool2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        int dev = 0;
-        F8_CUDA(cudaGetDevice(&dev));
-        F8_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_done = true;
+    static DeviceOnce once;
+    int num_sms = 0;
+    {
+        const int rc = device_once(once, &num_sms, []() -> int {
+            F8_CUDA(cudaFuncSetAttribute(head_pool2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            F8_CUDA(cudaFuncSetAttribute(head_pool2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            return F8_OK;
+        });
+        if (rc) return rc;
     }
     // the image as one uint32 per pixel, rows split i = 4 J + k: (x, k, J, n); a box is six rows
     // J of one plane k, 232 pixels wide from x = -4 (copy A) or x = -6 (copy B)
@@ -436,13 +430,14 @@ int launch_head_pool(const f8_conv_args &a, cudaStream_t s) {
     if (rc != F8_OK) return rc;
     long long grid = (long long)a.n * TILES_IMG;
     if (grid > num_sms) grid = num_sms;
-    static const bool want_stats = getenv("F8_STATS") != nullptr;
+    static const bool want_stats = debug_env("F8_STATS") != nullptr;
     static long long *stats_dev = nullptr;
     if (want_stats) {
         if (!stats_dev) F8_CUDA(cudaMalloc(&stats_dev, 16 * 1024 * sizeof(long long)));
         F8_CUDA(cudaMemsetAsync(stats_dev, 0, 16 * 1024 * sizeof(long long), s));
         g.stats = stats_dev;
     }
+    note_kernel("head_pool2");
     if (a.in_signed) F8_CUDA(f8host::launch_pdl(head_pool2_kernel<true>, (unsigned)grid, THREADS, SMEM_BYTES, s, g, ep, tmap));
     else F8_CUDA(f8host::launch_pdl(head_pool2_kernel<false>, (unsigned)grid, THREADS, SMEM_BYTES, s, g, ep, tmap));
     F8_CUDA(cudaGetLastError());

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <string>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -32,6 +33,14 @@ void set_error(const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static thread_local char g_kernel[96] = "";
+void note_kernel(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_kernel, sizeof(g_kernel), fmt, ap);
     va_end(ap);
 }
 
@@ -121,6 +130,7 @@ struct f8_plan {
     uint8_t *host_stage = nullptr;
     size_t host_stage_bytes = 0;
     cudaEvent_t host_stage_free = nullptr;   // recorded after the H2D copy that reads the staging
+    std::vector<std::string> kernel_names;   // per op: the kernel template of the last f8_plan_profile
 };
 
 // ---------------------------------------------------------------------------------------
@@ -493,6 +503,7 @@ extern "C" int f8_plan_profile(f8_plan *plan, const void *x_dev, int x_layout, i
         return F8_ERR_ARG;
     }
     std::vector<cudaEvent_t> ev;
+    plan->kernel_names.assign(plan->ops.size(), std::string());
     int rc = plan_run_impl(plan, x_dev, x_layout, n, logits_dev, workspace_dev, workspace_bytes,
                            chunk, stream, &ev);
     cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
@@ -551,10 +562,14 @@ static int plan_run_impl(f8_plan *plan, const void *x_dev, int x_layout, int n,
                 events->push_back(b);
                 F8_CUDA(cudaEventRecord(a, s));
             }
+            if (events) f8host::g_kernel[0] = 0;
             int rc = run_op(plan, po, nn, x, x_layout, lg, static_cast<uint8_t *>(workspace_dev),
                             chunk, s);
             if (rc) return rc;
-            if (events) F8_CUDA(cudaEventRecord(events->back(), s));
+            if (events) {
+                F8_CUDA(cudaEventRecord(events->back(), s));
+                plan->kernel_names[&po - plan->ops.data()] = f8host::g_kernel;
+            }
         }
     }
     return F8_OK;
@@ -792,6 +807,16 @@ extern "C" int f8_requant_i32(const int32_t *x, int32_t *y, size_t count, int fl
     if (rc) return rc;
     if (!count) return F8_OK;
     return f8host::launch_requant_i32(x, y, count, shift, is_signed, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int f8_plan_kernel_name(const f8_plan *plan, int op_index, char *dst, int cap) {
+    if (!plan || !dst || cap <= 0 || op_index < 0 || op_index >= (int)plan->ops.size()) {
+        set_error("plan_kernel_name: bad arguments");
+        return F8_ERR_ARG;
+    }
+    const std::string name = op_index < (int)plan->kernel_names.size() ? plan->kernel_names[op_index] : std::string();
+    snprintf(dst, (size_t)cap, "%s", name.c_str());
+    return F8_OK;
 }
 
 extern "C" const char *f8_last_error(void) { return f8host::g_err; }

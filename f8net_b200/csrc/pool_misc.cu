@@ -302,6 +302,7 @@ int launch_maxpool(const f8_conv_args &a, cudaStream_t s) {
         return F8_ERR_UNSUPPORTED;
     }
     const long long total = (long long)a.n * a.hout * a.wout * (a.cin_pad >> 2);
+    note_kernel("maxpool");
     maxpool_kernel<<<grid_for(total), THREADS, 0, s>>>(static_cast<const int32_t *>(a.in), a.n,
                                                        a.hin, a.win, a.hout, a.wout, a.cin_pad,
                                                        make_ep(a));
@@ -311,6 +312,7 @@ int launch_maxpool(const f8_conv_args &a, cudaStream_t s) {
 
 int launch_pool_requant(const f8_conv_args &a, cudaStream_t s) {
     const long long total = (long long)a.n * (a.cin_pad >> 2);
+    note_kernel("pool_requant");
     pool_requant_kernel<<<grid_for(total), THREADS, 0, s>>>(static_cast<const int32_t *>(a.in),
                                                             a.n, a.hin * a.win, a.cin_pad,
                                                             make_ep(a));
@@ -331,6 +333,7 @@ int launch_pool_fc(const f8_conv_args &a, cudaStream_t s) {
     auto kern = imgs == 4 ? (a.out_signed[0] ? pool_fc_kernel<true, 4> : pool_fc_kernel<false, 4>)
                           : (a.out_signed[0] ? pool_fc_kernel<true, 2> : pool_fc_kernel<false, 2>);
     if (smem > 48 * 1024) F8_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    note_kernel("pool_fc");
     F8_CUDA(launch_pdl(kern, grid, TAIL_THREADS, smem, s, static_cast<const int32_t *>(a.in), a.n, a.hin * a.win,
                        a.cin_pad, static_cast<const uint4 *>(a.wpack), pk.rows, a.bias, a.cout, a.out_shift[0],
                        a.out_f32, a.out_f32_ld));
@@ -340,6 +343,7 @@ int launch_pool_fc(const f8_conv_args &a, cudaStream_t s) {
 
 int launch_convert_input(const int32_t *x, void *out, int n, int h, int w, int, cudaStream_t s) {
     const long long total = (long long)n * h * w;
+    note_kernel("convert_input");
     F8_CUDA(launch_pdl(convert_input_kernel, grid_for(total), THREADS, 0, s, x, static_cast<uint32_t *>(out), n, h * w));
     F8_CUDA(cudaGetLastError());
     return F8_OK;
@@ -349,6 +353,7 @@ int launch_integerize_f32(const float *x, void *out, int n, int h, int w, int no
                           cudaStream_t s) {
     const long long total = (long long)n * h * w;
     const float scale = normalize ? ldexpf(1.0f, fraclen) : 255.0f;
+    note_kernel("integerize_f32");
     integerize_f32_kernel<<<grid_for(total), THREADS, 0, s>>>(x, static_cast<uint32_t *>(out), n, h * w,
                                                               normalize, scale);
     F8_CUDA(cudaGetLastError());
@@ -358,6 +363,7 @@ int launch_integerize_f32(const float *x, void *out, int n, int h, int w, int no
 int launch_integerize_u8(const uint8_t *x, const uint8_t *lut_dev, void *out, int n, int h, int w,
                          cudaStream_t s) {
     const long long total = (long long)n * h * w;
+    note_kernel("integerize_u8");
     integerize_u8_kernel<<<grid_for((total + 3) / 4), THREADS, 0, s>>>(x, lut_dev, static_cast<uint32_t *>(out),
                                                                         total);
     F8_CUDA(cudaGetLastError());

@@ -226,6 +226,15 @@ class Engine:
                                          ms, nops))
         return [(op.name, op.kind, float(ms[i])) for i, op in enumerate(self.plan.ops)]
 
+    def kernel_names(self):
+        """Kernel template that served each op in the most recent ``profile`` call."""
+        out = []
+        buf = ctypes.create_string_buffer(96)
+        for i in range(len(self.plan.ops)):
+            C.check(self.lib.f8_plan_kernel_name(self._h, i, buf, 96))
+            out.append(buf.value.decode())
+        return out
+
     def topk(self, logits, ks=(1, 5)):
         """forward_loss's prediction step (fix_train.py:698-703): indices of the max(ks) largest
         logits per image, on the logits' device."""

@@ -189,6 +189,11 @@ F8_API int f8_plan_profile(f8_plan *plan, const void *x_dev, int x_layout, int n
                     void *workspace_dev, size_t workspace_bytes, int chunk, void *stream,
                     float *op_ms, int n_ops);
 
+/* Name of the kernel template that served op `op_index` in the most recent f8_plan_profile of this
+ * plan ("" when that op launched nothing, e.g. CONVERT_INPUT with an engine-native input): lets a
+ * measurement be attributed per kernel template rather than per op kind. */
+F8_API int f8_plan_kernel_name(const f8_plan *plan, int op_index, char *dst, int cap);
+
 /* Number of kernel launches one f8_plan_run(x_layout, n, chunk) enqueues. */
 F8_API int f8_plan_launch_count(const f8_plan *plan, int x_layout, int n, int chunk);
 /* Which dense-conv backend the plan uses: 0 = mma.sync (legacy IMMA); 1 = tcgen05 (resident-
