@@ -7,7 +7,8 @@
 A "step" is one pass of the hot path over one batch of synthetic images (per GPU).  At N=1
 the workload is BASELINE.json configs[1]: ResNet18 int_op_only, batch 256, 224x224 synthetic
 on 1xB200.  N>1 (torchrun, one rank per GPU): each rank runs its own 256-image shard (weak
-scaling, no data-path collective) and the logits are all-gathered once per step (NCCL).
+scaling, no data-path collective) and the logits are all-gathered once per step (NCCL); the
+gather of step i overlaps the forward pass of step i+1 (two gather buffers).
 
 One JSON line on stdout (rank 0).  ``value``: inputs resident in HBM as the engine-native
 NHWC u8 tensor, rotating over several distinct batches so that every step's input comes from
@@ -15,9 +16,16 @@ HBM, not L2.  ``e2e``: the same metric through the reference-facing call with HO
 pinned int32 NCHW input (the reference's tensor), host-side narrowing to the engine's 8-bit
 layout, H2D copy, run, D2H copy of the logits, all inside the timed region (two engines on two
 streams overlap copy and compute).
-``roofline``: the dominant kernel family (dense conv implicit GEMM), algorithmic bytes of its
-launches / their device time measured with CUDA events around every launch.  ``cpu_baseline``:
-the CPU oracle port (oracle/) on the host cores, a bounded sample of the same workload.
+``roofline``: the dominant kernel TEMPLATE (``top_kernels`` lists the three largest), algorithmic
+bytes of its launches / their device time measured with CUDA events around every launch.
+``configs``: the other BASELINE.json networks at the same per-GPU batch (MobileNet V2, ResNet50,
+MobileNet V1; 256 per GPU, i.e. 2048 over 8 GPUs), each timed the same way.
+``parity``: before anything is timed, a seeded check batch of N x 256 images runs (a) sharded +
+all-gathered and (b) whole on every rank; the gathered logits must equal every rank's own
+single-GPU result bit for bit, and the first two images are the committed golden fixture whose
+logits the unmodified reference produced (tests/golden/<arch>_n2.npz).
+``cpu_baseline``: the CPU oracle port (oracle/) on the host cores, a bounded sample of the same
+workload.
 """
 import argparse
 import json
@@ -32,6 +40,11 @@ sys.path.insert(0, ROOT)
 
 METRIC = "images/sec (int_op_only, bit-exact)"
 UNIT = "images/s"
+NAMES = {"resnet18": "ResNet18", "resnet50": "ResNet50", "mobilenet_v1": "MobileNet V1",
+         "mobilenet_v2": "MobileNet V2"}
+OTHER_CONFIGS = ["mobilenet_v2", "resnet50", "mobilenet_v1"]      # BASELINE.json configs[2..4]
+IMAGE = 224
+L2_BYTES = 126_000_000
 
 
 def parse():
@@ -46,19 +59,27 @@ def parse():
     ap.add_argument("--backend", type=int, default=-1, help="-1 auto, 0 mma.sync, 1 tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE networks")
+    ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
-def config_for(args, extra=None):
-    names = {"resnet18": "ResNet18", "resnet50": "ResNet50", "mobilenet_v1": "MobileNet V1",
-             "mobilenet_v2": "MobileNet V2"}
-    cfg = {"workload": f"{names.get(args.arch, args.arch)} int_op_only, batch={args.batch}/GPU, "
-                       f"224x224 synthetic (weights seed 1234, inputs seed 1995)",
-           "arch": args.arch, "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus,
-           "parallelism": f"batch-sharded x{args.gpus}, one all-gather of logits"}
-    if extra:
-        cfg.update(extra)
-    return cfg
+def rotation(batch):
+    """How many distinct resident input batches rotate so that each step reads its input from HBM."""
+    in_bytes = batch * IMAGE * IMAGE * 4
+    r = max(2, -(-160_000_000 // in_bytes))
+    return r + (r & 1), in_bytes
+
+
+def config_for(arch, batch, gpus):
+    """The workload, identical for both arms (``--impl reference`` prints the same dict)."""
+    r, in_bytes = rotation(batch)
+    return {"workload": f"{NAMES.get(arch, arch)} int_op_only, batch={batch}/GPU, "
+                        f"224x224 synthetic (weights seed 1234, inputs seed 1995)",
+            "arch": arch, "batch_per_gpu": batch, "global_batch": batch * gpus,
+            "parallelism": f"batch-sharded x{gpus}, one all-gather of logits",
+            "l2": f"inputs larger than L2: {r} distinct input batches "
+                  f"({r * in_bytes / 1e6:.0f} MB > {L2_BYTES / 1e6:.0f} MB L2) rotated per step"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -66,7 +87,6 @@ def config_for(args, extra=None):
 # infrastructure; bench.py may execute it only here, as the baseline being reported)
 # ------------------------------------------------------------------------------------------
 def cpu_forward_timer(arch):
-    import numpy as np
     from f8net_b200 import synth
     from oracle import nets, oracle as O
     hs = synth.HEAD_SIGNED.get(arch, False)
@@ -82,6 +102,11 @@ def cpu_forward_timer(arch):
     return run, O.max_threads()
 
 
+PORT_NOTE = ("C port of the reference's CPU path (the reference is Python on ATen int32 kernels and "
+             "cannot travel to the GPU box); the port is faster than ATen's int32 convolution "
+             "(SURVEY.md: 12.9 img/s at batch 32 on 8 vCPU), so GPU/CPU ratios are conservative")
+
+
 def cpu_baseline(arch, budget_s=15.0):
     run, threads = cpu_forward_timer(arch)
     run(1)                                   # warm-up (library load, page-in)
@@ -91,7 +116,7 @@ def cpu_baseline(arch, budget_s=15.0):
     return {"value": n / best, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{n} images of the same workload through the C oracle port "
                       f"(oracle/f8_oracle.c + oracle/nets.py), OpenMP over {threads} threads, "
-                      f"best of 2"}
+                      f"best of 2", "note": PORT_NOTE}
 
 
 def reference_arm(args):
@@ -115,14 +140,14 @@ def reference_arm(args):
         run(n, seed=200 + i)
     dt = time.perf_counter() - t0
     v = n * args.steps / dt
-    sample = (f"{n} images per step (bounded sample of the {args.batch}-image batch), C oracle "
+    sample = (f"sampled: {n} images per step (bounded sample of the {args.batch}-image batch), C oracle "
               f"port of the reference CPU path, {threads} OpenMP threads")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-            "data": "synthetic", "config": config_for(args, {"sample_images_per_step": n}),
+            "data": "synthetic", "config": config_for(args.arch, args.batch, args.gpus),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": sample},
+                             "sample": sample, "note": PORT_NOTE},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -184,16 +209,306 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
-def gpu_arm(args):
-    import numpy as np
+class ArchRun:
+    """One network on this rank's GPU: engine, resident rotating inputs, CUDA graphs, and (N>1)
+    the overlapped all-gather of the logits."""
+
+    def __init__(self, arch, args, device, rank, world):
+        import numpy as np
+        import torch
+
+        import f8net_b200
+        from f8net_b200 import synth
+        from f8net_b200.roofline import network_work
+        self.torch, self.np = torch, np
+        self.arch, self.args, self.device, self.rank, self.world = arch, args, device, rank, world
+        self.B = B = args.batch
+        self.hs = hs = synth.HEAD_SIGNED.get(arch, False)
+        self.sd = synth.make_state_dict(arch, hs)
+        self.kw = {}
+        if args.chunk:
+            self.kw["chunk"] = args.chunk
+        if args.backend >= 0:
+            self.kw["backend"] = args.backend
+        self.eng = f8net_b200.compile(self.sd, arch=arch, head_signed=hs, device=device, **self.kw)
+        self.ops_img, self.bytes_img, self.wbytes = network_work(self.eng.net)
+        S = self.eng.net.image_size
+        self.R, self.in_bytes = rotation(B)
+        g = torch.Generator(device=device).manual_seed(1995 + rank)
+        self.xs = [self._random_batch(B, g) for _ in range(self.R)]
+        self.classes = self.eng.net.num_classes
+        self.logits = torch.empty((B, self.classes), dtype=torch.float32, device=device)
+        self.og = None
+        if world > 1:
+            from f8net_b200.sharded import OverlappedGather
+            self.og = OverlappedGather(B, self.classes, self.xs[0])
+        self.graphs = None
+        self.S = S
+
+    def _random_batch(self, n, g):
+        torch = self.torch
+        S = IMAGE
+        if self.hs:
+            x = torch.randint(-127, 128, (n, S, S, 4), dtype=torch.int8, device=self.device, generator=g)
+        else:
+            x = torch.randint(0, 256, (n, S, S, 4), dtype=torch.uint8, device=self.device, generator=g)
+        x[..., 3] = 0
+        return x
+
+    # -- parity: gathered logits == every rank's own single-GPU logits; golden fixture -----
+    def parity(self):
+        import torch.distributed as dist
+
+        from f8net_b200 import synth
+        from f8net_b200.sharded import ShardedRunner
+        torch, np = self.torch, self.np
+        B, world, rank = self.B, self.world, self.rank
+        g = torch.Generator(device=self.device).manual_seed(20260)     # same batch on every rank
+        xchk = self._random_batch(world * B, g)
+        gx = synth.make_input(self.arch, 2, self.hs)                   # the golden fixture's two images
+        g4 = np.zeros((2, IMAGE, IMAGE, 4), dtype=np.int8 if self.hs else np.uint8)
+        g4[..., :3] = gx.transpose(0, 2, 3, 1)
+        xchk[:2] = torch.from_numpy(g4).to(self.device)
+        whole = self.eng.run_device(xchk)                              # [world*B, classes] on this GPU alone
+        out = {"check_batch": world * B}
+        if world > 1:
+            runner = ShardedRunner(self.eng.run_device, self.classes)
+            gathered = runner(xchk[rank * B:(rank + 1) * B].contiguous())
+            ok = torch.tensor([int(torch.equal(gathered, whole))], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            out["gathered_logits_exact"] = bool(ok.item())
+            first = gathered[:2]
+        else:
+            first = whole[:2]
+        gold_path = os.path.join(ROOT, "tests", "golden", f"{self.arch}_n2.npz")
+        if os.path.exists(gold_path):
+            gold = np.load(gold_path)["logits"].astype(np.int64)
+            out["golden_logits_exact"] = bool(np.array_equal(first.cpu().numpy().astype(np.int64), gold))
+        torch.cuda.synchronize()
+        del xchk, whole
+        bad = [k for k, v in out.items() if v is False]
+        if bad:
+            raise SystemExit(f"bench.py parity check failed for {self.arch}: {bad} (rank {rank})")
+        return out
+
+    # -- timing of the device-resident path -----------------------------------------------
+    def capture(self):
+        torch = self.torch
+        if self.args.no_graph:
+            return
+        for i in range(2):
+            self.eng.run_device(self.xs[i], out=self.logits)      # warm every kernel before capture
+        torch.cuda.synchronize()
+        self.graphs = []
+        cs = torch.cuda.Stream(self.device)
+        with torch.cuda.stream(cs):
+            for i in range(self.R):
+                gr = torch.cuda.CUDAGraph()
+                out = self.logits if self.og is None else self.og.slot(i)      # R is even: slot(i) == slot(i % R)
+                with torch.cuda.graph(gr, stream=cs):
+                    self.eng.run_device(self.xs[i], out=out, stream=cs)
+                self.graphs.append(gr)
+        torch.cuda.synchronize()
+
+    def do_step(self, i):
+        og = self.og
+        if og is not None:
+            og.ready(i)                       # step i-2's gather has released this buffer
+        if self.graphs is not None:
+            self.graphs[i % self.R].replay()
+        else:
+            self.eng.run_device(self.xs[i % self.R], out=self.logits if og is None else og.slot(i))
+        if og is not None:
+            og.submit(i)                      # async all-gather behind the forward pass just enqueued
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def time_steps(self, steps, warmup, clocks_index=None):
+        import torch.distributed as dist
+        torch = self.torch
+        for i in range(max(warmup, 3)):
+            self.do_step(i)
+        if self.og is not None:
+            self.og.drain()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(clocks_index) if clocks_index is not None else None
+        if sampler:
+            sampler.__enter__()
+        self.barrier()
+        e0.record()
+        for i in range(steps):
+            self.do_step(i)
+        if self.og is not None:
+            self.og.drain()                   # the current stream waits for the last two gathers
+        e1.record()
+        self.barrier()
+        if sampler:
+            sampler.__exit__()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, (sampler.summary() if sampler else None)
+
+    def summary(self, ms, steps, hbm_peak):
+        from f8net_b200 import _capi as C
+        per = ms / steps / 1e3
+        alg = (self.bytes_img * self.B + self.wbytes) / per / 1e9        # per GPU
+        return {"value": self.world * self.B * steps / (ms / 1e3), "ms_per_step": ms / steps,
+                "steps": steps,
+                "whole_net": {"algorithmic_gbs_per_gpu": alg, "frac_of_hbm_peak": alg / hbm_peak,
+                              "int8_tops_per_gpu": self.ops_img * self.B / per / 1e12,
+                              "algorithmic_mb_per_image": self.bytes_img / 1e6},
+                "gpu_launches_per_step": self.eng.launches(self.B, C.F8_IN_NHWC4_8)}
+
+    def close(self):
+        self.graphs = None
+        self.xs = None
+        self.eng.close()
+        self.torch.cuda.empty_cache()
+
+
+def e2e_measure(run, args, device, barrier, world):
+    """The reference-facing call with host buffers inside the timed region."""
     import torch
     import torch.distributed as dist
 
     import f8net_b200
+    B, S = args.batch, IMAGE
+    eng = run.eng
+    engines = [eng, f8net_b200.compile(run.sd, arch=run.arch, head_signed=run.hs, device=device, **run.kw)]
+    streams = [torch.cuda.Stream(device), torch.cuda.Stream(device)]
+    lo, hi = (-127, 128) if run.hs else (0, 256)
+    hy = [torch.empty((B, run.classes), dtype=torch.float32).pin_memory() for _ in range(2)]
+
+    def timed(bufs):
+        def steps(k):
+            for i in range(k):
+                j = i % 2
+                streams[j].synchronize()      # the previous use of this slot's host buffers is done
+                engines[j].run_host(bufs[j], out=hy[j], sync=False, stream=streams[j])
+            for s in streams:
+                s.synchronize()
+        steps(3)
+        barrier()
+        t0 = time.perf_counter()
+        steps(args.steps)
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return world * B * args.steps / dt
+
+    hx = [torch.randint(lo, hi, (B, 3, S, S), dtype=torch.int32).pin_memory() for _ in range(2)]
+    v = timed(hx)
+    del hx
+    # run_host repacks the int32 tensor to NHWC4 bytes with the host cores (inside the timed region)
+    # and ships those; F8_HOST_PACK_THREADS=0 ships the int32 tensor itself
+    host_pack = os.environ.get("F8_HOST_PACK_THREADS", "") != "0"
+    e2e = {"value": v, "unit": UNIT,
+           "h2d_bytes_per_step": B * S * S * 4 if host_pack else B * 3 * S * S * 4,
+           "host_tensor_bytes_per_step": B * 3 * S * S * 4,
+           "d2h_bytes_per_step": B * run.classes * 4,
+           "input": "pinned int32 NCHW (the reference's tensor), two engines on two streams"
+                    + ("; run_host narrows it to NHWC4 bytes on the host cores (timed) before the copy" if host_pack else ""),
+           "host_bound": "the int32 tensor is 602 KB per image of host-DRAM reads; the narrowing is "
+                         "bound by host memory bandwidth, not by the GPU",
+           "timer": "host perf_counter around the loop, stream syncs inside"}
+    # the same call fed with decoded uint8 pixels [B,H,W,3] (SURVEY.md 8(f) rank 1): ToTensor +
+    # Normalize + forward_loss's integerisation run on the device, 4x fewer PCIe bytes
+    hp = [torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    v8 = timed(hp)
+    e2e_u8 = {"value": v8, "unit": UNIT,
+              "h2d_bytes_per_step": B * 3 * S * S, "d2h_bytes_per_step": B * run.classes * 4,
+              "input": "pinned uint8 [B,H,W,3] decoded pixels; ToTensor + Normalize + integerisation "
+                       "(fix_train.py:299-318, :676-692) on the device"}
+    engines[1].close()
+    return e2e, e2e_u8
+
+
+def roofline_for(run, args, hbm_peak, peak_src, ms_step, int8_peak):
+    """Per kernel template: algorithmic bytes / device time of its launches (live CUDA events)."""
+    from f8net_b200.roofline import op_work
+    eng, B = run.eng, run.B
+    work = op_work(eng.plan)
+    acc = [0.0] * len(work)
+    reps = min(args.steps, 10)
+    for i in range(reps):
+        for j, (_, _, t_ms) in enumerate(eng.profile(run.xs[i % run.R])):
+            acc[j] += t_ms / reps
+    names = eng.kernel_names()
+    tmpl = {}
+    for w, t_ms, name in zip(work, acc, names):
+        if not name:
+            continue
+        f = tmpl.setdefault(name, {"ms": 0.0, "bytes": 0.0, "ops": 0.0, "launches": 0})
+        f["ms"] += t_ms
+        f["bytes"] += w["bytes_per_image"] * B + w["weight_bytes"]
+        f["ops"] += w["ops"] * B
+        f["launches"] += 1
+    total_ms = sum(acc)
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(run.arch, {})
+        if traffic.get("batch") != B:
+            traffic = {}
+    except (OSError, ValueError):
+        pass
+
+    def entry(name):
+        d = tmpl[name]
+        ach = d["bytes"] / (d["ms"] / 1e3) / 1e9 if d["ms"] > 0 else 0.0
+        tops = d["ops"] / (d["ms"] / 1e3) / 1e12 if d["ms"] > 0 else 0.0
+        tr = traffic.get(name, {}).get("dram_bytes_per_launch")
+        return {"kernel": name, "launches_per_step": d["launches"],
+                "achieved": ach, "frac": ach / hbm_peak,
+                "algorithmic_bytes_per_launch": d["bytes"] / d["launches"],
+                "avg_launch_ms": d["ms"] / d["launches"],
+                "share_of_step": d["ms"] / total_ms if total_ms else None,
+                "int8_tops_achieved": tops,
+                "int8_frac": tops / int8_peak["tops"] if int8_peak else None,
+                "traffic": tr}
+
+    order = sorted(tmpl, key=lambda k: -tmpl[k]["ms"])
+    top = [entry(k) for k in order[:3]]
+    dom = top[0]
+    roofline = {
+        "bound": "hbm", "achieved": dom["achieved"], "peak": hbm_peak, "unit": "GB/s",
+        "frac": dom["frac"], "traffic": dom["traffic"],
+        "kernel": dom["kernel"], "launches_per_step": dom["launches_per_step"],
+        "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+        "avg_launch_ms": dom["avg_launch_ms"], "share_of_step": dom["share_of_step"],
+        "peak_source": peak_src,
+        "int8_tops_achieved": dom["int8_tops_achieved"],
+        "int8_peak_tops": int8_peak["tops"] if int8_peak else None,
+        "int8_peak_source": int8_peak["shape"] if int8_peak else None,
+        "int8_frac": dom["int8_frac"],
+        "method": f"CUDA event pair around every launch on the launch stream (f8_plan_profile), mean of "
+                  f"{reps} steps, batch {B}, launches grouped by kernel template (f8_plan_kernel_name); the "
+                  f"sum of event-bracketed launches is {total_ms:.3f} ms against {ms_step:.3f} ms for the "
+                  f"graph-replayed step, so per-launch fractions are understated by up to "
+                  f"{100 * max(0.0, total_ms / ms_step - 1):.0f} %",
+        "traffic_source": traffic.get("source"),
+        "top_kernels": top,
+        "per_kernel_ms": {k: round(tmpl[k]["ms"], 4) for k in order},
+    }
+    return roofline
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
     from f8net_b200 import _capi as C
-    from f8net_b200 import synth
-    from f8net_b200.roofline import network_work, op_work
-    from f8net_b200.sharded import ShardedRunner
+    from f8net_b200.peaks import measure_int8_peak
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -208,230 +523,78 @@ def gpu_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
 
-    arch, B = args.arch, args.batch
-    hs = synth.HEAD_SIGNED.get(arch, False)
-    sd = synth.make_state_dict(arch, hs)
-    kw = {}
-    if args.chunk:
-        kw["chunk"] = args.chunk
-    if args.backend >= 0:
-        kw["backend"] = args.backend
-    eng = f8net_b200.compile(sd, arch=arch, head_signed=hs, device=device, **kw)
-    ops_img, bytes_img, wbytes = network_work(eng.net)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s"
 
-    # R distinct resident input batches (engine-native NHWC u8/s8), more than L2 (126 MB)
-    S = eng.net.image_size
-    in_bytes = B * S * S * 4
-    R = max(2, -(-160_000_000 // in_bytes))
-    g = torch.Generator(device=device).manual_seed(1995 + rank)
-    if hs:
-        xs = [torch.randint(-127, 128, (B, S, S, 4), dtype=torch.int8, device=device, generator=g)
-              for _ in range(R)]
-    else:
-        xs = [torch.randint(0, 256, (B, S, S, 4), dtype=torch.uint8, device=device, generator=g)
-              for _ in range(R)]
-    for x in xs:
-        x[..., 3] = 0
-    runner = ShardedRunner(eng.run_device, eng.net.num_classes) if world > 1 else None
+    # ---- headline network ----
+    run = ArchRun(args.arch, args, device, rank, world)
+    parity = run.parity()
+    run.capture()
+    ms, clocks = run.time_steps(args.steps, args.warmup, clocks_index=local)
+    head = run.summary(ms, args.steps, hbm_peak)
+    launches = head["gpu_launches_per_step"] * args.steps
 
-    def step(i):
-        x = xs[i % R]
-        return runner(x) if runner is not None else eng.run_device(x, out=logits)
+    e2e = e2e_u8 = None
+    if not args.no_e2e:
+        e2e, e2e_u8 = e2e_measure(run, args, device, run.barrier, world)
 
-    logits = torch.empty((B, eng.net.num_classes), dtype=torch.float32, device=device)
-
-    # CUDA graphs of the R step variants (launch-bound inner loop).  N>1: the graph holds this
-    # rank's forward pass, writing into its slice of the gather buffer; the NCCL all-gather of the
-    # logits follows it every step
-    graphs = None
-    full = mine = None
-    if runner is not None:
-        full = runner.gather_buffer(B, xs[0])
-        mine = full[rank]
-    if not args.no_graph:
-        for i in range(min(R, 2)):
-            step(i)                       # warm every kernel (cudaFuncSetAttribute) before capture
-        torch.cuda.synchronize()
-        graphs = []
-        cs = torch.cuda.Stream(device)
-        with torch.cuda.stream(cs):
-            for i in range(R):
-                gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr, stream=cs):
-                    eng.run_device(xs[i], out=logits if mine is None else mine, stream=cs)
-                graphs.append(gr)
-        torch.cuda.synchronize()
-
-    def do_step(i):
-        if graphs is not None:
-            graphs[i % R].replay()
-            if runner is not None:
-                dist.all_gather_into_tensor(full.view(-1), mine.reshape(-1))
-        else:
-            step(i)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(max(args.warmup, 3)):
-        do_step(i)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        barrier()
-        e0.record()
-        for i in range(args.steps):
-            do_step(i)
-        e1.record()
-        barrier()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = world * B * args.steps / (ms / 1e3)
-    launches = eng.launches(B, C.F8_IN_NHWC4_8) * args.steps
-
-    # ---- e2e: reference-facing call, host buffers, copies in the timed region ----
-    engines = [eng, f8net_b200.compile(sd, arch=arch, head_signed=hs, device=device, **kw)]
-    streams = [torch.cuda.Stream(device), torch.cuda.Stream(device)]
-    lo, hi = (-127, 128) if hs else (0, 256)
-    hx = [torch.randint(lo, hi, (B, 3, S, S), dtype=torch.int32).pin_memory() for _ in range(2)]
-    hy = [torch.empty((B, eng.net.num_classes), dtype=torch.float32).pin_memory() for _ in range(2)]
-
-    def e2e_steps(k):
-        for i in range(k):
-            j = i % 2
-            streams[j].synchronize()      # the previous use of this slot's host buffers is done
-            engines[j].run_host(hx[j], out=hy[j], sync=False, stream=streams[j])
-        for s in streams:
-            s.synchronize()
-
-    e2e_steps(3)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps(args.steps)
-    barrier()
-    e2e_dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_dt], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_dt = float(t.item())
-    # run_host repacks the int32 tensor to NHWC4 bytes with the host cores (inside the timed region)
-    # and ships those; F8_HOST_PACK_THREADS=0 ships the int32 tensor itself
-    host_pack = os.environ.get("F8_HOST_PACK_THREADS", "") != "0"
-    e2e = {"value": world * B * args.steps / e2e_dt, "unit": UNIT,
-           "h2d_bytes_per_step": B * S * S * 4 if host_pack else B * 3 * S * S * 4,
-           "host_tensor_bytes_per_step": B * 3 * S * S * 4,
-           "d2h_bytes_per_step": B * eng.net.num_classes * 4,
-           "input": "pinned int32 NCHW (the reference's tensor), two engines on two streams"
-                    + ("; run_host narrows it to NHWC4 bytes on the host cores (timed) before the copy" if host_pack else ""),
-           "timer": "host perf_counter around the loop, stream syncs inside"}
-
-    # ---- the same call fed with decoded uint8 pixels [B,H,W,3]: ToTensor +
-    # Normalize + forward_loss's integerisation run on the device, 4x fewer PCIe bytes ----
-    hp = [torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
-
-    def e2e_u8_steps(k):
-        for i in range(k):
-            j = i % 2
-            streams[j].synchronize()
-            engines[j].run_host(hp[j], out=hy[j], sync=False, stream=streams[j])
-        for s in streams:
-            s.synchronize()
-
-    e2e_u8_steps(3)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_u8_steps(args.steps)
-    barrier()
-    u8_dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([u8_dt], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        u8_dt = float(t.item())
-    e2e_u8 = {"value": world * B * args.steps / u8_dt, "unit": UNIT,
-              "h2d_bytes_per_step": B * 3 * S * S, "d2h_bytes_per_step": B * eng.net.num_classes * 4,
-              "input": "pinned uint8 [B,H,W,3] decoded pixels; ToTensor + Normalize + integerisation "
-                       "(fix_train.py:299-318, :676-692) on the device"}
-
-    line = None
+    roofline = cb = None
     if rank == 0:
-        # ---- roofline of the dominant kernel family: per-launch CUDA events ----
-        peaks = {}
+        int8_peak = None
         try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s"
-        work = op_work(eng.plan)
-        acc = [0.0] * len(work)
-        reps = min(args.steps, 10)
-        for i in range(reps):
-            for j, (_, _, t_ms) in enumerate(eng.profile(xs[i % R])):
-                acc[j] += t_ms / reps
-        fam = {}
-        for w, t_ms in zip(work, acc):
-            f = fam.setdefault(w["kind"], {"ms": 0.0, "bytes": 0.0, "ops": 0.0, "launches": 0})
-            f["ms"] += t_ms
-            f["bytes"] += w["bytes_per_image"] * B + w["weight_bytes"]
-            f["ops"] += w["ops"] * B
-            f["launches"] += 1
-        total_ms = sum(acc)
-        dom_kind = max(fam, key=lambda k: fam[k]["ms"])
-        d = fam[dom_kind]
-        kind_names = {C.F8_OP_CONVERT_INPUT: "convert_input", C.F8_OP_CONV_DENSE: "conv_dense",
-                      C.F8_OP_CONV_DW: "conv_dw3x3", C.F8_OP_MAXPOOL: "maxpool",
-                      C.F8_OP_POOL_REQUANT: "pool_requant", C.F8_OP_HEAD_POOL: "head_conv_pool",
-                      C.F8_OP_POOL_FC: "pool_fc"}
-        achieved = d["bytes"] / (d["ms"] / 1e3) / 1e9 if d["ms"] > 0 else 0.0
-        # DRAM bytes per launch of this kernel family from the committed `ncu --set full` capture
-        traffic = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(arch, {})
-            if tr.get("batch") == B and kind_names[dom_kind] in tr:
-                traffic = tr[kind_names[dom_kind]]["dram_bytes_per_launch"]
-        except (OSError, ValueError):
-            pass
-        roofline = {
-            "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-            "frac": achieved / hbm_peak, "traffic": traffic,
-            "kernel": kind_names[dom_kind], "launches_per_step": d["launches"],
-            "algorithmic_bytes_per_launch": d["bytes"] / d["launches"],
-            "avg_launch_ms": d["ms"] / d["launches"],
-            "share_of_step": d["ms"] / total_ms if total_ms else None,
-            "peak_source": peak_src,
-            "int8_tops_achieved": d["ops"] / (d["ms"] / 1e3) / 1e12 if d["ms"] > 0 else 0.0,
-            "method": f"CUDA event pair around every launch on the launch stream "
-                      f"(f8_plan_profile), mean of {reps} steps, batch {B}",
-            "whole_net": {"algorithmic_gbs": (bytes_img * B + wbytes) * world / (ms / args.steps / 1e3) / 1e9,
-                          "int8_tops": ops_img * B * world / (ms / args.steps / 1e3) / 1e12,
-                          "frac_of_hbm_peak": (bytes_img * B + wbytes) / (ms / args.steps / 1e3) / 1e9 / hbm_peak},
-            "per_kernel_ms": {kind_names[k]: round(v["ms"], 4) for k, v in fam.items()},
-        }
-        cb = None
-        if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_baseline(arch)
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
-            "data": "synthetic",
-            "config": config_for(args, {
-                "chunk": eng.chunk, "backend": "tcgen05" if eng.backend == 1 else "mma.sync",
-                "cuda_graph": graphs is not None,
-                "l2": f"{R} distinct resident input batches ({R * in_bytes / 1e6:.0f} MB > 126 MB L2) rotated per step",
-                "resident_input": "NHWC 8-bit [B,224,224,4]"}),
-            "e2e": e2e, "e2e_uint8_input": e2e_u8, "gpu_launches": launches, "clocks": clocks.summary(),
-            "roofline": roofline, "cpu_baseline": cb,
-        }
+            int8_peak = measure_int8_peak(device)
+        except C.F8Error as e:                       # e.g. mma.sync-only device
+            int8_peak = None
+            print(f"int8 peak measurement unavailable: {e}", file=sys.stderr)
+        roofline = roofline_for(run, args, hbm_peak, peak_src, ms / args.steps, int8_peak)
+        roofline["whole_net"] = dict(head["whole_net"], int8_frac=(
+            head["whole_net"]["int8_tops_per_gpu"] / int8_peak["tops"] if int8_peak else None))
+    engine_info = {"chunk": run.eng.chunk, "backend": "tcgen05" if run.eng.backend == 1 else "mma.sync",
+                   "cuda_graph": run.graphs is not None, "resident_input": "NHWC 8-bit [B,224,224,4]",
+                   "gather": "async all-gather of step i overlaps the forward pass of step i+1" if world > 1 else None}
+    run.close()
+    if world > 1:
+        dist.barrier()
+
+    # ---- the other BASELINE.json networks at the same per-GPU batch ----
+    configs = []
+    if not args.no_configs:
+        steps2 = max(5, min(args.steps, 50))
+        for arch in OTHER_CONFIGS:
+            if arch == args.arch:
+                continue
+            r2 = ArchRun(arch, args, device, rank, world)
+            p2 = r2.parity()
+            r2.capture()
+            ms2, _ = r2.time_steps(steps2, min(args.warmup, 5))
+            s2 = r2.summary(ms2, steps2, hbm_peak)
+            configs.append(dict(config=config_for(arch, args.batch, world), parity=p2, **s2))
+            launches += s2["gpu_launches_per_step"] * steps2
+            r2.close()
+            if world > 1:
+                dist.barrier()
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_baseline(args.arch)
+
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    if line is not None:
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
+            "data": "synthetic", "config": config_for(args.arch, args.batch, world),
+            "engine": engine_info, "parity": parity,
+            "e2e": e2e, "e2e_uint8_input": e2e_u8, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "configs": configs, "cpu_baseline": cb,
+        }
         print(json.dumps(line), flush=True)
 
 

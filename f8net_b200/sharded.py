@@ -54,3 +54,47 @@ class ShardedRunner:
             # in-place all-gather: the input is this rank's slice of the output
             self.dist.all_gather_into_tensor(full.view(-1), mine.reshape(-1), group=self.group)
         return full.view(self.world * n, self.num_classes)
+
+
+class OverlappedGather:
+    """Steady-state form of the same exchange for a stream of batches: the all-gather of step i
+    overlaps the forward pass of step i+1.  Two gather buffers alternate; ``slot(i)`` is this
+    rank's slice of buffer i % 2 (where step i's classifier writes), ``submit(i)`` starts the
+    asynchronous all-gather of that buffer behind the work already enqueued on the current
+    stream, and ``ready(i)`` makes the current stream (CUDA) or the host (gloo) wait until the
+    gather that last used buffer i % 2 -- step i-2's -- has finished, which is what the forward
+    pass of step i needs before it overwrites the slice.  ``result(i)`` waits for step i's own
+    gather and returns the [world * n, classes] logits."""
+
+    def __init__(self, n_per_rank: int, num_classes: int, like, group=None):
+        import torch
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.n, self.num_classes = n_per_rank, num_classes
+        self.bufs = [torch.empty((self.world, n_per_rank, num_classes), dtype=torch.float32,
+                                 device=like.device) for _ in range(2)]
+        self.work = [None, None]
+
+    def slot(self, i):
+        return self.bufs[i % 2][self.rank]
+
+    def ready(self, i):
+        w = self.work[i % 2]
+        if w is not None:
+            w.wait()
+            self.work[i % 2] = None
+
+    def submit(self, i):
+        full = self.bufs[i % 2]
+        self.work[i % 2] = self.dist.all_gather_into_tensor(
+            full.view(-1), full[self.rank].reshape(-1), group=self.group, async_op=True)
+
+    def result(self, i):
+        self.ready(i)
+        return self.bufs[i % 2].view(self.world * self.n, self.num_classes)
+
+    def drain(self):
+        for j in range(2):
+            self.ready(j)

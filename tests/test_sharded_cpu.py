@@ -81,3 +81,47 @@ def test_two_rank_shard_and_all_gather_matches_single_process():
     want = nets.forward(arch, synth.make_state_dict(arch), synth.make_input(arch, n_total))
     assert got.shape == (n_total, 1000)
     assert np.array_equal(got, want)
+
+
+def _overlap_worker(rank, world, port, steps, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from f8net_b200.sharded import OverlappedGather
+        n, classes = 3, 5
+        og = OverlappedGather(n, classes, torch.empty(1))
+        seen = []
+        for i in range(steps):
+            og.ready(i)                      # buffer i % 2 is free again (step i-2 gathered)
+            og.slot(i).copy_(torch.full((n, classes), float(100 * i + rank)))
+            og.submit(i)
+            if i >= 1:
+                seen.append(og.result(i - 1).clone())     # step i-1's gather, overlapped with step i
+        seen.append(og.result(steps - 1).clone())
+        og.drain()
+        if rank == 1:
+            q.put(torch.stack(seen).numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_gather_double_buffering_keeps_step_order():
+    """OverlappedGather (bench.py's N>1 steady state): the gather of step i runs while step i+1
+    writes the other buffer; every step's gathered logits are rank-major and belong to that step."""
+    world, steps = 2, 5
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, world, port, steps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert got.shape == (steps, world * 3, 5)
+    for i in range(steps):
+        for r in range(world):
+            assert (got[i, 3 * r:3 * r + 3] == 100 * i + r).all()
