@@ -9,9 +9,10 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libf8b200.so")
 
-F8_ABI_VERSION = 1
+F8_ABI_VERSION = 2
 F8_OK, F8_ERR_ARG, F8_ERR_CUDA, F8_ERR_UNSUPPORTED, F8_ERR_NOMEM = 0, -1, -2, -3, -4
 F8_IN_NCHW_I32, F8_IN_NHWC4_8, F8_IN_NCHW_F32, F8_IN_NHWC3_U8 = 0, 1, 2, 3
+F8_OPF_INT_MAXPOOL = 1
 F8_OP_CONVERT_INPUT, F8_OP_CONV_DENSE, F8_OP_CONV_DW, F8_OP_MAXPOOL, F8_OP_POOL_REQUANT, \
     F8_OP_HEAD_POOL, F8_OP_POOL_FC = range(7)
 
@@ -29,7 +30,7 @@ class f8_op(ctypes.Structure):
         ("weight", _vp), ("bias", _vp),
         ("carry_in_buf", _i32), ("carry_shift", _i32), ("relu", _i32), ("carry_out_buf", _i32),
         ("out_buf", _i32 * 2), ("out_shift", _i32 * 2), ("out_signed", _i32 * 2),
-        ("out_f32", _i32),
+        ("out_f32", _i32), ("flags", _i32),
     ]
 
 
@@ -56,7 +57,7 @@ class f8_conv_args(ctypes.Structure):
         ("carry_shift", _i32), ("relu", _i32),
         ("carry_out", _vp),
         ("out", _vp * 2), ("out_shift", _i32 * 2), ("out_signed", _i32 * 2),
-        ("out_f32", _vp), ("out_f32_ld", _i32),
+        ("out_f32", _vp), ("out_f32_ld", _i32), ("flags", _i32),
     ]
 
 

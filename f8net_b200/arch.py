@@ -72,6 +72,8 @@ class NetSpec:
     image_size: int = 224
     num_classes: int = 1000
     block_setting: list = field(default_factory=list)
+    maxpool_int: bool = False              # FLAGS.quant_maxpool: FXQMaxPool2d, integer max without the
+                                           # float round trip (fix_quant_ops.py:141-157, fix_resnet.py:355-356)
 
     def convs(self):
         """Every int layer in state_dict order."""
@@ -153,11 +155,17 @@ def _mbv2(head_signed, num_classes):
                    block_setting=[list(t) for t in _MBV2])
 
 
-def graph_for(arch, head_signed=False, num_classes=1000):
+def graph_for(arch, head_signed=False, num_classes=1000, quant_maxpool=False):
     """NetSpec from the architecture name.  ``head_signed`` mirrors FLAGS.normalize
-    (double_side of the head conv, fix_resnet.py:437-438)."""
+    (double_side of the head conv, fix_resnet.py:437-438); ``quant_maxpool`` mirrors
+    FLAGS.quant_maxpool (ResNets: FXQMaxPool2d instead of nn.MaxPool2d on floats,
+    fix_resnet.py:331-334).  FLAGS.quant_avgpool is always True on this path: the shipped
+    int_op_only configs set it, and without it the reference leaves integer arithmetic
+    (AdaptiveAvgPool2d on x.float(), fix_resnet.py:375-382)."""
     if arch.startswith("resnet"):
-        return _resnet(int(arch[6:]), head_signed, num_classes)
+        net = _resnet(int(arch[6:]), head_signed, num_classes)
+        net.maxpool_int = bool(quant_maxpool)
+        return net
     if arch == "mobilenet_v1":
         return _mbv1(head_signed, num_classes)
     if arch == "mobilenet_v2":
@@ -185,7 +193,19 @@ def graph_from_module(im):
     """Walk a reference IntModel (any of the three model files) into a NetSpec."""
     import torch.nn as nn
     head = _conv_spec_from_module(im.head[0], "head.0")
-    maxpool = any(isinstance(m, nn.MaxPool2d) for m in im.head)
+    pools = [m for m in im.head if isinstance(m, nn.MaxPool2d)]
+    maxpool = bool(pools)
+    # FXQMaxPool2d subclasses nn.MaxPool2d (fix_quant_ops.py:141): told apart by class name
+    maxpool_int = any(type(m).__name__ == "FXQMaxPool2d" for m in pools)
+    for m in pools:
+        k, s, p = (v if isinstance(v, int) else v[0] for v in (m.kernel_size, m.stride, m.padding))
+        if (k, s, p) != (3, 2, 1):
+            raise ValueError(f"head max-pool {k}x{k} s{s} p{p}: the F8Net head pools 3x3 s2 p1")
+    # the integer tail is FXQAvgPool2d(7) (FLAGS.quant_avgpool); with nn.AdaptiveAvgPool2d the
+    # reference averages in float32 (fix_resnet.py:375-382) -- different arithmetic, not this path
+    if type(getattr(im, "avgpool", None)).__name__ != "FXQAvgPool2d":
+        raise ValueError("IntModel.avgpool is not FXQAvgPool2d: build the model with quant_avgpool: True "
+                         "(the int_op_only configs do); the float average pool is outside the integer path")
     has_tail = hasattr(im, "tail")
     blocks = []
     setting = list(im.block_setting)
@@ -226,4 +246,4 @@ def graph_from_module(im):
     else:
         family, arch = "mobilenet_v1", "mobilenet_v1"
     return NetSpec(arch, family, head, maxpool, blocks, tail, fc,
-                   num_classes=fc.cout, block_setting=setting)
+                   num_classes=fc.cout, block_setting=setting, maxpool_int=maxpool_int)

@@ -94,6 +94,7 @@ struct Epilogue {
     int shift1, signed1;
     int cout;                 // logical channel count (float output bound)
     int cout_pad;             // row pitch of the NHWC outputs
+    int int_pool;             // max-pool kernels: FXQMaxPool2d (integer max, no float round trip)
 };
 
 // acc (already including bias) + optional residual carry -> int32 value every output derives from

@@ -353,7 +353,7 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
                     r[i] = safe ? max((int32_t)((uint32_t)m[i] + (uint32_t)b16[i]), 0) : m[i];
                     any |= (uint32_t)r[i];
                 }
-                if (any >= (1u << 24)) {
+                if (!ep.int_pool && any >= (1u << 24)) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) r[i] = f8::f2i_x86((float)r[i]);
                 }
@@ -410,6 +410,7 @@ int launch_head_pool(const f8_conv_args &a, cudaStream_t s) {
     ep.shift1 = a.out_shift[1]; ep.signed1 = a.out_signed[1];
     ep.cout = a.cout;
     ep.cout_pad = a.cout_pad;
+    ep.int_pool = (a.flags & F8_OPF_INT_MAXPOOL) != 0;
     static DeviceOnce once;
     int num_sms = 0;
     {

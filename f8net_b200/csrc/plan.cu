@@ -444,6 +444,7 @@ static int run_op(const f8_plan *p, const PlanOp &po, int n, const uint8_t *x, i
     a.carry_in = reinterpret_cast<const int32_t *>(buf(o.carry_in_buf));
     a.carry_shift = o.carry_shift;
     a.relu = o.relu;
+    a.flags = o.flags;
     a.carry_out = reinterpret_cast<int32_t *>(buf(o.carry_out_buf));
     for (int j = 0; j < 2; ++j) {
         a.out[j] = buf(o.out_buf[j]);

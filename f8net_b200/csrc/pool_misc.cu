@@ -45,8 +45,13 @@ maxpool_kernel(const int32_t *__restrict__ in, int n, int hin, int win, int hout
                 m.z = max(m.z, v.z); m.w = max(m.w, v.w);
             }
         }
-        int32_t v[4] = {f8::f2i_x86((float)m.x), f8::f2i_x86((float)m.y),
-                        f8::f2i_x86((float)m.z), f8::f2i_x86((float)m.w)};
+        // nn.MaxPool2d on x.float(), then .int() (fix_resnet.py:358-359) -- or FXQMaxPool2d's integer max
+        // (fix_quant_ops.py:141-157; its zero padding never wins over the post-ReLU values)
+        int32_t v[4] = {m.x, m.y, m.z, m.w};
+        if (!ep.int_pool) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[c] = f8::f2i_x86((float)v[c]);
+        }
         const size_t o = (((size_t)img * hout + p) * wout + q) * cpad + c4 * 4;
         if (ep.relu) {
 #pragma unroll
@@ -288,6 +293,7 @@ f8::Epilogue make_ep(const f8_conv_args &a) {
     ep.shift0 = a.out_shift[0]; ep.signed0 = a.out_signed[0];
     ep.shift1 = a.out_shift[1]; ep.signed1 = a.out_signed[1];
     ep.cout = a.cout; ep.cout_pad = a.cout_pad;
+    ep.int_pool = (a.flags & F8_OPF_INT_MAXPOOL) != 0;
     return ep;
 }
 

@@ -258,11 +258,12 @@ class Engine:
 
 
 def compile(model_or_state_dict, arch: Optional[str] = None, head_signed: Optional[bool] = None,
-            device=None, chunk: int = 256, backend=None) -> Engine:
+            device=None, chunk: int = 256, backend=None, quant_maxpool: bool = False) -> Engine:
     """Build an Engine from a reference ``IntModel`` (module tree walked for stride / groups /
     input_symmetric), or from its ``state_dict()`` plus the architecture name -- the
     attributes the dict lacks are then re-derived from the architecture (SURVEY.md 8(b));
-    ``head_signed`` mirrors FLAGS.normalize (fix_resnet.py:437-438) and defaults to False."""
+    ``head_signed`` mirrors FLAGS.normalize (fix_resnet.py:437-438) and defaults to False;
+    ``quant_maxpool`` mirrors FLAGS.quant_maxpool (FXQMaxPool2d head pool, fix_resnet.py:331-334)."""
     if hasattr(model_or_state_dict, "state_dict") and hasattr(model_or_state_dict, "head"):
         net = graph_from_module(model_or_state_dict)
         sd = model_or_state_dict.state_dict()
@@ -274,5 +275,5 @@ def compile(model_or_state_dict, arch: Optional[str] = None, head_signed: Option
             arch = infer_arch(sd)
         if arch not in ARCHS and not arch.startswith("resnet"):
             raise ValueError(f"unknown arch {arch!r}")
-        net = graph_for(arch, bool(head_signed))
+        net = graph_for(arch, bool(head_signed), quant_maxpool=bool(quant_maxpool))
     return Engine(net, sd, device=device, chunk=chunk, backend=backend)

@@ -60,6 +60,7 @@ class Op:
     carry_out_buf: int = -1
     outs: List[Tuple[int, int, int]] = field(default_factory=list)   # (buf, shift, signed)
     out_f32: int = 0
+    flags: int = 0
     # planning-only
     fa: int = 0                      # fraclen of the int32 value this op produces
     index: int = -1
@@ -172,6 +173,7 @@ class Plan:
                 else:
                     o.out_buf[j], o.out_shift[j], o.out_signed[j] = -1, 0, 0
             o.out_f32 = op.out_f32
+            o.flags = op.flags
         bufs = (C.f8_buffer * max(1, len(self.bufs)))()
         keep.append(bufs)
         for i, b in enumerate(self.bufs):
@@ -259,6 +261,7 @@ def build_plan(net: NetSpec, sd: Dict[str, np.ndarray], fuse_head: bool = False,
         head.kind = C.F8_OP_HEAD_POOL
         head.name = "head.0+maxpool"
         head.hout = head.wout = _out_hw(head.hout, 3, 2, 1)
+        head.flags = C.F8_OPF_INT_MAXPOOL if net.maxpool_int else 0      # FXQMaxPool2d, fix_resnet.py:355-356
         P.emit(head)
         cur, fa, hw = head, head.fa, head.hout
     else:
@@ -268,7 +271,8 @@ def build_plan(net: NetSpec, sd: Dict[str, np.ndarray], fuse_head: bool = False,
             # x = self.head[-1](x.float()).int(), fix_resnet.py:358-359
             mp = Op(C.F8_OP_MAXPOOL, "head.maxpool", cin=cur.cout, cout=cur.cout,
                     cin_pad=cur.cout_pad, cout_pad=cur.cout_pad, k=3, stride=2, pad=1, hin=hw, win=hw,
-                    hout=_out_hw(hw, 3, 2, 1), wout=_out_hw(hw, 3, 2, 1), in_buf=P.carry(cur), fa=fa)
+                    hout=_out_hw(hw, 3, 2, 1), wout=_out_hw(hw, 3, 2, 1), in_buf=P.carry(cur), fa=fa,
+                    flags=C.F8_OPF_INT_MAXPOOL if net.maxpool_int else 0)
             P.emit(mp)
             cur, hw = mp, mp.hout
 

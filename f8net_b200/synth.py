@@ -185,3 +185,75 @@ def make_float_state_dict(arch, seed=77, flags=None):
         fl = float(torch.randint(3, 10, (1,), generator=g)) + float(torch.rand((), generator=g)) * 0.8 - 0.4
         sd[p + ".input_fraclen"] = torch.ones(1) * fl
     return sd
+
+
+TRAINED = ("mobilenet_v2", "resnet50_ptcv", "resnet50_nvidia")
+
+
+def load_trained_fraclens(name):
+    """Per-layer (input_fraclen, weight_fraclen) of a network the reference's authors trained,
+    parsed from the logs they ship (tools/parse_fraclen_logs.py): returns (arch, head_signed,
+    {int prefix: (fi, fw)})."""
+    with open(os.path.join(_DATA, f"trained_fraclens_{name}.json")) as f:
+        doc = json.load(f)
+    return doc["arch"], bool(doc["head_signed"]), {k: tuple(v) for k, v in doc["fraclens"].items()}
+
+
+def make_trained_state_dict(name, seed=2468, gain=1.0):
+    """Second fixture family of SURVEY.md 8(d): the TRAINED per-layer formats (fi 1..8, fw 0..7,
+    including the fw in {0, 1} layers of MobileNetV2) with synthetic weights.  A layer's real-valued
+    gain has to carry the activation range from its own input format to its consumer's
+    (range ~ 2^(8 - fi)), so sigma_float = gain * sqrt(2 / K) * 2^(fi - fi_next) and
+    w_int = clamp(round(N(0, sigma_float * 2^fw)), -127, 127); biases as in make_state_dict.
+    Returns (arch, head_signed, state_dict)."""
+    arch, head_signed, table = load_trained_fraclens(name)
+    net = graph_for(arch, head_signed)
+    rng = np.random.default_rng(seed)
+    convs = net.convs()
+    # consumer of every layer: the next body conv, or the first conv of the next block
+    order = []
+    for blk in net.blocks:
+        order.append([c.prefix for c in blk.body])
+    consumer = {}
+    seq = [net.head.prefix] + [p for body in order for p in body]
+    seq += [net.tail.prefix] if net.tail is not None else []
+    seq += [net.fc.prefix]
+    for a, b in zip(seq, seq[1:]):
+        consumer[a] = b
+    for i, blk in enumerate(net.blocks):
+        if blk.shortcut is not None:
+            consumer[blk.shortcut.prefix] = consumer[blk.body[-1].prefix]
+    residual_feeders = {blk.body[-1].prefix for blk in net.blocks if blk.identity or blk.shortcut is not None}
+    sd = {}
+    for L in convs:
+        fi, fw = table[L.prefix]
+        shape = L.weight_shape()
+        K = int(np.prod(shape[1:]))
+        fi_next = table[consumer[L.prefix]][0] if L.prefix in consumer else fi
+        sigma = gain * math.sqrt(2.0 / K) * 2.0 ** (fi - fi_next)
+        if L.prefix in residual_feeders:
+            sigma *= 0.5
+        sigma_int = min(40.0, max(0.6, sigma * (1 << fw)))
+        w = np.clip(np.rint(rng.normal(0.0, sigma_int, size=shape)), -127, 127).astype(np.int32)
+        u = rng.uniform(-1.0, 1.0, size=(L.cout,))
+        sd[L.prefix + ".weight"] = w
+        sd[L.prefix + ".bias"] = bias_from(u, fw, fi)
+        sd[L.prefix + ".weight_fraclen"] = np.array(fw, dtype=np.int32)
+        sd[L.prefix + ".input_fraclen"] = np.array([fi], dtype=np.int32)
+    return arch, head_signed, sd
+
+
+def make_maxpool_state_dict(arch, head_signed=None):
+    """Fixture that tells the two head max-pools apart (FLAGS.quant_maxpool, fix_resnet.py:355-359):
+    the calibrated parameters with the head bias of eight channels pushed just under 2^31, so that
+    many pooled values land in [2^31 - 64, 2^31) -- ``nn.MaxPool2d(x.float()).int()`` rounds those to
+    2^31 and the x86 conversion returns INT_MIN (0 after the next requant), FXQMaxPool2d keeps them
+    (255 after the next requant) -- and others lose low bits above 2^24 in the float round trip."""
+    if head_signed is None:
+        head_signed = HEAD_SIGNED.get(arch, False)
+    sd = make_state_dict(arch, head_signed)
+    b = sd["head.0.bias"].astype(np.int64)
+    b[:8] = (1 << 31) - (25000 if head_signed else 60000) + 1500 * np.arange(8)
+    b[8:12] = (1 << 24) + 12345 + 2 * np.arange(4)
+    sd["head.0.bias"] = b.astype(np.int32)
+    return sd

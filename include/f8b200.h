@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define F8_ABI_VERSION 1
+#define F8_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define F8_API __attribute__((visibility("default")))
@@ -74,6 +74,14 @@ typedef enum f8_op_kind {
                                  (out_shift[0] / out_signed[0], no buffer) + nn.Linear + .float()
                                  (fix_quant_ops.py:126-134, fix_resnet.py:367-383)                */
 } f8_op_kind;
+
+/* f8_op.flags / f8_conv_args.flags */
+typedef enum f8_op_flags {
+    /* MAXPOOL / HEAD_POOL: the head pool is FXQMaxPool2d (FLAGS.quant_maxpool, fix_quant_ops.py:141-157,
+     * fix_resnet.py:331-334, :355-356): a pure integer max, WITHOUT the x.float() ... .int() round trip
+     * of nn.MaxPool2d (fix_resnet.py:358-359) */
+    F8_OPF_INT_MAXPOOL = 1
+} f8_op_flags;
 
 /*
  * One fused launch.  "Epilogue" = everything the reference does between one int layer's
@@ -116,6 +124,7 @@ typedef struct f8_op {
     int32_t out_shift[2];
     int32_t out_signed[2];
     int32_t out_f32;           /* 1: write float logits to the plan output          */
+    int32_t flags;             /* f8_op_flags                                        */
 } f8_op;
 
 /* One workspace buffer: bytes per image and its offset (in per-image bytes) inside the
@@ -222,6 +231,7 @@ typedef struct f8_conv_args {
     int32_t out_signed[2];
     float *out_f32;            /* [n*hout*wout, out_f32_ld] or NULL                       */
     int32_t out_f32_ld;
+    int32_t flags;             /* f8_op_flags                                              */
 } f8_conv_args;
 
 /* Bytes of the packed weight image for a layer and the packing itself (host -> host).

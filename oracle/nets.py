@@ -208,11 +208,11 @@ def mobilenet_v2_forward(sd, x, head_signed=False, trace=None):
     return _pool_fc(h, fa, fc, trace)
 
 
-def forward(arch, sd, x, head_signed=False, trace=None):
+def forward(arch, sd, x, head_signed=False, trace=None, quant_maxpool=False):
     """arch in {'resnet18','resnet50','mobilenet_v1','mobilenet_v2'}; x int32 NCHW."""
     x = np.ascontiguousarray(x, dtype=np.int32)
     if arch.startswith("resnet"):
-        return resnet_forward(sd, int(arch[6:]), x, head_signed, trace)
+        return resnet_forward(sd, int(arch[6:]), x, head_signed, trace, quant_maxpool)
     if arch == "mobilenet_v1":
         return mobilenet_v1_forward(sd, x, head_signed, trace)
     if arch == "mobilenet_v2":

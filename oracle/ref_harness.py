@@ -9,7 +9,7 @@ The reference keeps its config in a module-level singleton read from sys.argv at
 (/root/reference/myutils/config.py:152-178), so one process can host one architecture:
 use it as a script,
 
-    python -m oracle.ref_harness <arch> <in.npz> <out.npz>
+    python -m oracle.ref_harness <arch> <in.npz> <out.npz> [flag=0|1 ...]
 
 in.npz : 'x' int32 [N,3,224,224] + every state_dict tensor under its reference key.
 out.npz: 'logits' float32 [N,1000], 'keys' (state_dict key order of the reference IntModel),
@@ -118,13 +118,13 @@ def build_int_model(arch, float_state_dict=None, keep_grid_search=False, flag_ov
     return im, FLAGS
 
 
-def run(arch, x_np, sd_np, capture=True):
+def run(arch, x_np, sd_np, capture=True, flag_overrides=None):
     """Load the synthetic state dict into the reference IntModel and run its forward."""
     import numpy as np
     import torch
     import torch.nn as nn
 
-    im, FLAGS = build_int_model(arch)
+    im, FLAGS = build_int_model(arch, flag_overrides=flag_overrides)
     keys = list(im.state_dict().keys())
     ref_sd = im.state_dict()
     new_sd = {}
@@ -156,9 +156,11 @@ def run(arch, x_np, sd_np, capture=True):
 def main(argv):
     import numpy as np
     arch, inp, outp = argv[1], argv[2], argv[3]
+    # optional FLAGS overrides, e.g. quant_maxpool=1 (FXQMaxPool2d head pool)
+    overrides = {kv.split("=")[0]: bool(int(kv.split("=")[1])) for kv in argv[4:]}
     data = np.load(inp)
     sd = {k: data[k] for k in data.files if k != "x"}
-    logits, keys, cap, sym, _ = run(arch, data["x"], sd)
+    logits, keys, cap, sym, _ = run(arch, data["x"], sd, flag_overrides=overrides)
     cap = {k: v for k, v in cap.items()}
     np.savez(outp, logits=logits, keys=np.array(keys),
              sym_names=np.array(list(sym.keys())),

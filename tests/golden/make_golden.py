@@ -78,20 +78,20 @@ def calibrate(arch, head_signed, n=2):
     return table
 
 
-def run_reference(arch, x, sd):
+def run_reference(arch, x, sd, flags=()):
     with tempfile.TemporaryDirectory() as td:
         inp, outp = os.path.join(td, "in.npz"), os.path.join(td, "out.npz")
         np.savez(inp, x=x, **sd)
         env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
         subprocess.check_call([sys.executable, "-W", "ignore", "-m", "oracle.ref_harness", arch,
-                               inp, outp], cwd=ROOT, env=env)
+                               inp, outp, *flags], cwd=ROOT, env=env)
         o = np.load(outp)
         return {k: o[k] for k in o.files}
 
 
-def compare_and_pack(arch, head_signed, x, sd, ref):
+def compare_and_pack(arch, head_signed, x, sd, ref, quant_maxpool=False):
     tr = {}
-    y = nets.forward(arch, sd, x, head_signed, tr)
+    y = nets.forward(arch, sd, x, head_signed, tr, quant_maxpool=quant_maxpool)
     assert list(ref["keys"]) == list(sd.keys()), "state_dict key order differs from reference"
     assert np.array_equal(y, ref["logits"]), f"{arch}: oracle logits != reference logits"
     refsym = dict(zip(ref["sym_names"], ref["sym_vals"]))

@@ -40,6 +40,7 @@ int main(void) {
   printf("%zu %zu %zu %zu ", sizeof(f8_op), sizeof(f8_buffer), sizeof(f8_model_desc), sizeof(f8_conv_args));
   printf("%zu %zu %zu %zu ", offsetof(f8_op, weight), offsetof(f8_op, carry_in_buf), offsetof(f8_op, out_buf), offsetof(f8_op, out_f32));
   printf("%zu %zu %zu %zu %zu\n", offsetof(f8_conv_args, in), offsetof(f8_conv_args, carry_shift), offsetof(f8_conv_args, carry_out), offsetof(f8_conv_args, out_f32), offsetof(f8_model_desc, workspace_per_image));
+  printf("%zu %zu %d\n", offsetof(f8_op, flags), offsetof(f8_conv_args, flags), (int)F8_OPF_INT_MAXPOOL);
   return 0; }
 """
     with tempfile.TemporaryDirectory() as td:
@@ -54,7 +55,8 @@ int main(void) {
             C.f8_op.out_f32.offset,
             C.f8_conv_args.in_.offset, C.f8_conv_args.carry_shift.offset,
             C.f8_conv_args.carry_out.offset, C.f8_conv_args.out_f32.offset,
-            C.f8_model_desc.workspace_per_image.offset]
+            C.f8_model_desc.workspace_per_image.offset,
+            C.f8_op.flags.offset, C.f8_conv_args.flags.offset, C.F8_OPF_INT_MAXPOOL]
     assert got == want
 
 

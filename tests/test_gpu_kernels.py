@@ -205,18 +205,22 @@ def _args_for_pool(n, c, hin, hout, k, stride, pad):
     return a
 
 
-def test_maxpool_float_round_trip(G, f8lib):
-    """x = head[-1](x.float()).int()  (fix_resnet.py:358-359) incl. values above 2^24."""
+@pytest.mark.parametrize("int_pool", [False, True], ids=["float_rt", "FXQMaxPool2d"])
+def test_maxpool_float_round_trip(G, f8lib, int_pool):
+    """x = head[-1](x.float()).int()  (fix_resnet.py:358-359) incl. values above 2^24 -- and the
+    FLAGS.quant_maxpool variant FXQMaxPool2d (fix_quant_ops.py:141-157): integer max, no round trip."""
     rng = np.random.default_rng(8)
     n, c, h = 3, 64, 18
     x = rng.integers(0, 5_000_000, (n, c, h, h)).astype(np.int32)
     x[0, :, 3, 3] = 2 ** 24 + 1
     x[1, 1, 5, 5] = 2 ** 31 - 1
     x[2, 2] = rng.integers(2 ** 24, 2 ** 31 - 1, (h, h))
-    want = O.maxpool_float_rt(x, 3, 2, 1)
+    want = O.maxpool_int(x, 3, 2, 1) if int_pool else O.maxpool_float_rt(x, 3, 2, 1)
+    assert int_pool == bool((O.maxpool_int(x, 3, 2, 1) == want).all())      # the data tells them apart
     ho = want.shape[2]
     xd = G.dev(nchw_to_carry(x))
     a = _args_for_pool(n, c, h, ho, 3, 2, 1)
+    a.flags = C.F8_OPF_INT_MAXPOOL if int_pool else 0
     a.in_ = xd.data_ptr()
     co = torch.empty((carry_elems(n, ho, ho, cpad(c)),), dtype=torch.int32, device="cuda:0")
     q0 = torch.empty((n, ho, ho, cpad(c)), dtype=torch.uint8, device="cuda:0")
@@ -229,8 +233,9 @@ def test_maxpool_float_round_trip(G, f8lib):
     assert np.array_equal(nhwc_to_nchw(q0.cpu().numpy(), c), O.requant(want, 0, 15, False))
 
 
+@pytest.mark.parametrize("int_pool", [False, True], ids=["float_rt", "FXQMaxPool2d"])
 @pytest.mark.parametrize("signed", [False, True])
-def test_head_conv_pool_fused(G, f8lib, signed):
+def test_head_conv_pool_fused(G, f8lib, signed, int_pool):
     """x = head[:-1](x); x = head[-1](x.float()).int() in one launch (fix_resnet.py:355-362),
     incl. accumulators above 2^24 (float rounding) and at INT_MAX (x86 .int() indefinite)."""
     if not f8lib.f8_has_umma(0):
@@ -243,7 +248,7 @@ def test_head_conv_pool_fused(G, f8lib, signed):
     b[11] = -2 ** 31 + 5
     x = rng.integers(lo, hi, (n, 3, 224, 224)).astype(np.int32)
     acc = O.relu(O.conv2d(x, w, b, 2, 3, 1))
-    pooled = O.maxpool_float_rt(acc, 3, 2, 1)
+    pooled = O.maxpool_int(acc, 3, 2, 1) if int_pool else O.maxpool_float_rt(acc, 3, 2, 1)
     outs = ((14, False), (13, True))
     want_q = [O.requant(pooled, 0, s, g) for s, g in outs]
     xd = G.dev(G.nchw_to_nhwc8(x, 4, signed))
@@ -254,6 +259,7 @@ def test_head_conv_pool_fused(G, f8lib, signed):
     a.kh, a.kw, a.stride, a.pad = 7, 7, 2, 3
     a.hin, a.win, a.hout, a.wout = 224, 224, 56, 56
     a.in_signed = int(signed)
+    a.flags = C.F8_OPF_INT_MAXPOOL if int_pool else 0
     a.in_, a.wpack, a.bias = xd.data_ptr(), wd.data_ptr(), bd.data_ptr()
     co = torch.full((carry_elems(n, 56, 56, 64),), -7, dtype=torch.int32, device="cuda:0")
     q = [torch.full((n, 56, 56, 64), 0x77, dtype=torch.uint8, device="cuda:0") for _ in outs]

@@ -62,6 +62,32 @@ def test_golden_logits_from_the_reference(cuda, f8lib, arch, family, backend):
     assert torch.equal(y3.cpu(), y)
 
 
+@pytest.mark.parametrize("name", synth.TRAINED)
+def test_trained_fraclen_family_golden(cuda, f8lib, name):
+    """The per-layer formats of the networks the reference's authors trained (fraclen_visual/*.out;
+    fi 1..8, fw 0..7): golden logits from the unmodified reference (make_variant_golden.py)."""
+    from util import trained_fixture
+    arch, hs, sd, x, gold = trained_fixture(name)
+    for backend in (0, 1):
+        eng = f8net_b200.compile(sd, arch=arch, head_signed=hs, backend=backend)
+        y = eng(torch.from_numpy(x))
+        assert np.array_equal(y.numpy().astype(np.int64), gold["logits"].astype(np.int64)), (name, backend)
+
+
+@pytest.mark.parametrize("backend", [pytest.param(0, id="imma"), pytest.param(1, id="tcgen05")])
+@pytest.mark.parametrize("arch", ["resnet18", "resnet50"])
+def test_both_head_pools_golden(cuda, f8lib, arch, backend):
+    """FLAGS.quant_maxpool (fix_resnet.py:331-334, :355-359): FXQMaxPool2d's integer max against
+    nn.MaxPool2d on floats, on a fixture where 99 % of the reference's logits differ between them."""
+    from util import qmaxpool_fixture
+    hs, sd, x, gold = qmaxpool_fixture(arch)
+    xt = torch.from_numpy(x)
+    yf = f8net_b200.compile(sd, arch=arch, head_signed=hs, backend=backend)(xt)
+    yi = f8net_b200.compile(sd, arch=arch, head_signed=hs, backend=backend, quant_maxpool=True)(xt)
+    assert np.array_equal(yf.numpy().astype(np.int64), gold["logits_float_pool"].astype(np.int64))
+    assert np.array_equal(yi.numpy().astype(np.int64), gold["logits"].astype(np.int64))
+
+
 @pytest.mark.parametrize("arch", ARCHS)
 def test_oracle_parity_ragged_batch_and_chunks(cuda, f8lib, arch):
     hs = synth.HEAD_SIGNED[arch]

@@ -10,7 +10,7 @@ from f8net_b200 import synth
 from oracle import nets
 from oracle import oracle as O
 
-from util import checksum
+from util import checksum, qmaxpool_fixture, trained_fixture
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ARCHS = list(synth.HEAD_SIGNED)
@@ -36,6 +36,38 @@ def test_oracle_matches_reference_golden(arch, family):
     # every int layer's 8-bit input and int32 accumulator, pinned by checksum
     for name, want in zip(gold["layer_names"], gold["layer_checksums"]):
         assert checksum(trace[str(name)]) == want, f"{arch}/{family}: {name}"
+
+
+@pytest.mark.parametrize("name", synth.TRAINED)
+def test_oracle_matches_reference_on_trained_fraclens(name):
+    """Second fixture family: the per-layer formats of the networks the reference's
+    authors trained (fraclen_visual/*.out), golden logits / layer tensors from the unmodified reference
+    (tests/golden/make_variant_golden.py)."""
+    arch, hs, sd, x, gold = trained_fixture(name)
+    fis = {int(sd[k][0]) for k in sd if k.endswith(".input_fraclen")}
+    fws = {int(sd[k]) for k in sd if k.endswith(".weight_fraclen")}
+    if name == "mobilenet_v2":
+        assert {0, 1} <= fws and {1, 8} <= fis          # the fw in {0,1} layers SURVEY names
+    trace = {}
+    y = nets.forward(arch, sd, x, hs, trace)
+    assert np.array_equal(y.astype(np.int64), gold["logits"].astype(np.int64))
+    for lname, want in zip(gold["layer_names"], gold["layer_checksums"]):
+        assert checksum(trace[str(lname)]) == want, f"{name}: {lname}"
+
+
+@pytest.mark.parametrize("arch", ["resnet18", "resnet50"])
+def test_oracle_matches_reference_with_both_head_pools(arch):
+    """FLAGS.quant_maxpool: FXQMaxPool2d (integer max, fix_quant_ops.py:141-157) against
+    nn.MaxPool2d on x.float() (fix_resnet.py:358-359); the fixture makes them disagree."""
+    hs, sd, x, gold = qmaxpool_fixture(arch)
+    yf = nets.forward(arch, sd, x, hs)
+    ti = {}
+    yi = nets.forward(arch, sd, x, hs, ti, quant_maxpool=True)
+    assert np.array_equal(yf.astype(np.int64), gold["logits_float_pool"].astype(np.int64))
+    assert np.array_equal(yi.astype(np.int64), gold["logits"].astype(np.int64))
+    assert (yf != yi).mean() > 0.5
+    for lname, want in zip(gold["layer_names"], gold["layer_checksums"]):
+        assert checksum(ti[str(lname)]) == want, f"{arch}: {lname}"
 
 
 # ---- literal restatement of fix_quant_ops.py:90-114 with Python ints -------------------

@@ -64,3 +64,27 @@ def carry_to_nchw(buf, n, c, h, w, c_pad=None):
 
 def carry_elems(n, h, w, c_pad):
     return (n * h * w + 127) // 128 * 128 * c_pad
+
+
+# ---- round-2 fixture families (tests/golden/make_variant_golden.py) --------------------------
+import os as _os
+
+_GOLD = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
+TRAINED_SEED, QMP_SEED = 5150, 808
+
+
+def trained_fixture(name):
+    """(arch, head_signed, state_dict, x, golden) of the trained-fraclen family."""
+    from f8net_b200 import synth
+    arch, hs, sd = synth.make_trained_state_dict(name)
+    x = synth.make_input(arch, 2, hs, seed=TRAINED_SEED)
+    return arch, hs, sd, x, np.load(_os.path.join(_GOLD, f"trained_{name}_n2.npz"))
+
+
+def qmaxpool_fixture(arch):
+    """(head_signed, state_dict, x, golden) of the FXQMaxPool2d-vs-float-pool family."""
+    from f8net_b200 import synth
+    hs = synth.HEAD_SIGNED[arch]
+    sd = synth.make_maxpool_state_dict(arch, hs)
+    x = synth.make_input(arch, 2, hs, seed=QMP_SEED)
+    return hs, sd, x, np.load(_os.path.join(_GOLD, f"qmaxpool_{arch}_n2.npz"))
