@@ -27,3 +27,20 @@ def export_int_state_dict(*args, **kwargs):
 def compile_float(*args, **kwargs):
     from .export import compile_float as _c
     return _c(*args, **kwargs)
+
+
+def export_onnx(*args, **kwargs):
+    """Opset-11 ONNX file of the integer graph (the reference's onnx_export for the int_op_only model)."""
+    from .onnx_export import export_onnx as _e
+    return _e(*args, **kwargs)
+
+
+def save_engine(*args, **kwargs):
+    """Self-contained int8 engine file (weights + formats + graph meta)."""
+    from .engine_file import save_engine as _s
+    return _s(*args, **kwargs)
+
+
+def load_engine(*args, **kwargs):
+    from .engine_file import load_engine as _l
+    return _l(*args, **kwargs)

@@ -810,6 +810,27 @@ extern "C" int f8_requant_i32(const int32_t *x, int32_t *y, size_t count, int fl
     return f8host::launch_requant_i32(x, y, count, shift, is_signed, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int f8_plan_read_buffer(const f8_plan *plan, int buf_index, int n, int chunk, const void *workspace_dev,
+                                   void *dst_host, size_t dst_bytes, void *stream) {
+    if (!plan || !workspace_dev || !dst_host || n <= 0 || chunk < n || buf_index < 0 ||
+        buf_index >= (int)plan->bufs.size()) {
+        set_error("plan_read_buffer: bad arguments");
+        return F8_ERR_ARG;
+    }
+    const f8_buffer &b = plan->bufs[buf_index];
+    const size_t bytes = (size_t)b.bytes_per_image * (size_t)n;
+    if (bytes > dst_bytes) {
+        set_error("plan_read_buffer: buffer %d holds %zu bytes for %d images, destination has %zu", buf_index, bytes, n,
+                  dst_bytes);
+        return F8_ERR_ARG;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint8_t *src = static_cast<const uint8_t *>(workspace_dev) + (size_t)b.offset_per_image * (size_t)chunk;
+    F8_CUDA(cudaMemcpyAsync(dst_host, src, bytes, cudaMemcpyDeviceToHost, s));
+    F8_CUDA(cudaStreamSynchronize(s));
+    return F8_OK;
+}
+
 extern "C" int f8_plan_kernel_name(const f8_plan *plan, int op_index, char *dst, int cap) {
     if (!plan || !dst || cap <= 0 || op_index < 0 || op_index >= (int)plan->ops.size()) {
         set_error("plan_kernel_name: bad arguments");

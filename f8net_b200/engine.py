@@ -52,7 +52,8 @@ class Engine:
     """One compiled plan on one GPU.  Stateless at inference like the reference's IntModel:
     the only mutable state is scratch memory, so use one Engine per stream."""
 
-    def __init__(self, net: NetSpec, state_dict, device=None, chunk: int = 256, backend=None):
+    def __init__(self, net: NetSpec, state_dict, device=None, chunk: int = 256, backend=None,
+                 keep_buffers: bool = False):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("f8net_b200 needs a CUDA device (sm_100a); there is no CPU path")
@@ -66,7 +67,9 @@ class Engine:
         # the fused head conv + max-pool launch exists on the tcgen05 backend only
         # (the fused tail launch -- pool + requant + classifier -- likewise)
         self.plan: Plan = build_plan(net, _to_numpy_sd(state_dict), fuse_head=(int(backend) == 1),
-                                     fuse_tail=(int(backend) == 1))
+                                     fuse_tail=(int(backend) == 1), keep_buffers=keep_buffers)
+        self.keep_buffers = bool(keep_buffers)
+        self._last = None                      # (n, chunk) of the most recent run_device
         self.chunk = int(chunk)
         desc, keep = self.plan.to_desc()
         handle = ctypes.c_void_p()
@@ -131,11 +134,21 @@ class Engine:
     def launches(self, n, layout=C.F8_IN_NCHW_I32, chunk=None):
         return int(self.lib.f8_plan_launch_count(self._h, layout, int(n), int(chunk or self.chunk)))
 
+    def _grow(self, attr, need, dtype):
+        """Scratch tensors grow by replacement.  The caching allocator only knows the allocation
+        stream, while the library enqueues on whatever stream the caller passes, so work still in
+        flight could see the freed block handed to someone else: drain the device before the old
+        tensor is dropped (growth is rare: first call, or a larger batch / chunk)."""
+        cur = getattr(self, attr)
+        if cur is None or cur.numel() < need:
+            if cur is not None:
+                self._torch.cuda.synchronize(self.device)
+            cur = self._torch.empty(need, dtype=dtype, device=self.device)
+            setattr(self, attr, cur)
+        return cur
+
     def _workspace(self, chunk):
-        need = self.plan.workspace_per_image * chunk
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = self._torch.empty(need, dtype=self._torch.uint8, device=self.device)
-        return self._ws
+        return self._grow("_ws", self.plan.workspace_per_image * chunk, self._torch.uint8)
 
     def _layout_of(self, x):
         torch = self._torch
@@ -180,7 +193,23 @@ class Engine:
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
         C.check(self.lib.f8_plan_run(self._h, x.data_ptr(), layout, n, out.data_ptr(),
                                      ws.data_ptr(), ws.numel(), chunk, st.cuda_stream))
+        self._last = (n, chunk)
         return out
+
+    def read_buffer(self, index):
+        """Debug / parity aid: plan buffer ``index`` (see ``plan.bufs``) as the most recent single-pass
+        ``run_device`` left it, as a uint8 numpy array of n * bytes_per_image bytes.  Needs an Engine
+        built with ``keep_buffers=True`` (otherwise dead buffers are reused by later layers)."""
+        if not self.keep_buffers:
+            raise RuntimeError("read_buffer needs compile(..., keep_buffers=True)")
+        if self._last is None or self._last[0] > self._last[1]:
+            raise RuntimeError("read_buffer: run one pass first (n <= chunk)")
+        n, chunk = self._last
+        dst = np.empty(self.plan.bufs[index].bytes_per_image * n, dtype=np.uint8)
+        st = self._torch.cuda.current_stream(self.device)
+        C.check(self.lib.f8_plan_read_buffer(self._h, int(index), n, chunk, self._ws.data_ptr(),
+                                             dst.ctypes.data, dst.nbytes, st.cuda_stream))
+        return dst
 
     def run_host(self, x, chunk=None, out=None, sync=True, stream=None):
         """x: CPU tensor (int32 NCHW or 8-bit NHWC4; pinned for full PCIe speed).  Copies in,
@@ -196,11 +225,8 @@ class Engine:
         if n == 0:
             return out
         nbytes = x.numel() * x.element_size()
-        if self._stage is None or self._stage.numel() < nbytes:
-            self._stage = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        if self._logits is None or self._logits.numel() < n * self.net.num_classes:
-            self._logits = torch.empty(n * self.net.num_classes, dtype=torch.float32,
-                                       device=self.device)
+        self._grow("_stage", nbytes, torch.uint8)
+        self._grow("_logits", n * self.net.num_classes, torch.float32)
         chunk = min(int(chunk or self.chunk), n)
         ws = self._workspace(chunk)
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
@@ -250,6 +276,13 @@ class Engine:
             mn, mx = int(x.min()), int(x.max())
             if mn < lo or mx > hi:
                 raise ValueError(f"input range [{mn},{mx}] outside the head's [{lo},{hi}]")
+        if strict and x.dtype == torch.float32 and not self.input_prep["normalize"]:
+            # forward_loss asserts input >= 0 (fix_train.py:689) and (255 x).round() must stay in the
+            # head's 8 bits; the normalize branch clamps to +-127 itself (fix_quant, fix_train.py:682-687)
+            mn, mx = float(x.min()), float(x.max())
+            if mn < 0.0 or mx > 1.0 or mn != mn:
+                raise ValueError(f"float input range [{mn},{mx}] outside [0,1]: the reference asserts "
+                                 f"input >= 0 and its head conv would see values beyond 8 bits")
         if x.is_cuda:
             return self.run_device(x)
         return self.run_host(x)
@@ -258,7 +291,8 @@ class Engine:
 
 
 def compile(model_or_state_dict, arch: Optional[str] = None, head_signed: Optional[bool] = None,
-            device=None, chunk: int = 256, backend=None, quant_maxpool: bool = False) -> Engine:
+            device=None, chunk: int = 256, backend=None, quant_maxpool: bool = False,
+            keep_buffers: bool = False) -> Engine:
     """Build an Engine from a reference ``IntModel`` (module tree walked for stride / groups /
     input_symmetric), or from its ``state_dict()`` plus the architecture name -- the
     attributes the dict lacks are then re-derived from the architecture (SURVEY.md 8(b));
@@ -276,4 +310,4 @@ def compile(model_or_state_dict, arch: Optional[str] = None, head_signed: Option
         if arch not in ARCHS and not arch.startswith("resnet"):
             raise ValueError(f"unknown arch {arch!r}")
         net = graph_for(arch, bool(head_signed), quant_maxpool=bool(quant_maxpool))
-    return Engine(net, sd, device=device, chunk=chunk, backend=backend)
+    return Engine(net, sd, device=device, chunk=chunk, backend=backend, keep_buffers=keep_buffers)

@@ -110,7 +110,9 @@ class Plan:
         return producer.carry_out_buf
 
     # -- liveness + offsets -------------------------------------------------------------
-    def finalize(self):
+    def finalize(self, keep_buffers=False):
+        """Liveness + first-fit offsets.  ``keep_buffers``: every buffer gets its own range (no reuse),
+        so that all intermediate tensors survive the run (per-layer parity, Engine.read_buffer)."""
         for b in self.bufs:
             b.first, b.last = 10 ** 9, -1
         for op in self.ops:
@@ -130,7 +132,7 @@ class Plan:
         for b in sorted(self.bufs, key=lambda t: (t.first, -t.bytes_per_image)):
             size = (b.bytes_per_image + 255) // 256 * 256
             busy = sorted((p.offset, p.offset + (p.bytes_per_image + 255) // 256 * 256)
-                          for p in placed if not (p.last < b.first or p.first > b.last))
+                          for p in placed if keep_buffers or not (p.last < b.first or p.first > b.last))
             off = 0
             for lo, hi in busy:
                 if off + size <= lo:
@@ -223,7 +225,7 @@ def _out_hw(h, k, s, p):
 
 
 def build_plan(net: NetSpec, sd: Dict[str, np.ndarray], fuse_head: bool = False,
-               fuse_tail: bool = False) -> Plan:
+               fuse_tail: bool = False, keep_buffers: bool = False) -> Plan:
     """Lower the integer graph to fused launches.  ``sd`` maps the reference state_dict keys
     to integer arrays (numpy or anything np.asarray accepts).  ``fuse_head``: emit the ResNet
     head conv + ReLU + max-pool as one F8_OP_HEAD_POOL launch (tcgen05 backend)."""
@@ -322,7 +324,7 @@ def build_plan(net: NetSpec, sd: Dict[str, np.ndarray], fuse_head: bool = False,
                   fa=fw_fc + fi_fc, out_f32=1)
         tail.outs.append((-1, fa_pool - fi_fc, int(net.fc.sym)))      # requant of the pooled sum, no buffer
         P.emit(tail)
-        return P.finalize()
+        return P.finalize(keep_buffers)
     pool = Op(C.F8_OP_POOL_REQUANT, "avgpool", cin=cur.cout, cout=cur.cout, cin_pad=cur.cout_pad,
               cout_pad=cur.cout_pad, k=hw, stride=1, pad=0, hin=hw, win=hw, hout=1, wout=1,
               in_buf=P.carry(cur), fa=fa_pool)
@@ -330,4 +332,4 @@ def build_plan(net: NetSpec, sd: Dict[str, np.ndarray], fuse_head: bool = False,
     fc = conv_op(net.fc, pool, fa_pool, False, 1)
     fc.out_f32 = 1
     P.emit(fc)
-    return P.finalize()
+    return P.finalize(keep_buffers)

@@ -203,6 +203,16 @@ F8_API int f8_plan_profile(f8_plan *plan, const void *x_dev, int x_layout, int n
  * measurement be attributed per kernel template rather than per op kind. */
 F8_API int f8_plan_kernel_name(const f8_plan *plan, int op_index, char *dst, int cap);
 
+/* Debug / parity aid (the reference's equivalent is a forward hook on a module, e.g.
+ * register_forward_pre_hook on an int nn.Conv2d to see its 8-bit input): copies plan buffer
+ * `buf_index` as the last pass of f8_plan_run(n <= chunk images, chunk) left it in `workspace_dev`
+ * -- n * bytes_per_image bytes from workspace + offset_per_image * chunk -- to `dst_host`, on
+ * `stream`, and synchronises.  Meaningful for every buffer only when the planner gave each buffer
+ * its own range (host planner: keep_buffers=True); with liveness-based reuse a buffer holds what
+ * its last writer left. */
+F8_API int f8_plan_read_buffer(const f8_plan *plan, int buf_index, int n, int chunk,
+                               const void *workspace_dev, void *dst_host, size_t dst_bytes, void *stream);
+
 /* Number of kernel launches one f8_plan_run(x_layout, n, chunk) enqueues. */
 F8_API int f8_plan_launch_count(const f8_plan *plan, int x_layout, int n, int chunk);
 /* Which dense-conv backend the plan uses: 0 = mma.sync (legacy IMMA); 1 = tcgen05 (resident-

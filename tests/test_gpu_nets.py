@@ -161,6 +161,12 @@ def test_input_validation(cuda, f8lib):
     bad = torch.full((1, 3, 224, 224), 300, dtype=torch.int32)
     with pytest.raises(ValueError, match="outside"):
         eng(bad, strict=True)
+    # the float tensor of forward_loss: the reference asserts input >= 0 (fix_train.py:689)
+    with pytest.raises(ValueError, match="outside"):
+        eng(torch.full((1, 3, 224, 224), -0.25), strict=True)
+    with pytest.raises(ValueError, match="outside"):
+        eng(torch.full((1, 3, 224, 224), 1.5).cuda(), strict=True)
+    eng(torch.rand((1, 3, 224, 224)), strict=True)
 
 
 @pytest.mark.parametrize("switch,arch", [("F8_PAIR", "resnet18"), ("F8_CPA", "mobilenet_v2"), ("F8_PDL", "resnet18")])
