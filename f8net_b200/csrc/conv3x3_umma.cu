@@ -238,12 +238,14 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                 const int yy = Yb - img * HP;
                 for (int cg = 0; cg < ncg; ++cg) {
                     F8_TIMED_WAIT(w_empty, mbar_wait(a_empty(slot), phase ^ 1));
+                    const bool skip_tma = F8_DBG && (g.probe & 256) && it != bid;      // probe: stale patch (WRONG results)
                     if (lane == 0) {
-                        mbar_expect_tx(a_full(slot), (uint32_t)(PLANES * nbox * BS * 64));
+                        mbar_expect_tx(a_full(slot), skip_tma ? 0u : (uint32_t)(PLANES * nbox * BS * 64));
                         mbar_arrive(a_full(slot));
                     }
                     __syncwarp();
-                    if (PLANES == 1) {
+                    if (skip_tma) {
+                    } else if (PLANES == 1) {
                         if (lane < nbox)
                             tma_load_4d(smem_base + slot * a_stage + lane * BS * 64, &tmaps.m[PAIR ? rank : 0u], (cg0 + cg) * 64, -1,
                                         yy - 1, img, a_full(slot));
@@ -286,8 +288,10 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                     for (int fr = 0; fr < 3; ++fr) {
                         F8_TIMED_WAIT(w_bempty, mbar_wait(b_empty(slot), phase ^ 1));
                         const uint32_t sb = sb_base + slot * B_STAGE;
-                        mbar_expect_tx(b_full(slot), 12u * ROWS_B * 16u);
+                        const bool skip_w = F8_DBG && (g.probe & 512) && it != bid;    // probe: stale weights (WRONG results)
+                        mbar_expect_tx(b_full(slot), skip_w ? 0u : 12u * ROWS_B * 16u);
                         mbar_arrive(b_full(slot));
+                        if (skip_w) { if (++slot == SB) { slot = 0; phase ^= 1; } continue; }
 #pragma unroll
                         for (int fs = 0; fs < 3; ++fs) {
                             const size_t kc = (size_t)((fr * 3 + fs) * Ck + kcg * 64) >> 4;
@@ -370,12 +374,31 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                 const int dw_halves = (DW && ep.cout_pad - (tile_group0(it) + cg) * 64 <= 32) ? 1 : 2;
 #pragma unroll
                 for (int fr = 0; fr < 3; ++fr) {
-                    F8_TIMED_WAIT(w_b, mbar_wait(b_full(bslot), bphase));
+                    if (!(F8_DBG && (g.probe & 1024))) F8_TIMED_WAIT(w_b, mbar_wait(b_full(bslot), bphase));
                     if (PAIR) F8_TIMED_WAIT(w_b, mbar_wait_cluster(b_peer(bslot), bphase));
-                    tc_fence_after();
+                    if (!(F8_DBG && (g.probe & 2048))) tc_fence_after();
                     const uint32_t sb = sb_base + bslot * B_STAGE;
                     const uint32_t a_row = (((sa & 0x3ffffu) >> 4) | a_lbo_field) + tap_row[fr];
                     const uint32_t b_row = ((sb & 0x3ffffu) >> 4) | b_lbo_field;
+                    if (!DW && F8_DBG && (g.probe & 128)) {
+                        // probe: long runs on one accumulator (segment outermost)
+                        if (elect_one()) {
+#pragma unroll
+                            for (int i = 0; i < MB; ++i)
+#pragma unroll
+                                for (int fs = 0; fs < 3; ++fs)
+#pragma unroll
+                                    for (int h = 0; h < 2; ++h) {
+                                        const uint32_t a_lo0 = a_row + (STRIDE == 2 ? (fs == 0 ? tap_col[0] : (fs == 1 ? SLOT16 : tap_col[1]))
+                                                                                    : SLOT16 * (uint32_t)fs);
+                                        const uint32_t b_lo0 = b_row + (uint32_t)(fs * (B_TILE >> 4));
+                                        umma_i8_lohi(tacc + (uint32_t)(i * BN), a_lo0 + (uint32_t)(i * 512 + h * 2), desc_hi_a,
+                                                     b_lo0 + (uint32_t)h * ((2 * BROWS * 16) >> 4), desc_hi, idesc,
+                                                     (h | fs | fr) ? 1u : first);
+                                    }
+                            umma_commit(b_empty(bslot));
+                        }
+                    } else
                     if (elect_one()) {
 #pragma unroll
                         for (int fs = 0; fs < 3; ++fs) {
@@ -401,10 +424,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                                                          (fs | fr) ? 1u : 0u);
                                 }
                             } else {
-#pragma unroll
-                            for (int i = 0; i < MB; ++i) {
-#pragma unroll
-                                for (int h = 0; h < 2; ++h) {
+                            auto issue = [&](int i, int h) {
                                     const uint32_t a_lo1 = a_lo0 + (TMA ? (uint32_t)(i * 512 + h * 2)
                                                                         : (uint32_t)((i * 2048) >> 4) + (uint32_t)h * ((2 * lbo_a) >> 4));
                                     const uint32_t b_lo1 = b_lo0 + (uint32_t)h * ((2 * BROWS * 16) >> 4);
@@ -412,14 +432,25 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                                                             instr_desc_m(A_SIGNED, BN, 256), (h | fs | fr) ? 1u : first);
                                     else umma_i8_lohi(tacc + (uint32_t)(i * BN), a_lo1, desc_hi_a, b_lo1, desc_hi, idesc,
                                                       (h | fs | fr) ? 1u : first);
-                                }
+                            };
+                            if (F8_DBG && (g.probe & 64)) {       // probe: alternate the accumulators every MMA
+#pragma unroll
+                                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                                    for (int i = 0; i < MB; ++i) issue(i, h);
+                            } else {
+#pragma unroll
+                            for (int i = 0; i < MB; ++i) {
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) issue(i, h);
+                            }
                             }
                             }
                         }
                         if (PAIR) umma_commit2(b_empty(bslot));
-                        else umma_commit(b_empty(bslot));
+                        else if (!(F8_DBG && (g.probe & 4096) && fr != 2)) umma_commit(b_empty(bslot));
                     }
-                    __syncwarp();
+                    if (!(F8_DBG && (g.probe & 8192))) __syncwarp();
                     if (++bslot == SB) { bslot = 0; bphase ^= 1; }
                 }
                 if (elect_one()) { if (PAIR) umma_commit2(a_empty(aslot)); else umma_commit(a_empty(aslot)); }
