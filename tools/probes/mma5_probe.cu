@@ -20,13 +20,17 @@ using namespace f8u;
 constexpr int N = 64, G = 24, RING = 4;
 
 template <int MODE>
-__global__ void __launch_bounds__(64, 1) k(int iters, long long *out) {
+__global__ void __launch_bounds__(64, 1) k(int iters, long long *out, int rnd) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t bar, ring[RING];
     __shared__ uint32_t tslot;
     const uint32_t a_base = f8::smem_u32(smem), b_base = a_base + 48 * 1024;
-    for (int i = threadIdx.x; i < 112 * 1024 / 4; i += blockDim.x) ((uint32_t *)smem)[i] = 0x01010101u * (i & 3);
+    for (int i = threadIdx.x; i < 112 * 1024 / 4; i += blockDim.x) {
+        uint32_t h = (uint32_t)i * 2654435761u + (uint32_t)blockIdx.x * 40503u;      // rnd: pseudo-random bytes (full toggle rate)
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        ((uint32_t *)smem)[i] = rnd == 1 ? h : (rnd == 2 ? 0u : 0x01010101u * (i & 3));
+    }
     if (threadIdx.x == 0) {
         mbar_init(f8::smem_u32(&bar), 1);
         for (int s = 0; s < RING; ++s) mbar_init(f8::smem_u32(&ring[s]), 1);
@@ -104,18 +108,19 @@ __global__ void __launch_bounds__(64, 1) k(int iters, long long *out) {
 static long long *dout;
 
 template <int MODE>
-void run() {
+void run(int rnd = 0) {
     const int iters = 500;
     CK(cudaFuncSetAttribute(k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024));
     for (int rep = 0; rep < 2; ++rep) {
-        k<MODE><<<148, 64, 130 * 1024>>>(iters, dout);
+        k<MODE><<<148, 64, 130 * 1024>>>(iters, dout, rnd);
         CK(cudaDeviceSynchronize());
     }
     std::vector<long long> h(148);
     CK(cudaMemcpy(h.data(), dout, 148 * 8, cudaMemcpyDeviceToHost));
     long long mx = 0;
     for (auto v : h) mx = v > mx ? v : mx;
-    printf("mode %3d [%s%s%s%s%s%s]: %7.1f cycles/burst (back-to-back %d) -> +%.0f per stage boundary\n", MODE, MODE & 1 ? "commit " : "",
+    printf("data=%s mode %3d [%s%s%s%s%s%s]: %7.1f cycles/burst (back-to-back %d) -> +%.0f per stage boundary\n",
+           rnd == 1 ? "random" : (rnd == 2 ? "zeros" : "pattern"), MODE, MODE & 1 ? "commit " : "",
            MODE & 2 ? "wait " : "", MODE & 4 ? "fence " : "", MODE & 8 ? "warp+elect " : "", MODE & 16 ? "descs " : "",
            MODE & 32 ? "syncwarp " : (MODE & 128 ? "ld.shared " : (MODE & 256 ? "scout+bar.sync " : "")), (double)mx / iters, G * 48, (double)mx / iters - G * 48);
 }
@@ -123,5 +128,6 @@ void run() {
 int main() {
     CK(cudaMalloc(&dout, 256 * sizeof(long long)));
     run<0>(); run<1>(); run<3>(); run<7>(); run<16>(); run<8>(); run<9>(); run<11>(); run<15>(); run<31>(); run<63>(); run<23>(); run<128 + 1>(); run<128 + 9>(); run<256 + 9>(); run<256 + 8 + 1 + 4 + 16>();
+    run<0>(1); run<0>(2); run<9>(1); run<256 + 8 + 1 + 4 + 16>(1); run<31>(1);
     return 0;
 }
