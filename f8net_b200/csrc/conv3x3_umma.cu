@@ -30,10 +30,16 @@
 // Persistent CTA, 1 per SM, 512 TMEM columns = 2 accumulator sets x MB segments x BN columns
 // (BN = 64: 4 segments, BN = 128: 2):
 //   warps 0-15 epilogue (TMEM read rate and the exact integer requantisation bound it: 16 warps)
-//   | warp 16 patch loader (TMA, one lane per box) | warp 17: one elected lane issues the MMAs
-//   | warp 18 lane 0 weight-stage loader (cp.async.bulk).
+//   | warp 16 patch loader (TMA, one lane per box) | warps 17, 19: MMA issuers (one elected lane each),
+//   alternating weight stages | warp 18 lane 0 weight-stage loader (cp.async.bulk).
+// Two MMA warps because the tensor pipe does not run ahead of the issuing thread (it queues ~4 MMAs,
+// tools/probes/mma4_probe.cu) and a stage boundary costs the issuing warp 500-700 cycles of plain
+// instruction latency (commit, ring counters, barrier wait, descriptors, elect / reconvergence;
+// profiles/r02_mma_loop_experiments.md): with one issuer the pipe idles for a third of every stage.
+// The two warps take the weight stages in turn and pass the turn through a named barrier, so each
+// one's boundary runs under the other's burst.
 // Variants: STRIDE = 2 (four parity-plane tensor maps), DW (depthwise: diagonal 64 x 64 weight
-// blocks, two N = 32 MMAs per tap), PAIR (CTA pairs, cta_group::2; see the kernel).
+// blocks, two N = 32 MMAs per tap).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -74,7 +80,6 @@ struct PGeom {
     const uint8_t *wpack;   // [K_pad/16][wrows][16], k = (r*3+s)*C + c
     int wrows;
     int N, H, W, C;         // H x W = OUTPUT size per image, C = cin_pad (multiple of 64)
-    int Nh;                 // pair mode: images of the first batch half (CTA rank 0); else N
     int Hin, Win;           // input size per image (= H, W for stride 1; 2H, 2W for stride 2)
     int plane_slots;        // slots of one parity plane (stride 1: the only plane)
     int PW;                 // W + 1
@@ -107,15 +112,8 @@ struct PGeom {
         }                                        \
     } while (0)
 
-// PAIR (dense stride 1, BN = 128): the kernel runs as clusters of two CTAs issuing cta_group::2 MMAs
-// (M = 256).  CTA r of a pair works on batch half r (same tile index, hence identical patch
-// geometry and identical shared-memory offsets in both CTAs), holds its own patch and only rows
-// [64 r, 64 r + 64) of every weight tile: per MMA each SM fetches 4 KB of A + 2 KB of B instead of
-// 4 + 4 (the shared-memory port is the bound of the single-CTA form) and the weight stream from
-// L2 is halved.  The leader (rank 0) issues; the peer's MMA warp forwards its "patch / weights
-// landed" barriers to the leader; tcgen05.commit multicasts every release to both CTAs.
-template <int BN, bool A_SIGNED, bool PLAIN_U8, int STRIDE, bool DW, bool PAIR>
-__global__ void __launch_bounds__((epi_warps_for(PLAIN_U8) + 3) * 32, 1)
+template <int BN, bool A_SIGNED, bool PLAIN_U8, int STRIDE, bool DW>
+__global__ void __launch_bounds__((epi_warps_for(PLAIN_U8) + 4) * 32, 1)
 conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant__ TMaps tmaps) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // stride 1: the patch arrives by TMA in the 64-byte-swizzled K-major layout [slot][64 B]
@@ -127,15 +125,16 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     constexpr int EPI_THREADS = EPI_WARPS * 32;
     constexpr int LOADER_WARP0 = EPI_WARPS;
     constexpr int MMA_WARP = EPI_WARPS + 1;       // one TMA warp, one MMA warp, one weight loader:
-    constexpr int WLOAD_WARP = EPI_WARPS + 2;     // 19 warps leave the epilogue a 96-register cap
+    constexpr int WLOAD_WARP = EPI_WARPS + 2;
+    constexpr int MMA_WARP2 = EPI_WARPS + 3;      // 20 warps leave the epilogue a 96-register cap
     constexpr int MB = mb_for(BN);
     constexpr int TM = 128 * MB;
-    constexpr int SB_MAX = PAIR ? 6 : sb_for(BN, PLAIN_U8);     // pair: half-size stages, a longer round trip
+    constexpr int SB_MAX = sb_for(BN, PLAIN_U8);
     const int SB = g.sb;
     constexpr int SA_MAX = sa_for(STRIDE);
     const int SA = g.sa;
     constexpr int A_LAG = a_lag_for(STRIDE);
-    constexpr int BROWS = DW ? 64 : (PAIR ? BN / 2 : BN); // weight rows of a tile held by this CTA (depthwise: one 64-channel group)
+    constexpr int BROWS = DW ? 64 : BN;                   // weight rows of a tile (depthwise: one 64-channel group)
     constexpr int B_TILE = BROWS * 64;                    // one tap
     constexpr int B_STAGE = 3 * B_TILE;                   // one filter row
     constexpr int CW = BN / (EPI_WARPS / 4);               // columns per epilogue warp slice (plain path)
@@ -151,10 +150,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     auto b_empty = [&](int s) { return bar_base + (uint32_t)(2 * SA_MAX + SB_MAX + s) * 8; };
     auto acc_full = [&](int b) { return bar_base + (uint32_t)(2 * SA_MAX + 2 * SB_MAX + b) * 8; };
     auto acc_empty = [&](int b) { return bar_base + (uint32_t)(2 * SA_MAX + 2 * SB_MAX + 2 + b) * 8; };
-    // pair mode, leader side: "the peer's patch / weight stage has landed"
-    auto a_peer = [&](int s) { return bar_base + (uint32_t)(2 * SA_MAX + 2 * SB_MAX + 4 + s) * 8; };
-    auto b_peer = [&](int s) { return bar_base + (uint32_t)(3 * SA_MAX + 2 * SB_MAX + 4 + s) * 8; };
-    constexpr int NBARS = 2 * SA_MAX + 2 * SB_MAX + 4 + (PAIR ? SA_MAX + SB_MAX : 0);
+    constexpr int NBARS = 2 * SA_MAX + 2 * SB_MAX + 4;
     uint8_t *after = smem + SA * a_stage + SB * B_STAGE + ((NBARS * 8 + 15) & ~15);   // bias copy: 16-byte aligned
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(after);
     int32_t *sbias = reinterpret_cast<int32_t *>(after + 16);
@@ -168,11 +164,10 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int total_items = g.n_super * g.ntiles_n;
-    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;           // pair mode: batch half of this CTA
-    const int bid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int nb = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    const int n_loc = PAIR ? (rank ? g.N - g.Nh : g.Nh) : g.N;     // images of this CTA's half
-    const int pix_off = PAIR ? (int)rank * g.Nh * g.H * g.W : 0;   // first output pixel of the half
+    const int bid = (int)blockIdx.x;
+    const int nb = (int)gridDim.x;
+    const int n_loc = g.N;
+    constexpr int pix_off = 0;
     // K loop: dense = every 64-channel group of the input; depthwise = the BN / 64 channel groups
     // of the output tile itself (each through its own diagonal weight block, on its own columns)
     constexpr int GPT = BN / 64;
@@ -187,24 +182,20 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
 
     if (warp == MMA_WARP) {
         if (lane == 0) {
-            for (int s = 0; s < SA; ++s) { mbar_init(a_full(s), TMA ? 1 : LOADERS); mbar_init(a_empty(s), 1); }
+            // a patch / an accumulator set is released (handed on) by BOTH MMA warps: tcgen05.commit covers the
+            // committing thread's own MMAs only, and each warp issues at least one stage of every channel group
+            for (int s = 0; s < SA; ++s) { mbar_init(a_full(s), TMA ? 1 : LOADERS); mbar_init(a_empty(s), 2); }
             for (int p = 0; p < PLANES; ++p) tma_prefetch_desc(&tmaps.m[p]);
             for (int s = 0; s < SB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-            // one arrival per epilogue warp (not 512 serialised atomics); pair mode: both CTAs' warps
-            for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
-            if (PAIR) {
-                for (int s = 0; s < SA; ++s) mbar_init(a_peer(s), 1);
-                for (int s = 0; s < SB; ++s) mbar_init(b_peer(s), 1);
-            }
+            // one arrival per epilogue warp (not 512 serialised atomics)
+            for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 2); mbar_init(acc_empty(b), EPI_WARPS); }
             fence_barrier_init();
         }
         __syncwarp();
-        if (PAIR) tmem_alloc2(f8::smem_u32(tmem_slot), 512);
-        else tmem_alloc(f8::smem_u32(tmem_slot), 512);
+        tmem_alloc(f8::smem_u32(tmem_slot), 512);
     }
     tc_fence_before();
     __syncthreads();
-    if (PAIR) cluster_sync_all();       // the peer's barriers exist before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // The next layer's launch may begin its own prologue as this grid's CTAs retire; everything
@@ -247,7 +238,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                     if (skip_tma) {
                     } else if (PLANES == 1) {
                         if (lane < nbox)
-                            tma_load_4d(smem_base + slot * a_stage + lane * BS * 64, &tmaps.m[PAIR ? rank : 0u], (cg0 + cg) * 64, -1,
+                            tma_load_4d(smem_base + slot * a_stage + lane * BS * 64, &tmaps.m[0], (cg0 + cg) * 64, -1,
                                         yy - 1, img, a_full(slot));
                     } else {
                         // box b of plane p: the same padded rows of every parity plane
@@ -271,16 +262,21 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
         }
     } else if (warp == WLOAD_WARP) {
         // =========================== weight-tile loader ===========================
-        if (lane == 0) {
+        // The whole warp runs the loop; lane l issues bulk copy l of the stage (12 copies: 3 taps x 4
+        // sixteen-byte K chunks, each BROWS rows).  One lane issuing all twelve was THE bound of this kernel:
+        // under the tensor core's operand traffic every cp.async.bulk issue takes ~130 cycles, so a stage
+        // took the loader ~1600 cycles -- longer than its 1152 cycles of MMAs (profiles/r02_mma_loop_experiments.md).
+        {
             int slot = 0, phase = 0;
             long long w_bempty = 0;
             const long long t_begin = clock64();
+            const int fs = lane >> 2, j = lane & 3;             // this lane's copy: tap column fs, K chunk j
             for (int it = bid; it < total_items; it += nb) {
                 const int st = it / g.ntiles_n;
-                const int n0 = DW ? 0 : (it - st * g.ntiles_n) * BN + (PAIR ? (int)rank * (BN / 2) : 0);
+                const int n0 = DW ? 0 : (it - st * g.ntiles_n) * BN;
                 const int Ck = DW ? 64 : g.C;
                 const int ncg = tile_ncg(it);
-                // depthwise: 64 weight rows per group image, dense: BN rows of the shared image (pair: this CTA's half)
+                // depthwise: 64 weight rows per group image, dense: BN rows of the shared image
                 constexpr uint32_t ROWS_B = (uint32_t)BROWS;
                 for (int cg = 0; cg < ncg; ++cg) {
                     const uint8_t *wsrc = g.wpack + (DW ? (size_t)(tile_group0(it) + cg) * (36 * 64 * 16) : 0);
@@ -288,37 +284,41 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                     for (int fr = 0; fr < 3; ++fr) {
                         F8_TIMED_WAIT(w_bempty, mbar_wait(b_empty(slot), phase ^ 1));
                         const uint32_t sb = sb_base + slot * B_STAGE;
-                        const bool skip_w = F8_DBG && (g.probe & 512) && it != bid;    // probe: stale weights (WRONG results)
-                        mbar_expect_tx(b_full(slot), skip_w ? 0u : 12u * ROWS_B * 16u);
-                        mbar_arrive(b_full(slot));
-                        if (skip_w) { if (++slot == SB) { slot = 0; phase ^= 1; } continue; }
-#pragma unroll
-                        for (int fs = 0; fs < 3; ++fs) {
+                        if (lane == 0) {
+                            mbar_expect_tx(b_full(slot), 12u * ROWS_B * 16u);
+                            mbar_arrive(b_full(slot));
+                        }
+                        __syncwarp();
+                        if (lane < 12) {
                             const size_t kc = (size_t)((fr * 3 + fs) * Ck + kcg * 64) >> 4;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                bulk_g2s(sb + fs * B_TILE + j * (BROWS * 16), wsrc + ((kc + j) * g.wrows + n0) * 16,
-                                         ROWS_B * 16u, b_full(slot));
+                            bulk_g2s(sb + fs * B_TILE + j * (BROWS * 16), wsrc + ((kc + j) * g.wrows + n0) * 16, ROWS_B * 16u,
+                                     b_full(slot));
                         }
                         if (++slot == SB) { slot = 0; phase ^= 1; }
                     }
                 }
             }
-            if (g.stats) {
+            if (F8_DBG && g.stats && lane == 0) {
                 g.stats[blockIdx.x * 16 + 3] = clock64() - t_begin;
                 g.stats[blockIdx.x * 16 + 4] = w_bempty;
             }
         }
-    } else if (warp == MMA_WARP) {
-        // =========================== MMA issuer ===================================
-        // The whole warp runs the loop (uniform control flow); one elected lane issues.
+    } else if (warp == MMA_WARP || warp == MMA_WARP2) {
+        // =========================== MMA issuers ==================================
+        // Two warps, each running the whole loop (uniform control flow, one elected lane issues); warp p owns
+        // the weight stages with (running stage number) % 2 == p.  A stage may only be issued after the
+        // previous one HAS BEEN ISSUED (accumulation order inside a tile): the turn passes through two named
+        // barriers (bar.arrive after a warp's stage, bar.sync before the other's) -- no shared-memory access.
+        // Everything else of a stage boundary (commit, ring counters, the mbarrier waits for the stage after
+        // next, descriptors) then runs while the OTHER warp's burst keeps the tensor pipe busy.
         // Descriptor high words are loop constants, low words advance by 32-bit adds.
+        const int me = warp == MMA_WARP ? 0 : 1;
         constexpr uint32_t idesc = instr_desc(A_SIGNED, BN);
         constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);          // SBO = 128 B, version 1
         // TMA patch: SWIZZLE_64B (layout type 4), SBO = 8 rows x 64 B, LBO unused
-        constexpr uint32_t desc_hi_a = TMA ? ((512u >> 4) | (1u << 14) | (4u << 29)) : desc_hi;
-        constexpr uint32_t SLOT16 = TMA ? 4u : 1u;                      // one slot in descriptor units of 16 B
-        const uint32_t a_lbo_field = TMA ? (1u << 16) : ((lbo_a >> 4) << 16);
+        constexpr uint32_t desc_hi_a = (512u >> 4) | (1u << 14) | (4u << 29);
+        constexpr uint32_t SLOT16 = 4u;                                 // one slot in descriptor units of 16 B
+        constexpr uint32_t a_lbo_field = 1u << 16;
         constexpr uint32_t b_lbo_field = ((uint32_t)(BROWS * 16) >> 4) << 16;
         int aslot = 0, aphase = 0, bslot = 0, bphase = 0, buf = 0, acc_phase = 0;
         // start-address offsets of the taps in descriptor units (16 B = one slot)
@@ -335,133 +335,97 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
         long long w_acc = 0, w_a = 0, w_b = 0;
         const long long t_begin = clock64();
         long long t_first_a = 0;
-        if (PAIR && rank != 0) {
-            // peer of a pair: no MMAs to issue; tell the leader when this CTA's patch / weight stages land
-            for (int it = bid; it < total_items; it += nb) {
-                const int ncg = tile_ncg(it);
-                for (int cg = 0; cg < ncg; ++cg) {
-                    mbar_wait(a_full(aslot), aphase);
-                    if (lane == 0) mbar_arrive_cluster(mapa_rank(a_peer(aslot), 0u));
-                    for (int fr = 0; fr < 3; ++fr) {
-                        mbar_wait(b_full(bslot), bphase);
-                        if (lane == 0) mbar_arrive_cluster(mapa_rank(b_peer(bslot), 0u));
-                        if (++bslot == SB) { bslot = 0; bphase ^= 1; }
-                    }
-                    if (++aslot == SA) { aslot = 0; aphase ^= 1; }
-                }
-            }
-        } else
+        int turn = 0;                     // whose stage is next (running stage number mod 2)
+        bool started = false;             // this warp has issued a stage before (the other warp's turn signal exists)
         for (int it = bid; it < total_items; it += nb) {
-            if (PAIR) F8_TIMED_WAIT(w_acc, mbar_wait_cluster(acc_empty(buf), acc_phase ^ 1));
-            else F8_TIMED_WAIT(w_acc, mbar_wait(acc_empty(buf), acc_phase ^ 1));
-            tc_fence_after();
+            bool acc_ready = false;
             const uint32_t tacc = tmem_base + (uint32_t)(buf * MB * BN);
-            int tile_soff = 0;                           // TMA: first slot of the tile inside its box-aligned patch
+            int tile_soff = 0;                           // first slot of the tile inside its box-aligned patch
             const int ncg = tile_ncg(it);
-            if (TMA) {
+            {
                 const int pi0 = (it / g.ntiles_n) * TM;
                 const int Y0 = (int)__umulhi((uint32_t)pi0, g.mPW);
                 const int Yb0 = g.BY == 1 ? Y0 : (int)__umulhi((uint32_t)Y0, g.mBY) * g.BY;
                 tile_soff = pi0 - Yb0 * g.PW;
             }
             for (int cg = 0; cg < ncg; ++cg) {
-                F8_TIMED_WAIT(w_a, mbar_wait(a_full(aslot), aphase));
-                if (PAIR) F8_TIMED_WAIT(w_a, mbar_wait_cluster(a_peer(aslot), aphase));
-                if (F8_DBG && g.stats && t_first_a == 0) t_first_a = clock64();
-                const uint32_t sa = smem_base + aslot * a_stage + (TMA ? (uint32_t)tile_soff * 64u : 0u);
+                bool a_ready = false;
+                const uint32_t sa = smem_base + aslot * a_stage + (uint32_t)tile_soff * 64u;
                 const uint32_t first = (uint32_t)(cg != 0);
                 // depthwise: does this channel group have channels 32..63?
                 const int dw_halves = (DW && ep.cout_pad - (tile_group0(it) + cg) * 64 <= 32) ? 1 : 2;
+                // this warp's last stage of the channel group / of the tile (stages alternate, three per group)
+                const int my_last_fr = ((turn + 2) & 1) == me ? 2 : 1;
 #pragma unroll
                 for (int fr = 0; fr < 3; ++fr) {
-                    if (!(F8_DBG && (g.probe & 1024))) F8_TIMED_WAIT(w_b, mbar_wait(b_full(bslot), bphase));
-                    if (PAIR) F8_TIMED_WAIT(w_b, mbar_wait_cluster(b_peer(bslot), bphase));
-                    if (!(F8_DBG && (g.probe & 2048))) tc_fence_after();
-                    const uint32_t sb = sb_base + bslot * B_STAGE;
-                    const uint32_t a_row = (((sa & 0x3ffffu) >> 4) | a_lbo_field) + tap_row[fr];
-                    const uint32_t b_row = ((sb & 0x3ffffu) >> 4) | b_lbo_field;
-                    if (!DW && F8_DBG && (g.probe & 128)) {
-                        // probe: long runs on one accumulator (segment outermost)
+                    if (turn == me) {
+                        // waits of MY stage: they ran ahead while the other warp was issuing
+                        if (!acc_ready) { F8_TIMED_WAIT(w_acc, mbar_wait(acc_empty(buf), acc_phase ^ 1)); acc_ready = true; }
+                        if (!a_ready) { F8_TIMED_WAIT(w_a, mbar_wait(a_full(aslot), aphase)); a_ready = true; }
+                        F8_TIMED_WAIT(w_b, mbar_wait(b_full(bslot), bphase));
+                        if (F8_DBG && g.stats && t_first_a == 0) t_first_a = clock64();
+                        const uint32_t sb = sb_base + bslot * B_STAGE;
+                        const uint32_t a_row = (((sa & 0x3ffffu) >> 4) | a_lbo_field) + tap_row[fr];
+                        const uint32_t b_row = ((sb & 0x3ffffu) >> 4) | b_lbo_field;
+                        // my turn: the other warp has issued the previous stage (none before the very first one)
+                        if (started || me == 1) turn_wait(me ^ 1);
+                        started = true;
+                        tc_fence_after();
                         if (elect_one()) {
 #pragma unroll
-                            for (int i = 0; i < MB; ++i)
+                            for (int fs = 0; fs < 3; ++fs) {
+                                // slot offset of tap (fr, fs): stride 1: fr*PW + fs; stride 2: parity plane
+                                // ((fr != 1), (fs != 1)) and a one-row / one-column step for fr > 0 / fs > 0
+                                const uint32_t a_lo0 = a_row + (STRIDE == 2 ? (fs == 0 ? tap_col[0] : (fs == 1 ? SLOT16 : tap_col[1]))
+                                                                            : SLOT16 * (uint32_t)fs);
+                                const uint32_t b_lo0 = b_row + (uint32_t)(fs * (B_TILE >> 4));
+                                if constexpr (DW) {
+                                    // diagonal 64 x 64 block: K half h (channels 32h..32h+31) only reaches output
+                                    // columns 32h..32h+31 -> two N = 32 MMAs on disjoint columns (one if the
+                                    // group has no upper half)
+                                    constexpr uint32_t idesc32 = instr_desc(A_SIGNED, 32);
 #pragma unroll
-                                for (int fs = 0; fs < 3; ++fs)
+                                    for (int i = 0; i < MB; ++i) {
 #pragma unroll
-                                    for (int h = 0; h < 2; ++h) {
-                                        const uint32_t a_lo0 = a_row + (STRIDE == 2 ? (fs == 0 ? tap_col[0] : (fs == 1 ? SLOT16 : tap_col[1]))
-                                                                                    : SLOT16 * (uint32_t)fs);
-                                        const uint32_t b_lo0 = b_row + (uint32_t)(fs * (B_TILE >> 4));
-                                        umma_i8_lohi(tacc + (uint32_t)(i * BN), a_lo0 + (uint32_t)(i * 512 + h * 2), desc_hi_a,
-                                                     b_lo0 + (uint32_t)h * ((2 * BROWS * 16) >> 4), desc_hi, idesc,
-                                                     (h | fs | fr) ? 1u : first);
+                                        for (int h = 0; h < 2; ++h)
+                                            if (h < dw_halves)
+                                                umma_i8_lohi(tacc + (uint32_t)(i * BN + 64 * cg + 32 * h),
+                                                             a_lo0 + (uint32_t)(i * 512 + h * 2), desc_hi_a,
+                                                             b_lo0 + (uint32_t)h * (((2 * BROWS * 16) >> 4) + 32u), desc_hi, idesc32,
+                                                             (fs | fr) ? 1u : 0u);
                                     }
-                            umma_commit(b_empty(bslot));
-                        }
-                    } else
-                    if (elect_one()) {
+                                } else {
 #pragma unroll
-                        for (int fs = 0; fs < 3; ++fs) {
-                            if (F8_DBG && (g.probe & 32)) continue;
-                            // slot offset of tap (fr, fs): stride 1: fr*PW + fs; stride 2: parity plane
-                            // ((fr != 1), (fs != 1)) and a one-row / one-column step for fr > 0 / fs > 0
-                            const uint32_t a_lo0 = a_row + (STRIDE == 2 ? (fs == 0 ? tap_col[0] : (fs == 1 ? SLOT16 : tap_col[1]))
-                                                                        : SLOT16 * (uint32_t)fs);
-                            const uint32_t b_lo0 = b_row + (uint32_t)(fs * (B_TILE >> 4));
-                            if constexpr (DW) {
-                                // diagonal 64 x 64 block: K half h (channels 32h..32h+31) only reaches output
-                                // columns 32h..32h+31 -> two N = 32 MMAs on disjoint columns (one if the
-                                // group has no upper half)
-                                constexpr uint32_t idesc32 = instr_desc(A_SIGNED, 32);
+                                    for (int i = 0; i < MB; ++i) {
 #pragma unroll
-                                for (int i = 0; i < MB; ++i) {
-#pragma unroll
-                                    for (int h = 0; h < 2; ++h)
-                                        if (h < dw_halves)
-                                            umma_i8_lohi(tacc + (uint32_t)(i * BN + 64 * cg + 32 * h),
-                                                         a_lo0 + (uint32_t)(i * 512 + h * 2), desc_hi_a,
-                                                         b_lo0 + (uint32_t)h * (((2 * BROWS * 16) >> 4) + 32u), desc_hi, idesc32,
-                                                         (fs | fr) ? 1u : 0u);
+                                        for (int h = 0; h < 2; ++h)
+                                            umma_i8_lohi(tacc + (uint32_t)(i * BN), a_lo0 + (uint32_t)(i * 512 + h * 2), desc_hi_a,
+                                                         b_lo0 + (uint32_t)h * ((2 * BROWS * 16) >> 4), desc_hi, idesc,
+                                                         (h | fs | fr) ? 1u : first);
+                                    }
                                 }
-                            } else {
-                            auto issue = [&](int i, int h) {
-                                    const uint32_t a_lo1 = a_lo0 + (TMA ? (uint32_t)(i * 512 + h * 2)
-                                                                        : (uint32_t)((i * 2048) >> 4) + (uint32_t)h * ((2 * lbo_a) >> 4));
-                                    const uint32_t b_lo1 = b_lo0 + (uint32_t)h * ((2 * BROWS * 16) >> 4);
-                                    if (PAIR) umma_i8_lohi2(tacc + (uint32_t)(i * BN), a_lo1, desc_hi_a, b_lo1, desc_hi,
-                                                            instr_desc_m(A_SIGNED, BN, 256), (h | fs | fr) ? 1u : first);
-                                    else umma_i8_lohi(tacc + (uint32_t)(i * BN), a_lo1, desc_hi_a, b_lo1, desc_hi, idesc,
-                                                      (h | fs | fr) ? 1u : first);
-                            };
-                            if (F8_DBG && (g.probe & 64)) {       // probe: alternate the accumulators every MMA
-#pragma unroll
-                                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                                    for (int i = 0; i < MB; ++i) issue(i, h);
-                            } else {
-#pragma unroll
-                            for (int i = 0; i < MB; ++i) {
-#pragma unroll
-                                for (int h = 0; h < 2; ++h) issue(i, h);
-                            }
-                            }
                             }
                         }
-                        if (PAIR) umma_commit2(b_empty(bslot));
-                        else if (!(F8_DBG && (g.probe & 4096) && fr != 2)) umma_commit(b_empty(bslot));
+                        __syncwarp();
+                        // the next stage (the other warp's) may be issued; none follows the CTA's very last stage
+                        if (!(it + nb >= total_items && cg == ncg - 1 && fr == 2)) turn_pass(me);
+                        if (elect_one()) {
+                            umma_commit(b_empty(bslot));
+                            if (fr == my_last_fr) {
+                                umma_commit(a_empty(aslot));                     // my MMAs on this patch
+                                if (cg == ncg - 1) umma_commit(acc_full(buf));   // my MMAs on this tile
+                            }
+                        }
+                        __syncwarp();
                     }
-                    if (!(F8_DBG && (g.probe & 8192))) __syncwarp();
+                    turn ^= 1;
                     if (++bslot == SB) { bslot = 0; bphase ^= 1; }
                 }
-                if (elect_one()) { if (PAIR) umma_commit2(a_empty(aslot)); else umma_commit(a_empty(aslot)); }
-                __syncwarp();
                 if (++aslot == SA) { aslot = 0; aphase ^= 1; }
             }
-            if (elect_one()) { if (PAIR) umma_commit2(acc_full(buf)); else umma_commit(acc_full(buf)); }
-            __syncwarp();
             if (++buf == 2) { buf = 0; acc_phase ^= 1; }
         }
-        if (F8_DBG && g.stats && lane == 0) {
+        if (F8_DBG && g.stats && lane == 0 && me == 0) {
             g.stats[blockIdx.x * 16 + 5] = clock64() - t_begin;
             g.stats[blockIdx.x * 16 + 6] = w_acc;
             g.stats[blockIdx.x * 16 + 7] = w_a;
@@ -598,19 +562,13 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) {            // this warp's accumulator columns are drained (pair: tell the leader)
-                    if (PAIR && rank != 0) mbar_arrive_cluster(mapa_rank(acc_empty(buf), 0u));
-                    else mbar_arrive(acc_empty(buf));
-                }
+                if (lane == 0) mbar_arrive(acc_empty(buf));      // this warp's accumulator columns are drained
             }
             if (PLAIN_U8) {
                 // every accumulator column this warp owns is in registers (or consumed)
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) {
-                    if (PAIR && rank != 0) mbar_arrive_cluster(mapa_rank(acc_empty(buf), 0u));
-                    else mbar_arrive(acc_empty(buf));
-                }
+                if (lane == 0) mbar_arrive(acc_empty(buf));
             }
             if (++buf == 2) { buf = 0; acc_phase ^= 1; }
         }
@@ -626,11 +584,9 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
 
     tc_fence_before();
     __syncthreads();
-    if (PAIR) cluster_sync_all();       // neither CTA leaves while the pair's MMAs may still read its memory
     if (warp == MMA_WARP) {
         tc_fence_after();
-        if (PAIR) tmem_dealloc2(tmem_base, 512);
-        else tmem_dealloc(tmem_base, 512);
+        tmem_dealloc(tmem_base, 512);
     }
     if (F8_DBG && g.stats && tid == 0) {
         g.stats[blockIdx.x * 16 + 11] = clock64() - t_entry;
@@ -644,14 +600,12 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
 
 namespace {
 
-template <int BN, int STRIDE, bool DW = false, bool PAIR = false>
+template <int BN, int STRIDE, bool DW = false>
 int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     constexpr bool dw = DW;
     constexpr int MB = mb_for(BN);
     constexpr int TM = 128 * MB;
-    constexpr int B_TILE = (DW ? 64 : (PAIR ? BN / 2 : BN)) * 64;
-    const int Nh = PAIR ? (a.n + 1) / 2 : a.n;          // pair mode: each CTA of a pair takes one batch half
-    if (PAIR && a.n < 2) return F8_ERR_UNSUPPORTED;
+    constexpr int B_TILE = (DW ? 64 : BN) * 64;
     constexpr bool TMA = true;
     constexpr int PLANES = STRIDE == 2 ? 4 : 1;
     // an even pitch keeps every box (one padded row of PW slots x 64 B) 128-byte aligned
@@ -700,7 +654,7 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     }
     const bool plain = f8::epilogue_is_plain_u8(ep);
     constexpr int SA_MAX = sa_for(STRIDE);
-    const int SB_MAX = PAIR ? 6 : sb_for(BN, plain);
+    const int SB_MAX = sb_for(BN, plain);
     int SA = SA_MAX, SB = SB_MAX;
     auto smem_for = [&](int sa, int sb) {
         return (size_t)sa * slots_pad * 64 + (size_t)sb * 3 * B_TILE + (3 * SA_MAX + 3 * SB_MAX + 4) * 8 + 16 +
@@ -713,7 +667,7 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     if (smem_bytes > 227 * 1024) return F8_ERR_UNSUPPORTED;
     // the kernel owns all 512 TMEM columns: keep a second CTA off the SM
     const size_t smem_launch = smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes;
-    const long long lin = (long long)Nh * (a.hout + 1) * PW;      // padded linear output space (of one batch half)
+    const long long lin = (long long)a.n * (a.hout + 1) * PW;     // padded linear output space
     // (the magic-number divisions need (lin + TM) * PW < 2^32)
     if ((lin + TM) * (long long)(PW > a.hout + 1 ? PW : a.hout + 1) >= 0xffffffffLL) return F8_ERR_UNSUPPORTED;
     const f8host::DensePack pk = f8host::dense_pack_geometry(a.cin_pad, a.cout_pad, 3, 3);
@@ -726,7 +680,6 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
         g.wrows = 64;
     }
     g.N = a.n; g.H = a.hout; g.W = a.wout; g.C = a.cin_pad;
-    g.Nh = Nh;
     g.Hin = a.hin; g.Win = a.win;
     g.plane_slots = plane_slots;
     g.PW = PW;
@@ -750,18 +703,16 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     int num_sms = 0;
     {
         const int rc = f8host::device_once(once, &num_sms, []() -> int {
-            F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, false, STRIDE, DW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, false, STRIDE, DW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, true, STRIDE, DW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, true, STRIDE, DW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, false, STRIDE, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, false, STRIDE, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, true, STRIDE, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, true, STRIDE, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             return F8_OK;
         });
         if (rc) return rc;
     }
     long long grid = (long long)g.n_super * g.ntiles_n;
-    if (PAIR) grid *= 2;                                  // two CTAs per item
     if (grid > num_sms) grid = num_sms;
-    if (PAIR) grid &= ~1LL;
     static const bool want_stats = f8host::debug_env("F8_STATS") != nullptr;
     static long long *stats_dev = nullptr;
     if (want_stats) {
@@ -785,24 +736,15 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
         const int rc = f8host::encode_tmap_u8_4d(&tmaps.m[p], base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc != F8_OK) return rc;
     }
-    if (PAIR) {     // the second batch half: the same view starting at image Nh
-        const uint8_t *base = static_cast<const uint8_t *>(a.in) + (size_t)Nh * a.hin * a.win * a.cin_pad;
-        const uint64_t dims[4] = {(uint64_t)a.cin_pad, (uint64_t)a.wout, (uint64_t)a.hout, (uint64_t)(a.n - Nh)};
-        const uint64_t strides[3] = {(uint64_t)a.cin_pad, (uint64_t)a.win * a.cin_pad, (uint64_t)a.hin * a.win * a.cin_pad};
-        const uint32_t box[4] = {64u, (uint32_t)PW, (uint32_t)BY, 1u};
-        const int rc = f8host::encode_tmap_u8_4d(&tmaps.m[1], base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
-        if (rc != F8_OK) return rc;
-    }
-    const unsigned th = (epi_warps_for(plain) + 3) * 32;
-    constexpr int CL = PAIR ? 2 : 1;
-    f8host::note_kernel("conv3x3_umma<BN=%d,s%d,%s%s%s>", BN, STRIDE, DW ? "dw" : "dense", plain ? ",plain" : ",generic",
-                        PAIR ? ",pair" : "");
+    const unsigned th = (epi_warps_for(plain) + 4) * 32;
+    constexpr int CL = 1;
+    f8host::note_kernel("conv3x3_umma<BN=%d,s%d,%s%s>", BN, STRIDE, DW ? "dw" : "dense", plain ? ",plain" : ",generic");
     if (a.in_signed) {
-        if (plain) F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, true, true, STRIDE, DW, PAIR>, gr, th, smem_launch, s, CL, g, ep, tmaps));
-        else F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, true, false, STRIDE, DW, PAIR>, gr, th, smem_launch, s, CL, g, ep, tmaps));
+        if (plain) F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, true, true, STRIDE, DW>, gr, th, smem_launch, s, CL, g, ep, tmaps));
+        else F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, true, false, STRIDE, DW>, gr, th, smem_launch, s, CL, g, ep, tmaps));
     } else {
-        if (plain) F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, false, true, STRIDE, DW, PAIR>, gr, th, smem_launch, s, CL, g, ep, tmaps));
-        else F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, false, false, STRIDE, DW, PAIR>, gr, th, smem_launch, s, CL, g, ep, tmaps));
+        if (plain) F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, false, true, STRIDE, DW>, gr, th, smem_launch, s, CL, g, ep, tmaps));
+        else F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, false, false, STRIDE, DW>, gr, th, smem_launch, s, CL, g, ep, tmaps));
     }
     F8_CUDA(cudaGetLastError());
     if (want_stats) {
@@ -865,15 +807,7 @@ int launch_conv3x3_umma(const f8_conv_args &a, cudaStream_t s) {
         a.out_f32 != nullptr)
         return F8_ERR_UNSUPPORTED;
     if (a.stride == 1 && a.hin == a.hout && a.win == a.wout) {
-        if (a.cout_pad > 64) {
-            // CTA pairs (cta_group::2, M = 256): half the weight stream and 3/4 of the operand fetch per SM
-            static const bool pair = getenv("F8_PAIR") != nullptr && atoi(getenv("F8_PAIR")) != 0;
-            if (pair) {
-                const int rc = launch_bn<128, 1, false, true>(a, s);
-                if (rc != F8_ERR_UNSUPPORTED) return rc;
-            }
-            return launch_bn<128, 1>(a, s);
-        }
+        if (a.cout_pad > 64) return launch_bn<128, 1>(a, s);
         return launch_bn<64, 1>(a, s);
     }
     // stride 2: four parity planes of the input; even input sizes only (every F8Net stage)

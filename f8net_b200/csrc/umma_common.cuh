@@ -32,6 +32,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
+// Turn passing between two MMA-issuing warps that alternate pipeline stages (warp p = 0 | 1): after issuing
+// its stage, warp p arrives on named barrier 2 + p; before issuing, the other warp syncs on it.  A named
+// barrier is not a shared-memory access (tools/probes/mma5_probe.cu: 4 cycles against 130-190 for an mbarrier
+// wait under the tensor core's operand traffic).  Arrivals cannot run ahead: between two of warp p's arrivals
+// lies its own sync on the other warp's barrier, which lies after the other warp's sync on p's.
+__device__ __forceinline__ void turn_pass(int p) {
+    if (p == 0) asm volatile("bar.arrive 2, 64;" ::: "memory");
+    else asm volatile("bar.arrive 3, 64;" ::: "memory");
+}
+__device__ __forceinline__ void turn_wait(int p) {
+    if (p == 0) asm volatile("bar.sync 2, 64;" ::: "memory");
+    else asm volatile("bar.sync 3, 64;" ::: "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
