@@ -230,10 +230,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                 for (int cg = 0; cg < ncg; ++cg) {
                     F8_TIMED_WAIT(w_empty, mbar_wait(a_empty(slot), phase ^ 1));
                     const bool skip_tma = F8_DBG && (g.probe & 256) && it != bid;      // probe: stale patch (WRONG results)
-                    if (lane == 0) {
-                        mbar_expect_tx(a_full(slot), skip_tma ? 0u : (uint32_t)(PLANES * nbox * BS * 64));
-                        mbar_arrive(a_full(slot));
-                    }
+                    if (lane == 0) mbar_arrive_expect_tx(a_full(slot), skip_tma ? 0u : (uint32_t)(PLANES * nbox * BS * 64));
                     __syncwarp();
                     if (skip_tma) {
                     } else if (PLANES == 1) {
@@ -284,10 +281,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                     for (int fr = 0; fr < 3; ++fr) {
                         F8_TIMED_WAIT(w_bempty, mbar_wait(b_empty(slot), phase ^ 1));
                         const uint32_t sb = sb_base + slot * B_STAGE;
-                        if (lane == 0) {
-                            mbar_expect_tx(b_full(slot), 12u * ROWS_B * 16u);
-                            mbar_arrive(b_full(slot));
-                        }
+                        if (lane == 0) mbar_arrive_expect_tx(b_full(slot), 12u * ROWS_B * 16u);
                         __syncwarp();
                         if (lane < 12) {
                             const size_t kc = (size_t)((fr * 3 + fs) * Ck + kcg * 64) >> 4;

@@ -53,7 +53,7 @@ class Engine:
     the only mutable state is scratch memory, so use one Engine per stream."""
 
     def __init__(self, net: NetSpec, state_dict, device=None, chunk: int = 256, backend=None,
-                 keep_buffers: bool = False):
+                 keep_buffers: bool = False, fuse_tail=None):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("f8net_b200 needs a CUDA device (sm_100a); there is no CPU path")
@@ -66,8 +66,10 @@ class Engine:
             backend = 1 if self.lib.f8_has_umma(self.device.index) else 0
         # the fused head conv + max-pool launch exists on the tcgen05 backend only
         # (the fused tail launch -- pool + requant + classifier -- likewise)
+        if fuse_tail is None:
+            fuse_tail = int(backend) == 1
         self.plan: Plan = build_plan(net, _to_numpy_sd(state_dict), fuse_head=(int(backend) == 1),
-                                     fuse_tail=(int(backend) == 1), keep_buffers=keep_buffers)
+                                     fuse_tail=bool(fuse_tail), keep_buffers=keep_buffers)
         self.keep_buffers = bool(keep_buffers)
         self._last = None                      # (n, chunk) of the most recent run_device
         self.chunk = int(chunk)
@@ -292,7 +294,7 @@ class Engine:
 
 def compile(model_or_state_dict, arch: Optional[str] = None, head_signed: Optional[bool] = None,
             device=None, chunk: int = 256, backend=None, quant_maxpool: bool = False,
-            keep_buffers: bool = False) -> Engine:
+            keep_buffers: bool = False, fuse_tail=None) -> Engine:
     """Build an Engine from a reference ``IntModel`` (module tree walked for stride / groups /
     input_symmetric), or from its ``state_dict()`` plus the architecture name -- the
     attributes the dict lacks are then re-derived from the architecture (SURVEY.md 8(b));
@@ -310,4 +312,5 @@ def compile(model_or_state_dict, arch: Optional[str] = None, head_signed: Option
         if arch not in ARCHS and not arch.startswith("resnet"):
             raise ValueError(f"unknown arch {arch!r}")
         net = graph_for(arch, bool(head_signed), quant_maxpool=bool(quant_maxpool))
-    return Engine(net, sd, device=device, chunk=chunk, backend=backend, keep_buffers=keep_buffers)
+    return Engine(net, sd, device=device, chunk=chunk, backend=backend, keep_buffers=keep_buffers,
+                  fuse_tail=fuse_tail)

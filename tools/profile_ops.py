@@ -24,10 +24,13 @@ def main():
     ap.add_argument("--chunk", type=int, default=32)
     ap.add_argument("--backend", type=int, default=-1)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--no-fuse-tail", action="store_true")
     a = ap.parse_args()
     hs = synth.HEAD_SIGNED.get(a.arch, False)
     sd = synth.make_state_dict(a.arch, hs)
     kw = {} if a.backend < 0 else {"backend": a.backend}
+    if a.no_fuse_tail:
+        kw["fuse_tail"] = False
     eng = f8net_b200.compile(sd, arch=a.arch, head_signed=hs, chunk=a.chunk, **kw)
     S = eng.net.image_size
     x = torch.randint(0, 128, (a.batch, S, S, 4), dtype=torch.int8 if hs else torch.uint8, device="cuda")
