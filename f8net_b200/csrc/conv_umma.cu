@@ -124,9 +124,13 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
     f8::pdl_wait();
 
     if (TMA_A && warp >= PRODUCER_WARP0 && warp < MMA_WARP) {
-        // =========================== producer: one thread, A by TMA + B bulk copies =====
-        if (tid == PRODUCER_WARP0 * 32) {
-            tma_prefetch_desc(&tmap);
+        // =========================== producer warp: A by TMA + B bulk copies ===========
+        // Under the tensor core's operand traffic every shared-memory-path instruction (mbarrier op, TMA /
+        // bulk-copy issue) takes the issuing warp 130-190 cycles (tools/probes/mma5_probe.cu), and a stage is
+        // only 128-256 cycles of MMAs: the stage is announced with ONE arrive.expect_tx, lane 0 issues the
+        // TMA box and lanes 1-4 the four weight chunks in one warp instruction.
+        if (warp == PRODUCER_WARP0) {
+            if (lane == 0) tma_prefetch_desc(&tmap);
             int slot = 0, phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int mt = t / ntiles_n;
@@ -134,13 +138,14 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
                 for (int kt = 0; kt < g.ktiles; ++kt) {
                     mbar_wait(empty_bar(slot), phase ^ 1);
                     const uint32_t sa = smem_base + slot * STAGE;
-                    mbar_expect_tx(full_bar(slot), A_STAGE + B_STAGE);
-                    mbar_arrive(full_bar(slot));
-                    tma_load_4d(sa, &tmap, kt * BK, mt * BM, 0, 0, full_bar(slot));
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                    if (lane == 0) mbar_arrive_expect_tx(full_bar(slot), A_STAGE + B_STAGE);
+                    __syncwarp();
+                    if (lane == 0) tma_load_4d(sa, &tmap, kt * BK, mt * BM, 0, 0, full_bar(slot));
+                    if (lane >= 1 && lane <= 4) {
+                        const int j = lane - 1;
                         bulk_g2s(sa + A_STAGE + j * B_CHUNK, g.wpack + ((size_t)(kt * 4 + j) * g.wrows + n0) * 16,
                                  B_CHUNK, full_bar(slot));
+                    }
                     if (++slot == S) { slot = 0; phase ^= 1; }
                 }
             }
@@ -502,13 +507,15 @@ conv1x1_res_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const
             if (++aslot == S) aslot = 0;
         }
     } else if (warp == PRODUCER_WARP) {
-        if (lane == 0) {
-            tma_prefetch_desc(&tmap);
-            tma_prefetch_desc(&omap);
-            // resident weights: chunk-major image rows [0, BN) of every 16-byte K chunk
-            mbar_expect_tx(w_full, (uint32_t)w_bytes);
-            mbar_arrive(w_full);
-            for (int kc = 0; kc < g.ktiles * 4; ++kc)
+        {
+            if (lane == 0) {
+                tma_prefetch_desc(&tmap);
+                tma_prefetch_desc(&omap);
+                // resident weights: chunk-major image rows [0, BN) of every 16-byte K chunk
+                mbar_arrive_expect_tx(w_full, (uint32_t)w_bytes);
+            }
+            __syncwarp();
+            for (int kc = lane; kc < g.ktiles * 4; kc += 32)        // one chunk per lane per warp instruction
                 bulk_g2s(w_base + kc * B_CHUNK, g.wpack + (size_t)kc * g.wrows * 16, B_CHUNK, w_full);
             f8::pdl_wait();                     // the activation is the previous launch's output
             int slot = 0, phase = 0;
@@ -520,14 +527,15 @@ conv1x1_res_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const
                 for (int kt = 0; kt < g.ktiles; ++kt) {
                     R_TIMED(st_a, mbar_wait(empty_bar(slot), phase ^ 1));
                     const uint32_t sa = smem_base + slot * STAGE;
-                    mbar_expect_tx(full_bar(slot), (uint32_t)(nseg * A_STAGE));
-                    mbar_arrive(full_bar(slot));
-                    for (int sg = 0; sg < nseg; ++sg)
-                        tma_load_4d(sa + sg * A_STAGE, &tmap, kt * BK, (t * MSEG + sg) * BM, 0, 0, full_bar(slot));
+                    if (lane == 0) mbar_arrive_expect_tx(full_bar(slot), (uint32_t)(nseg * A_STAGE));
+                    __syncwarp();
+                    // lane sg issues the TMA box of segment sg: one warp instruction for the whole stage
+                    if (lane < nseg)
+                        tma_load_4d(sa + lane * A_STAGE, &tmap, kt * BK, (t * MSEG + lane) * BM, 0, 0, full_bar(slot));
                     if (++slot == S) { slot = 0; phase ^= 1; }
                 }
             }
-            if (F8_DBG && stats) { stats[blockIdx.x * 16 + 0] = clock64() - st_t0; stats[blockIdx.x * 16 + 1] = st_a; }
+            if (F8_DBG && stats && lane == 0) { stats[blockIdx.x * 16 + 0] = clock64() - st_t0; stats[blockIdx.x * 16 + 1] = st_a; }
         }
     } else if (warp == MMA_WARP) {
         constexpr uint32_t idesc = instr_desc(A_SIGNED, BN);
