@@ -409,18 +409,25 @@ def e2e_measure(run, args, device, barrier, world):
 
     hx = [torch.randint(lo, hi, (B, 3, S, S), dtype=torch.int32).pin_memory() for _ in range(2)]
     v = timed(hx)
+    raw_images = [int(e.lib.f8_plan_last_raw_images(e._h)) for e in engines]
     del hx
+    import ctypes
+    nthreads = ctypes.c_int(0)
+    isa = eng.lib.f8_host_pack_info(ctypes.byref(nthreads)).decode()
     # run_host repacks the int32 tensor to NHWC4 bytes with the host cores (inside the timed region)
     # and ships those; F8_HOST_PACK_THREADS=0 ships the int32 tensor itself
     host_pack = os.environ.get("F8_HOST_PACK_THREADS", "") != "0"
     e2e = {"value": v, "unit": UNIT,
-           "h2d_bytes_per_step": B * S * S * 4 if host_pack else B * 3 * S * S * 4,
+           "h2d_bytes_per_step": (B * S * S * 4 + 2 * raw_images[0] * S * S * 4) if host_pack else B * 3 * S * S * 4,
            "host_tensor_bytes_per_step": B * 3 * S * S * 4,
            "d2h_bytes_per_step": B * run.classes * 4,
            "input": "pinned int32 NCHW (the reference's tensor), two engines on two streams"
-                    + ("; run_host narrows it to NHWC4 bytes on the host cores (timed) before the copy" if host_pack else ""),
-           "host_bound": "the int32 tensor is 602 KB per image of host-DRAM reads; the narrowing is "
-                         "bound by host memory bandwidth, not by the GPU",
+                    + ("; run_host splits the batch in 16-image sub-batches: the host cores narrow them to NHWC4 bytes from "
+                       "the front (timed), the copy engine ships raw ones from the back, narrowed on the device" if host_pack else ""),
+           "host_narrowing": {"simd": isa, "threads_per_rank": nthreads.value,
+                              "images_shipped_raw_last_step": raw_images, "of": B},
+           "host_bound": "the int32 tensor is 602 KB per image that either a host core or the copy engine must read "
+                         "from host DRAM: this number is bound by host memory bandwidth and PCIe, not by the GPU",
            "timer": "host perf_counter around the loop, stream syncs inside"}
     # the same call fed with decoded uint8 pixels [B,H,W,3]: ToTensor +
     # Normalize + forward_loss's integerisation run on the device, 4x fewer PCIe bytes

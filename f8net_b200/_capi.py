@@ -77,6 +77,8 @@ SYMBOLS = {
     "f8_plan_kernel_name": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]),
     "f8_plan_read_buffer": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp,
                                            ctypes.c_size_t, _vp]),
+    "f8_host_pack_info": (ctypes.c_char_p, [ctypes.POINTER(ctypes.c_int)]),
+    "f8_plan_last_raw_images": (ctypes.c_int, [_vp]),
     "f8_plan_launch_count": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "f8_plan_set_backend": (ctypes.c_int, [_vp, ctypes.c_int]),
     "f8_pack_weights_bytes": (ctypes.c_size_t, [ctypes.c_int] * 7),

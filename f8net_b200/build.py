@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libf8b200.so")
-SOURCES = ["plan.cu", "conv_mma.cu", "conv_umma.cu", "conv3x3_umma.cu", "head_pool2_umma.cu", "head3x3_umma.cu", "dw_conv.cu", "pool_misc.cu"]
-HEADERS = [os.path.join(CSRC, "f8_common.cuh"), os.path.join(CSRC, "umma_common.cuh"), os.path.join(CSRC, "tma_common.cuh"), os.path.join(HERE, "..", "include", "f8b200.h")]
+SOURCES = ["plan.cu", "conv_mma.cu", "conv_umma.cu", "conv3x3_umma.cu", "head_pool2_umma.cu", "head3x3_umma.cu", "dw_conv.cu", "pool_misc.cu", "host_pack.cpp"]
+HEADERS = [os.path.join(CSRC, "f8_common.cuh"), os.path.join(CSRC, "umma_common.cuh"), os.path.join(CSRC, "tma_common.cuh"), os.path.join(CSRC, "host_pack.h"), os.path.join(HERE, "..", "include", "f8b200.h")]
 
 
 def _nvcc():

@@ -15,12 +15,10 @@
 #include <condition_variable>
 #include <mutex>
 #include <thread>
-#if defined(__SSE2__)
-#include <emmintrin.h>
-#endif
 #include <vector>
 
 #include "f8_common.cuh"
+#include "host_pack.h"
 #ifdef F8_WITH_UMMA
 #include "tma_common.cuh"
 #endif
@@ -130,6 +128,9 @@ struct f8_plan {
     uint8_t *host_stage = nullptr;
     size_t host_stage_bytes = 0;
     cudaEvent_t host_stage_free = nullptr;   // recorded after the H2D copy that reads the staging
+    cudaEvent_t dma_idle = nullptr;          // "the copy engine has executed everything enqueued so far"
+    f8hp::Pool *pack_pool = nullptr;         // helper threads of the host-side narrowing (owned)
+    int last_raw_images = 0;                 // images of the last run_host the copy engine shipped un-narrowed
     std::vector<std::string> kernel_names;   // per op: the kernel template of the last f8_plan_profile
 };
 
@@ -326,6 +327,8 @@ extern "C" void f8_plan_destroy(f8_plan *plan) {
     if (plan->lut_dev) cudaFree(plan->lut_dev);
     if (plan->host_stage) cudaFreeHost(plan->host_stage);
     if (plan->host_stage_free) cudaEventDestroy(plan->host_stage_free);
+    if (plan->dma_idle) cudaEventDestroy(plan->dma_idle);
+    delete plan->pack_pool;
     delete plan;
 }
 
@@ -576,114 +579,92 @@ static int plan_run_impl(f8_plan *plan, const void *x_dev, int x_layout, int n,
     return F8_OK;
 }
 
-// int32 NCHW [n,3,hw] -> NHWC4 bytes (channel 3 = 0) on the host, rows [r0, r1) of the n*h image rows.
-// Keeps the low byte of every value, exactly what convert_input_kernel does on the device: the
-// reference's tensor holds 8-bit-range integers (fix_train.py:682-692), so 3 of every 4 bytes that
-// would cross PCIe carry nothing.
-static void pack_rows_nchw_i32(const int32_t *x, uint8_t *dst, int h, int w, long long r0, long long r1) {
-    const size_t hw = (size_t)h * w;
-    for (long long r = r0; r < r1; ++r) {
-        const long long img = r / h;
-        const int y = (int)(r - img * h);
-        const int32_t *c0 = x + (size_t)img * 3 * hw + (size_t)y * w;
-        const int32_t *c1 = c0 + hw, *c2 = c1 + hw;
-        uint32_t *o = reinterpret_cast<uint32_t *>(dst) + (size_t)r * w;
-        int i = 0;
-#if defined(__SSE2__)
-        // streaming stores: the staging is written once and read by the DMA engine, never by this core
-        if ((reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
-            const __m128i m = _mm_set1_epi32(0xff);
-            for (; i + 4 <= w; i += 4) {
-                const __m128i a = _mm_and_si128(_mm_loadu_si128(reinterpret_cast<const __m128i *>(c0 + i)), m);
-                const __m128i b = _mm_and_si128(_mm_loadu_si128(reinterpret_cast<const __m128i *>(c1 + i)), m);
-                const __m128i c = _mm_and_si128(_mm_loadu_si128(reinterpret_cast<const __m128i *>(c2 + i)), m);
-                _mm_stream_si128(reinterpret_cast<__m128i *>(o + i),
-                                 _mm_or_si128(a, _mm_or_si128(_mm_slli_epi32(b, 8), _mm_slli_epi32(c, 16))));
-            }
-        }
-#endif
-        for (; i < w; ++i)
-            o[i] = ((uint32_t)c0[i] & 0xffu) | (((uint32_t)c1[i] & 0xffu) << 8) | (((uint32_t)c2[i] & 0xffu) << 16);
-    }
-#if defined(__SSE2__)
-    _mm_sfence();
-#endif
-}
-
-// Persistent helper threads for the host-side repack (spawning 15 threads per call costs a fifth of
-// the 2 ms the repack itself takes).  Workers sleep on a condition variable between calls and are
-// detached: they never touch CUDA and die with the process.
-class PackPool {
-  public:
-    void run(const int32_t *x, uint8_t *dst, int h, int w, long long rows, int T) {
-        std::lock_guard<std::mutex> serial(call_);          // one repack at a time
-        if (T > 1) {
-            std::unique_lock<std::mutex> lk(m_);
-            while ((int)workers_ < T - 1) {
-                std::thread(&PackPool::worker, this, (int)workers_ + 1).detach();
-                ++workers_;
-            }
-            x_ = x; dst_ = dst; h_ = h; w_ = w; rows_ = rows; T_ = T;
-            pending_ = T - 1;
-            ++gen_;
-            lk.unlock();
-            work_.notify_all();
-        }
-        pack_rows_nchw_i32(x, dst, h, w, 0, rows / T);
-        if (T > 1) {
-            std::unique_lock<std::mutex> lk(m_);
-            done_.wait(lk, [&] { return pending_ == 0; });
-        }
-    }
-
-  private:
-    void worker(int id) {
-        unsigned long long seen = 0;
-        for (;;) {
-            std::unique_lock<std::mutex> lk(m_);
-            work_.wait(lk, [&] { return gen_ != seen; });
-            seen = gen_;
-            if (id >= T_) continue;                         // not needed for this call
-            const int32_t *x = x_;
-            uint8_t *dst = dst_;
-            const int h = h_, w = w_, T = T_;
-            const long long rows = rows_;
-            lk.unlock();
-            pack_rows_nchw_i32(x, dst, h, w, rows * id / T, rows * (id + 1) / T);
-            lk.lock();
-            if (--pending_ == 0) done_.notify_one();
-        }
-    }
-    std::mutex call_, m_;
-    std::condition_variable work_, done_;
-    size_t workers_ = 0;
-    const int32_t *x_ = nullptr;
-    uint8_t *dst_ = nullptr;
-    int h_ = 0, w_ = 0, T_ = 0, pending_ = 0;
-    long long rows_ = 0;
-    unsigned long long gen_ = 0;
-};
-
-static PackPool &pack_pool() {
-    static PackPool *pool = new PackPool;                   // never destroyed: its threads outlive main()
-    return *pool;
-}
-
+// ---------------------------------------------------------------------------------------
+// Host side of the reference-facing call (host_pack.cpp: SIMD narrowing, per-plan helper threads)
+// ---------------------------------------------------------------------------------------
 extern "C" int f8_pack_input_host(const int32_t *x, int n, int h, int w, void *dst, int threads) {
     if (!x || !dst || n <= 0 || h <= 0 || w <= 0) { set_error("pack_input_host: bad arguments"); return F8_ERR_ARG; }
-    const long long rows = (long long)n * h;
-    const int T = (int)std::min<long long>(std::max(1, threads), std::max<long long>(1, rows / 64));
-    pack_pool().run(x, static_cast<uint8_t *>(dst), h, w, rows, T);
+    static f8hp::Pool *pool = new f8hp::Pool;                // standalone entry point: one process-wide pool
+    pool->run(x, static_cast<uint8_t *>(dst), h, w, 0, (long long)n * h, threads);
     return F8_OK;
 }
 
-static int host_pack_threads() {
-    static const int t = [] {
-        if (const char *e = getenv("F8_HOST_PACK_THREADS")) return std::max(0, atoi(e));   // 0 = ship the int32 tensor as is
-        const unsigned hc = std::thread::hardware_concurrency();
-        return (int)std::min(16u, std::max(1u, hc));
-    }();
-    return t;
+extern "C" const char *f8_host_pack_info(int *threads) {
+    if (threads) *threads = f8hp::default_threads();
+    return f8hp::isa_name();
+}
+
+static bool is_pinned_host(const void *p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// F8_IN_NCHW_I32 from host memory.  The tensor holds 8-bit-range integers in int32: 602 KB per image, of which
+// the engine needs 200 KB.  Two resources can turn it into device-resident NHWC4 bytes, and they work AT THE
+// SAME TIME, in sub-batches of 16 images:
+//   * the host cores narrow a sub-batch into pinned staging (SIMD, streaming stores) and its 3.2 MB are copied;
+//   * the copy engine ships a sub-batch as it is (9.6 MB, pinned source only) and a device kernel narrows it.
+// The host takes sub-batches from the front, the copy engine from the back; a raw sub-batch is handed to the
+// copy engine whenever an event shows its queue has drained, so the split follows the measured speeds of the
+// two (many ranks sharing the host cores push it towards the copy engine, a lone rank towards the cores).
+static int stage_int32_input(f8_plan *plan, const int32_t *x_host, int n, uint8_t *x_stage_dev, int nthreads, cudaStream_t s) {
+    const int H = plan->image_h, W = plan->image_w;
+    const size_t img4 = (size_t)H * W * 4, img_raw = (size_t)H * W * 3 * 4;
+    const size_t bytes = (size_t)n * img4;
+    if (plan->host_stage_bytes < bytes) {
+        if (plan->host_stage) { F8_CUDA(cudaStreamSynchronize(s)); F8_CUDA(cudaFreeHost(plan->host_stage)); }
+        plan->host_stage = nullptr;
+        plan->host_stage_bytes = 0;
+        F8_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&plan->host_stage), bytes, cudaHostAllocDefault));
+        plan->host_stage_bytes = bytes;
+    }
+    if (!plan->host_stage_free) {
+        F8_CUDA(cudaEventCreateWithFlags(&plan->host_stage_free, cudaEventDisableTiming));
+        F8_CUDA(cudaEventCreateWithFlags(&plan->dma_idle, cudaEventDisableTiming));
+    } else {
+        F8_CUDA(cudaEventSynchronize(plan->host_stage_free));      // the previous call's copies have read the staging
+    }
+    if (!plan->pack_pool) plan->pack_pool = new f8hp::Pool;
+    constexpr int SUB = 16;
+    static const bool raw_allowed = [] { const char *e = getenv("F8_HOST_RAW_DMA"); return !(e && e[0] == '0'); }();
+    // raw sub-batches land behind the NHWC4 region of the staging buffer (sized for n int32 images)
+    uint8_t *raw_dev = x_stage_dev + bytes;
+    const int raw_cap = (int)(((size_t)n * img_raw - bytes) / img_raw);
+    const bool raw_ok = raw_allowed && n >= 4 * SUB && is_pinned_host(x_host);
+    int lo = 0, hi = n, raw_used = 0;
+    bool have_evt = false;
+    auto ship_raw = [&]() -> int {
+        const int cnt = SUB;
+        hi -= cnt;
+        uint8_t *dst = raw_dev + (size_t)raw_used * img_raw;
+        F8_CUDA(cudaMemcpyAsync(dst, x_host + (size_t)hi * H * W * 3, (size_t)cnt * img_raw, cudaMemcpyHostToDevice, s));
+        F8_CUDA(cudaEventRecord(plan->dma_idle, s));
+        have_evt = true;
+        raw_used += cnt;
+        return f8host::launch_convert_input(reinterpret_cast<const int32_t *>(dst), x_stage_dev + (size_t)hi * img4, cnt, H, W,
+                                            plan->head_signed, s);
+    };
+    if (raw_ok && raw_cap >= SUB) { const int rc = ship_raw(); if (rc) return rc; }
+    while (lo < hi) {
+        const int cnt = hi - lo < SUB ? hi - lo : SUB;
+        plan->pack_pool->run(x_host, plan->host_stage, H, W, (long long)lo * H, (long long)(lo + cnt) * H, nthreads);
+        F8_CUDA(cudaMemcpyAsync(x_stage_dev + (size_t)lo * img4, plan->host_stage + (size_t)lo * img4, (size_t)cnt * img4,
+                                cudaMemcpyHostToDevice, s));
+        lo += cnt;
+        // the copy engine has caught up with everything enqueued so far: give it a raw sub-batch from the back
+        if (raw_ok && hi - lo >= 2 * SUB && raw_used + SUB <= raw_cap && have_evt && cudaEventQuery(plan->dma_idle) == cudaSuccess) {
+            const int rc = ship_raw();
+            if (rc) return rc;
+        } else if (raw_ok) {
+            (void)cudaGetLastError();                       // cudaErrorNotReady from the query is not an error
+            F8_CUDA(cudaEventRecord(plan->dma_idle, s));
+            have_evt = true;
+        }
+    }
+    F8_CUDA(cudaEventRecord(plan->host_stage_free, s));
+    plan->last_raw_images = raw_used;
+    return F8_OK;
 }
 
 extern "C" int f8_plan_run_host(f8_plan *plan, const void *x_host, int x_layout, int n,
@@ -699,24 +680,10 @@ extern "C" int f8_plan_run_host(f8_plan *plan, const void *x_host, int x_layout,
     int cur = -1;
     F8_CUDA(cudaGetDevice(&cur));
     if (cur != plan->device) F8_CUDA(cudaSetDevice(plan->device));
-    const int nthreads = host_pack_threads();
+    const int nthreads = f8hp::default_threads();
     if (x_layout == F8_IN_NCHW_I32 && nthreads > 0) {
-        // repack to the engine-native NHWC4 bytes with the host cores, ship a third of the bytes
-        const size_t bytes = (size_t)n * plan->image_h * plan->image_w * 4;
-        if (plan->host_stage_bytes < bytes) {
-            if (plan->host_stage) { F8_CUDA(cudaStreamSynchronize(s)); F8_CUDA(cudaFreeHost(plan->host_stage)); }
-            plan->host_stage = nullptr;
-            plan->host_stage_bytes = 0;
-            F8_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&plan->host_stage), bytes, cudaHostAllocDefault));
-            plan->host_stage_bytes = bytes;
-        }
-        if (!plan->host_stage_free) F8_CUDA(cudaEventCreateWithFlags(&plan->host_stage_free, cudaEventDisableTiming));
-        else F8_CUDA(cudaEventSynchronize(plan->host_stage_free));      // the previous copy has read the staging
-        const long long rows = (long long)n * plan->image_h;
-        const int T = (int)std::min<long long>(nthreads, std::max<long long>(1, rows / 64));
-        pack_pool().run(static_cast<const int32_t *>(x_host), plan->host_stage, plan->image_h, plan->image_w, rows, T);
-        F8_CUDA(cudaMemcpyAsync(x_stage_dev, plan->host_stage, bytes, cudaMemcpyHostToDevice, s));
-        F8_CUDA(cudaEventRecord(plan->host_stage_free, s));
+        const int rc0 = stage_int32_input(plan, static_cast<const int32_t *>(x_host), n, static_cast<uint8_t *>(x_stage_dev), nthreads, s);
+        if (rc0) return rc0;
         x_layout = F8_IN_NHWC4_8;
     } else {
         F8_CUDA(cudaMemcpyAsync(x_stage_dev, x_host, x_img * (size_t)n, cudaMemcpyHostToDevice, s));
@@ -830,6 +797,8 @@ extern "C" int f8_plan_read_buffer(const f8_plan *plan, int buf_index, int n, in
     F8_CUDA(cudaStreamSynchronize(s));
     return F8_OK;
 }
+
+extern "C" int f8_plan_last_raw_images(const f8_plan *plan) { return plan ? plan->last_raw_images : 0; }
 
 extern "C" int f8_plan_kernel_name(const f8_plan *plan, int op_index, char *dst, int cap) {
     if (!plan || !dst || cap <= 0 || op_index < 0 || op_index >= (int)plan->ops.size()) {

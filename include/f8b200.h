@@ -185,11 +185,22 @@ F8_API int f8_plan_set_input_prep(f8_plan *plan, int normalize, int fraclen, con
  * F8_IN_NCHW_I32: the tensor holds 8-bit-range integers (fix_train.py:682-692), so the call first
  * narrows it on the host cores to NHWC4 bytes (the low byte of every value, as the device-side
  * conversion keeps) in a plan-owned pinned staging buffer and copies a third of the bytes; x_host
- * has been fully read when the call returns.  Environment F8_HOST_PACK_THREADS = number of host
- * threads (default min(16, cores); 0 = copy the int32 tensor as is).  One call at a time per plan. */
+ * is read by the host cores AND, when it is pinned, directly by the copy engine: the batch is split in
+ * sub-batches of 16 images which the host narrows from the front while the copy engine ships raw
+ * sub-batches from the back (narrowed by a device kernel), each at its own pace.  With sync = 0 the
+ * tensor must therefore stay unmodified until `stream` has executed the call's work.  Environment:
+ * F8_HOST_PACK_THREADS = host threads (default min(16, usable cores / LOCAL_WORLD_SIZE); 0 = copy the
+ * int32 tensor as is), F8_HOST_RAW_DMA=0 = host narrowing only.  One call at a time per plan. */
 F8_API int f8_plan_run_host(f8_plan *plan, const void *x_host, int x_layout, int n, float *logits_host,
                      void *x_stage_dev, float *logits_dev, void *workspace_dev,
                      size_t workspace_bytes, int chunk, int sync, void *stream);
+
+/* How the host side of f8_plan_run_host narrows int32 inputs on this machine: returns the SIMD body
+ * ("avx512" | "avx2" | "sse2" | "scalar"), *threads = helper threads per plan. */
+F8_API const char *f8_host_pack_info(int *threads);
+/* Images of the plan's most recent f8_plan_run_host(F8_IN_NCHW_I32) that the copy engine shipped
+ * un-narrowed (the rest were narrowed by the host cores). */
+F8_API int f8_plan_last_raw_images(const f8_plan *plan);
 
 /* Measurement aid (the reference's only timing device is a wall-clock decorator,
  * fix_train.py:41-53): one f8_plan_run with a CUDA event pair around every launch on

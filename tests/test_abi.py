@@ -5,6 +5,7 @@ import ctypes
 import os
 import re
 import subprocess
+import sys
 import tempfile
 
 import numpy as np
@@ -183,3 +184,33 @@ def test_pack_input_host_low_bytes_nhwc4(f8lib):
                 assert f8lib.f8_pack_input_host(x.ctypes.data, n, h, w, out.ctypes.data, threads) == 0
                 assert np.array_equal(out, want), (n, h, w, lo, threads)
     assert f8lib.f8_pack_input_host(None, 1, 1, 1, None, 1) != 0
+
+
+@pytest.mark.parametrize("isa", [0, 1, 2, 3])
+def test_pack_input_host_every_simd_body(f8lib, isa):
+    """The scalar / SSE2 / AVX2 / AVX-512 bodies of the host-side narrowing (host_pack.cpp; selected once
+    per process, F8_HOST_PACK_ISA overrides the CPU detection) give the same bytes, also for widths that
+    leave vector tails and outputs that are not vector aligned."""
+    code = (
+        "import numpy as np, ctypes\n"
+        "from f8net_b200 import _capi as C\n"
+        "lib = C.lib()\n"
+        "t = ctypes.c_int(0)\n"
+        "name = lib.f8_host_pack_info(ctypes.byref(t)).decode()\n"
+        "rng = np.random.default_rng(5)\n"
+        "for n, h, w in [(2, 7, 224), (3, 5, 37), (1, 3, 16), (2, 2, 9)]:\n"
+        "    x = rng.integers(-127, 256, (n, 3, h, w)).astype(np.int32)\n"
+        "    want = np.zeros((n, h, w, 4), np.uint8)\n"
+        "    want[..., :3] = (x.transpose(0, 2, 3, 1) & 0xff).astype(np.uint8)\n"
+        "    for off in (0, 4, 16):\n"
+        "        buf = np.full(n * h * w * 4 + 64 + off, 0x55, np.uint8)\n"
+        "        base = (-buf.ctypes.data) % 64 + off\n"
+        "        out = buf[base:base + n * h * w * 4]\n"
+        "        assert lib.f8_pack_input_host(x.ctypes.data, n, h, w, out.ctypes.data, 3) == 0\n"
+        "        assert np.array_equal(out.reshape(n, h, w, 4), want), (n, h, w, off)\n"
+        "print('ISA', name, t.value)\n")
+    env = dict(os.environ, F8_HOST_PACK_ISA=str(isa))
+    r = subprocess.run([sys.executable, "-c", code], env=env, cwd=ROOT, capture_output=True, text=True, timeout=120)
+    if r.returncode != 0 and "Illegal instruction" in r.stderr + str(r.returncode):
+        pytest.skip("this CPU lacks the instruction set")
+    assert r.returncode == 0 and "ISA " + ["scalar", "sse2", "avx2", "avx512"][isa] in r.stdout, (r.stdout, r.stderr[-1500:])
