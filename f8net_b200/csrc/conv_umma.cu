@@ -47,6 +47,11 @@ constexpr int PRODUCERS = 128;
 __host__ __device__ constexpr int threads_for(int bn, bool tma_a) { return (epi_warps_for(bn) + (tma_a ? 2 : 5)) * 32; }
 // ring depth per tile width: ~96-120 KB of operand bytes in flight per CTA
 __host__ __device__ constexpr int stages_for(int bn) { return bn <= 64 ? 8 : (bn <= 128 ? 6 : 5); }
+// TMA path: a ring stage is G K-steps of 64 bytes (G TMA boxes + 4 G weight chunks behind ONE mbarrier pair),
+// so that the MMA warp and the producer warp pay their stage boundary -- several hundred cycles of
+// shared-memory-path latency each, profiles/r02_mma_loop_experiments.md -- once per 2 G MMAs instead of once per 2
+__host__ __device__ constexpr int ksteps_for(int bn, bool tma_a) { return !tma_a ? 1 : (bn == 64 ? 4 : 2); }
+__host__ __device__ constexpr int ring_for(int bn, bool tma_a) { return !tma_a ? stages_for(bn) : (bn == 64 ? 2 : 3); }
 constexpr int A_STAGE = BM * BK;          // 8192 B: [4 chunks][128 rows][16 B]
 constexpr int A_CHUNK = BM * 16;          // 2048 B between K chunks (LBO of A)
 
@@ -61,6 +66,7 @@ struct UGeom {
     int ktiles;            // K_pad / 64
     int row_bytes;         // small-C mode
     int shift_px;          // small-C mode
+    int probe;             // debug build: timing probes (WRONG results)
 };
 
 using namespace f8u;
@@ -81,10 +87,12 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
     constexpr int PRODUCER_WARP0 = EPI_WARPS;     // 4 warps: A gather (+ its thread 0: B bulk copies)
     constexpr int MMA_WARP = EPI_WARPS + (TMA_A ? 1 : 4);   // TMEM alloc, one elected lane issues tcgen05.mma
     constexpr int THREADS = threads_for(BN, TMA_A);
-    constexpr int S = stages_for(BN);
+    constexpr int S = ring_for(BN, TMA_A);
+    constexpr int G = ksteps_for(BN, TMA_A);          // K = 64 steps per ring stage
     constexpr int B_STAGE = BN * BK;
     constexpr int B_CHUNK = BN * 16;
-    constexpr int STAGE = A_STAGE + B_STAGE;
+    constexpr int KSTEP = A_STAGE + B_STAGE;          // one K = 64 step: A tile then B tile
+    constexpr int STAGE = G * KSTEP;
     const uint32_t smem_base = f8::smem_u32(smem);
     // after the ring: full[S] empty[S] acc_full[2] acc_empty[2] | tmem slot | bias[2][BN]
     const uint32_t bar_base = smem_base + S * STAGE;
@@ -135,16 +143,20 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int mt = t / ntiles_n;
                 const int n0 = (t - mt * ntiles_n) * BN;
-                for (int kt = 0; kt < g.ktiles; ++kt) {
+                for (int kt0 = 0; kt0 < g.ktiles; kt0 += G) {
+                    const int kcnt = g.ktiles - kt0 < G ? g.ktiles - kt0 : G;      // K steps of this stage
                     mbar_wait(empty_bar(slot), phase ^ 1);
                     const uint32_t sa = smem_base + slot * STAGE;
-                    if (lane == 0) mbar_arrive_expect_tx(full_bar(slot), A_STAGE + B_STAGE);
+                    const bool skip_b = F8_DBG && (g.probe & 1) && t != (int)blockIdx.x;     // probes: stale operands (WRONG results)
+                    const bool skip_a = F8_DBG && (g.probe & 2) && t != (int)blockIdx.x;
+                    if (lane == 0) mbar_arrive_expect_tx(full_bar(slot), (uint32_t)(kcnt * ((skip_a ? 0 : A_STAGE) + (skip_b ? 0 : B_STAGE))));
                     __syncwarp();
-                    if (lane == 0) tma_load_4d(sa, &tmap, kt * BK, mt * BM, 0, 0, full_bar(slot));
-                    if (lane >= 1 && lane <= 4) {
-                        const int j = lane - 1;
-                        bulk_g2s(sa + A_STAGE + j * B_CHUNK, g.wpack + ((size_t)(kt * 4 + j) * g.wrows + n0) * 16,
-                                 B_CHUNK, full_bar(slot));
+                    // lanes 0..G-1: the TMA box of K step `lane`; lanes 8..8+4G-1: its four weight chunks
+                    if (lane < kcnt && !skip_a) tma_load_4d(sa + lane * KSTEP, &tmap, (kt0 + lane) * BK, mt * BM, 0, 0, full_bar(slot));
+                    if (lane >= 8 && lane < 8 + 4 * kcnt && !skip_b) {
+                        const int ks = (lane - 8) >> 2, j = (lane - 8) & 3;
+                        bulk_g2s(sa + ks * KSTEP + A_STAGE + j * B_CHUNK,
+                                 g.wpack + ((size_t)((kt0 + ks) * 4 + j) * g.wrows + n0) * 16, B_CHUNK, full_bar(slot));
                     }
                     if (++slot == S) { slot = 0; phase ^= 1; }
                 }
@@ -247,16 +259,23 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
             mbar_wait(acc_empty_bar(buf), acc_phase ^ 1);   // epilogue drained this buffer
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
-            for (int kt = 0; kt < g.ktiles; ++kt) {
+            for (int kt0 = 0; kt0 < g.ktiles; kt0 += G) {
+                const int kcnt = g.ktiles - kt0 < G ? g.ktiles - kt0 : G;
                 mbar_wait(full_bar(slot), phase);
                 tc_fence_after();
                 const uint32_t sa = smem_base + slot * STAGE;
                 const uint32_t a_lo = ((sa & 0x3ffffu) >> 4) | a_lbo_field;
                 const uint32_t b_lo = (((sa + A_STAGE) & 0x3ffffu) >> 4) | b_lbo_field;
                 if (elect_one()) {
-                    umma_i8_lohi(tacc, a_lo, desc_hi_a, b_lo, desc_hi, idesc, (uint32_t)(kt != 0));
-                    umma_i8_lohi(tacc, a_lo + a_khalf, desc_hi_a, b_lo + ((2 * B_CHUNK) >> 4),
-                                 desc_hi, idesc, 1u);
+#pragma unroll
+                    for (int j = 0; j < G; ++j) {
+                        if (j < kcnt) {
+                            const uint32_t o = (uint32_t)(j * (KSTEP >> 4));
+                            umma_i8_lohi(tacc, a_lo + o, desc_hi_a, b_lo + o, desc_hi, idesc, (uint32_t)((kt0 + j) != 0));
+                            umma_i8_lohi(tacc, a_lo + o + a_khalf, desc_hi_a, b_lo + o + ((2 * B_CHUNK) >> 4),
+                                         desc_hi, idesc, 1u);
+                        }
+                    }
                     umma_commit(empty_bar(slot));   // frees the stage once these MMAs have read it
                 }
                 __syncwarp();
@@ -792,14 +811,15 @@ int launch_res_p(const UGeom &g, const f8::Epilogue &ep, cudaStream_t s) {
     return F8_OK;
 }
 
-template <int BN>
+template <int BN, bool TMA_A>
 constexpr int smem_bytes_for() {
-    return stages_for(BN) * (A_STAGE + BN * BK) + (2 * stages_for(BN) + 4) * 8 + 16 + 2 * BN * 4 + 1024;
+    return ring_for(BN, TMA_A) * ksteps_for(BN, TMA_A) * (A_STAGE + BN * BK) + (2 * ring_for(BN, TMA_A) + 4) * 8 + 16 +
+           2 * BN * 4 + 1024;
 }
 
 template <int BN, bool A_SIGNED, bool SMALL_C, bool TMA_A>
 int launch_t(const UGeom &g, const f8::Epilogue &ep, cudaStream_t s) {
-    constexpr int smem_bytes = smem_bytes_for<BN>();
+    constexpr int smem_bytes = smem_bytes_for<BN, TMA_A>();
     auto kern = conv_umma_kernel<BN, A_SIGNED, SMALL_C, TMA_A>;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
@@ -870,6 +890,7 @@ int launch_conv_umma(const f8_conv_args &a, cudaStream_t s) {
     g.ktiles = pk.K_pad / BK;
     g.row_bytes = pk.row_bytes;
     g.shift_px = pk.shift_px;
+    if (const char *e = f8host::debug_env("F8_UPROBE")) g.probe = atoi(e);
     f8::Epilogue ep{};
     ep.bias = a.bias;
     ep.carry_in = a.carry_in;
