@@ -9,10 +9,14 @@
 // block's convolutions (fix_resnet.py:28-33, :57-58).
 //
 // Geometry.  TMEM lane = POOLED pixel.  Pooled pixel (p, q) takes the maximum of the nine conv
-// outputs (2p+dy-1, 2q+dx-1), dy, dx in {0,1,2}; each of them is computed for that lane, in its
-// own accumulator columns (2.25x the minimal MACs, in exchange for a pooling that needs no
-// shuffles, no shared-memory staging and no second pass).  Lanes run over the padded pooled index
-// L = 58 p + q of one image (q = 56, 57 are dropped): 128 consecutive L per tile.
+// outputs (2p+dy-1, 2q+dx-1), dy, dx in {0,1,2}.  The six with dx = 1, 2 are computed for that lane,
+// in its own accumulator columns; the three with dx = 0 are conv column 2q-1 = the dx = 2 column of
+// pooled pixel q-1, i.e. of the lane to the left, and arrive by one warp shuffle of that lane's
+// maximum over dy (1.5x the minimal MACs, no shared-memory staging, no second pass).  Lanes run over
+// the padded pooled index L = 58 p + q of one image (q = 56, 57 are dropped) in GROUPS OF EIGHT THAT
+// OVERLAP BY ONE: lane 8g + j of a tile is L = L0 + 7g + j - 1, so that lane j = 0 of every group is
+// a helper (the left neighbour of j = 1, its own result dropped) and no value ever crosses a warp:
+// 112 pooled positions per 128-lane tile.  In the operand descriptor this is SBO = 112 B.
 //
 // The A operand is the raw NHWC4 image, never an im2col copy.  Conv output (2p+dy-1, 2q+dx-1),
 // filter row r reads image row i = 4p + t - 5 (t = 2 dy + r) and the 8 pixels 4q + 2dx - 6 ..
@@ -22,16 +26,16 @@
 // i.e. a K-major SWIZZLE_NONE operand whose "core matrices" overlap: LBO = 16 B (next 16 bytes of
 // the window), SBO = 128 B (8 lanes further).  The three dx need 8-byte granular starts, so the
 // planes are staged twice: copy A with pixel -4 at byte 0 (dx = 1), copy B with pixel -6 at byte 0
-// (dx = 0, and dx = 2 at +16 B).  Copy A arrives by TMA: four boxes per tile (4 planes x 6 rows x
+// (dx = 2 at +16 B).  Copy A arrives by TMA: four boxes per tile (4 planes x 6 rows x
 // 928 B) over the image viewed as (x, k, J, n); every zero of the padding is the TMA
 // out-of-bounds fill.  TMA starts are 16-byte granular, so copy B = copy A moved up by 8 bytes is
 // made by two "shifter" warps, shared memory to shared memory, while the dx = 1 MMAs run.
 //
 // One MMA per image row t serves every dy that uses it (N = 64 |{dy}| columns, weights of filter
-// rows t - 2 dy side by side): 11 MMAs per dx, 33 per tile, into 192 accumulator columns
+// rows t - 2 dy side by side): 11 MMAs per dx, 22 per tile, into 192 accumulator columns
 // [dy0 | dy1 | dy2]; two such column sets alternate between the MMA warp and the epilogue.
-// Epilogue (16 warps: lane group x 16-channel group): running maximum over the three dx phases in
-// registers, then bias, ReLU, float round trip (x86 cvttss2si semantics), carry / 8-bit images.
+// Epilogue (16 warps: lane group x 16-channel group): maximum over dy of the two dx phases in
+// registers, the left neighbour's dx = 2 maximum by shuffle, then bias, ReLU, float round trip (x86 cvttss2si semantics), carry / 8-bit images.
 // max-then-bias equals the reference's bias-then-max unless acc + bias can wrap; the kernel checks
 // the bias range and otherwise applies the bias before the maximum (exact in every case).
 #include <cstdio>
@@ -47,7 +51,8 @@ using namespace f8u;
 constexpr int IMG = 224, POOLED = 56, COUT = 64;
 constexpr int LP = 58;                        // lanes per pooled row (2 dropped)
 constexpr int LANES_IMG = POOLED * LP;        // 3248
-constexpr int TILES_IMG = (LANES_IMG + 127) / 128;   // 26
+constexpr int TILE_L = 112;                   // pooled positions per tile: 16 groups of 8 lanes overlapping by one
+constexpr int TILES_IMG = (LANES_IMG + TILE_L - 1) / TILE_L;   // 29
 constexpr int ROW_BYTES = LP * 16;            // 928: one staged image row (232 pixels)
 constexpr int PLANE_ROWS = 6;
 constexpr int PLANE_BYTES = 5632;             // 6 * 928 = 5568 rounded up to 128
@@ -73,7 +78,7 @@ __host__ __device__ constexpr int w_off(int t) {          // byte offset of row 
 }
 constexpr int W_BYTES = w_off(11);            // 43008
 
-constexpr int OFF_STAGE = 0;
+constexpr int OFF_STAGE = 128;                // the helper lane of a tile's first group reads 16 bytes before its row
 constexpr int OFF_W = OFF_STAGE + NSTAGE * STAGE_BYTES;
 constexpr int OFF_BAR = OFF_W + W_BYTES;
 constexpr int NBARS = 3 * NSTAGE + 4 + 1;     // stage_full, stage_empty, acc_full[2], acc_empty[2], w_full, stageb_full
@@ -172,7 +177,7 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
         int slot = 0, phase = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int img = t / TILES_IMG;
-            const int L0 = (t - img * TILES_IMG) * 128;
+            const int L0 = (t - img * TILES_IMG) * TILE_L;
             const int p0 = L0 / LP;
             mbar_wait(stage_empty(slot), phase ^ 1);
             if (lane == 0) {
@@ -222,7 +227,8 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
         }
     } else if (warp == MMA_WARP) {
         // =========================== MMA issuer ===================================
-        constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);            // SBO = 128 B, version 1
+        constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);            // weights: SBO = 128 B, version 1
+        constexpr uint32_t desc_hi_a = (112u >> 4) | (1u << 14);          // image: SBO = 112 B: groups of 8 lanes overlap by one
         constexpr uint32_t a_lbo = (16u >> 4) << 16;                      // LBO = 16 B: overlapping windows
         mbar_wait(w_full, 0);
         const uint32_t w_lo0 = ((smem_base + OFF_W) & 0x3ffffu) >> 4;
@@ -232,16 +238,16 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
         const long long t_begin = clock64();
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int img = t / TILES_IMG;
-            const int L0 = (t - img * TILES_IMG) * 128;
+            const int L0 = (t - img * TILES_IMG) * TILE_L;
             const int p0 = L0 / LP;
             H2_TIMED(w_stage, mbar_wait(stage_full(slot), phase));
             tc_fence_after();
-            // descriptor start (16-byte units) of lane 0 in copy A, plane 0, row 0
+            // descriptor start (16-byte units) of lane 0 (= position L0 - 1) in copy A, plane 0, row 0
             const uint32_t a_lo0 =
-                (((smem_base + OFF_STAGE + slot * STAGE_BYTES) & 0x3ffffu) >> 4) + (uint32_t)(L0 - p0 * LP);
+                (((smem_base + OFF_STAGE + slot * STAGE_BYTES) & 0x3ffffu) >> 4) + (uint32_t)(L0 - 1 - p0 * LP);
 #pragma unroll
-            for (int dxi = 0; dxi < 3; ++dxi) {
-                constexpr int kDx[3] = {1, 0, 2};        // copy A (dx = 1) first: copy B is still being made
+            for (int dxi = 0; dxi < 2; ++dxi) {
+                constexpr int kDx[2] = {1, 2};           // copy A (dx = 1) first: copy B is still being made
                 const int dx = kDx[dxi];
                 const int buf = ph & 1;
                 if (dxi == 1) { H2_TIMED(w_stageb, mbar_wait(stageb_full(slot), phase)); tc_fence_after(); }
@@ -260,12 +266,12 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
                         const int nt = t_ndy(tt) * COUT;
                         const uint32_t a_off = (uint32_t)(((dx == 1 ? 0 : COPY_BYTES) + k * PLANE_BYTES +
                                                            (a - amin) * ROW_BYTES + (dx == 2 ? 16 : 0)) >> 4);
-                        umma_i8_lohi(tacc + (uint32_t)(t_dy0(tt) * COUT), (a_lo0 + a_off) | a_lbo, desc_hi,
+                        umma_i8_lohi(tacc + (uint32_t)(t_dy0(tt) * COUT), (a_lo0 + a_off) | a_lbo, desc_hi_a,
                                      (w_lo0 + (uint32_t)(w_off(tt) >> 4)) | ((uint32_t)((nt * 16) >> 4) << 16), desc_hi,
                                      instr_desc(A_SIGNED, nt), ti ? 1u : 0u);
                     }
                     umma_commit(acc_full(buf));
-                    if (dxi == 2) umma_commit(stage_empty(slot));
+                    if (dxi == 1) umma_commit(stage_empty(slot));
                 }
                 __syncwarp();
                 ++ph;
@@ -289,18 +295,18 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
         const long long t_begin = clock64();
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int img = t / TILES_IMG;
-            const int L = (t - img * TILES_IMG) * 128 + lg * 32 + lane;
-            const int p = L / LP, q = L - p * LP;
-            const bool valid = p < POOLED && q < POOLED;
+            // lane 8g + j of the tile is pooled position L0 + 7g + j - 1; j = 0 is the group's helper lane
+            const int li = lg * 32 + lane;
+            const int L = (t - img * TILES_IMG) * TILE_L + 7 * (li >> 3) + (li & 7) - 1;
+            const int p = L < 0 ? 0 : L / LP, q = L < 0 ? LP : L - p * LP;
+            const bool valid = (li & 7) != 0 && p < POOLED && q < POOLED;
             // conv row / column -1 is padding of the max-pool, not a conv output
             const bool no_dy0 = p == 0, no_dx0 = q == 0;
-            int32_t m[16];
+            const int32_t ident = safe ? (int32_t)0x80000000 : 0;
+            int32_t m[16];      // maximum over dy of the dx = 1 column, then of everything
+            int32_t m2[16];     // maximum over dy of the dx = 2 column (the right neighbour's dx = 0 column)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) m[i] = safe ? (int32_t)0x80000000 : 0;
-#pragma unroll
-            for (int dxi = 0; dxi < 3; ++dxi) {
-                constexpr int kDx[3] = {1, 0, 2};
-                const int dx = kDx[dxi];
+            for (int dxi = 0; dxi < 2; ++dxi) {
                 const int buf = ph & 1;
                 H2_TIMED(w_full, mbar_wait(acc_full(buf), (ph >> 1) & 1));
                 tc_fence_after();
@@ -313,34 +319,36 @@ head_pool2_kernel(const H2Geom g, const f8::Epilogue ep, const __grid_constant__
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty(buf));     // this warp's columns are in registers
-                // the pool's padding row / column: replace the excluded values by the identity of max
-                // (rare: only lanes of the first pooled row / column, so a branch, not 16 selects)
-                const int32_t ident = safe ? (int32_t)0x80000000 : 0;
+                // the pool's padding row: replace the excluded values by the identity of max
+                // (rare: only lanes of the first pooled row, so a branch, not 16 selects)
                 if (no_dy0) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v0[i] = ident;
                 }
-                if (dx == 0 && no_dx0) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v0[i] = v1[i] = v2[i] = ident;
-                }
+                int32_t (&dst)[16] = dxi == 0 ? m : m2;
                 if (safe) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) m[i] = max(max(m[i], v0[i]), max(v1[i], v2[i]));
+                    for (int i = 0; i < 16; ++i) dst[i] = max(v0[i], max(v1[i], v2[i]));
                 } else {
-                    // bias first (wrapping, like the reference's conv), ReLU through m >= 0; an excluded
+                    // bias first (wrapping, like the reference's conv), ReLU through the identity 0; an excluded
                     // value must stay at the identity, so the bias is skipped for it
-                    const bool skip0 = no_dy0 || (dx == 0 && no_dx0), skip12 = dx == 0 && no_dx0;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const uint32_t b = (uint32_t)b16[i];
-                        const int32_t a0 = skip0 ? 0 : (int32_t)((uint32_t)v0[i] + b);
-                        const int32_t a1 = skip12 ? 0 : (int32_t)((uint32_t)v1[i] + b);
-                        const int32_t a2 = skip12 ? 0 : (int32_t)((uint32_t)v2[i] + b);
-                        m[i] = max(max(m[i], a0), max(a1, a2));
+                        const int32_t a0 = no_dy0 ? 0 : (int32_t)((uint32_t)v0[i] + b);
+                        const int32_t a1 = (int32_t)((uint32_t)v1[i] + b);
+                        const int32_t a2 = (int32_t)((uint32_t)v2[i] + b);
+                        dst[i] = max(max(0, a0), max(a1, a2));
                     }
                 }
                 ++ph;
+            }
+            // dx = 0: conv column 2q - 1 is the dx = 2 column of the lane to the left (same pooled row: q >= 1);
+            // the shuffle never crosses a group of eight, whose first lane is the helper
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int32_t left = __shfl_up_sync(0xffffffffu, m2[i], 1);
+                m[i] = max(m[i], max(m2[i], no_dx0 ? ident : left));
             }
             if (valid) {
                 // .float() max-pool .int() (fix_resnet.py:358-359): the round trip is the identity for

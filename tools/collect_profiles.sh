@@ -1,20 +1,29 @@
 #!/bin/bash
-# Runs on the GPU box (under gpurun): tests, bench lines, per-layer tables, ncu launch list and the
-# ncu --set full capture of one forward pass.  Outputs under gpurun_out/<tag>_*.
-tag=${1:-r01}
+# Round-2 evidence collection on the GPU box (under gpurun).  Everything lands in gpurun_out/<tag>_*; copy what
+# should be judged into profiles/ afterwards (tools/make_profiles.py turns the ncu outputs into summaries).
+#   bash tools/collect_profiles.sh r02 [full]
+tag=${1:-r02}
+full=${2:-}
 out=gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > $out/${tag}_tests.log
-python bench.py > $out/${tag}_bench_resnet18.json 2> $out/${tag}_bench_resnet18.err
-for a in resnet50 mobilenet_v1 mobilenet_v2; do
-  python bench.py --arch $a --no-cpu-baseline > $out/${tag}_bench_$a.json 2> $out/${tag}_bench_$a.err
-done
-python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_reference.json 2>/dev/null
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -n 4 > $out/${tag}_tests.log
+timeout 600 python bench.py --steps 20 --warmup 5 > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_bench_reference.json 2>/dev/null
 for a in resnet18 resnet50 mobilenet_v1 mobilenet_v2; do
-  python tools/profile_ops.py --arch $a --batch 256 --chunk 256 > $out/${tag}_per_layer_$a.txt 2>&1
+  timeout 120 python tools/profile_ops.py --arch $a --batch 256 --chunk 256 > $out/${tag}_per_layer_$a.txt 2>&1
 done
-ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $out/${tag}_resnet18_launches.csv \
-  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > $out/${tag}_ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"umma_kernel|head_pool|pool_fc" -s 63 -c 21 \
-  -o $out/${tag}_dense python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph > $out/${tag}_ncu_full.log 2>&1
+if [ -n "$full" ]; then
+  for a in resnet18 resnet50 mobilenet_v1 mobilenet_v2; do
+    n=$(timeout 120 python tools/one_pass.py --arch $a --count | tail -n 1)
+    # launch list: per-launch gpu time of the second pass (cold caches, serialised: shares, not absolutes)
+    timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s $n -c $n --csv --log-file $out/${tag}_launches_$a.csv \
+      python tools/one_pass.py --arch $a --passes 2 --names $out/${tag}_names_$a.json > $out/${tag}_ncu_launches_$a.log 2>&1
+    # full capture of the same pass
+    timeout 900 ncu --set full --clock-control none --import-source on -s $n -c $n -f -o $out/${tag}_full_$a \
+      python tools/one_pass.py --arch $a --passes 2 > $out/${tag}_ncu_full_$a.log 2>&1
+    timeout 300 ncu -i $out/${tag}_full_$a.ncu-rep --page raw --csv > $out/${tag}_full_$a.csv 2> /dev/null
+    rm -f $out/${tag}_full_$a.ncu-rep          # gpurun brings back at most 64 MiB: keep the CSV export only
+  done
+fi
+du -sh $out
 cat $out/${tag}_tests.log
-cat $out/${tag}_bench_resnet18.json
+cut -c1-300 $out/${tag}_bench_n1.json
