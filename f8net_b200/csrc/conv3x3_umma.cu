@@ -112,7 +112,12 @@ struct PGeom {
         }                                        \
     } while (0)
 
-template <int BN, bool A_SIGNED, bool PLAIN_U8, int STRIDE, bool DW>
+// MC = 2 | 4 (dense stride 1, BN = 128): the kernel runs as clusters of MC CTAs that work on MC different M
+// tiles of the SAME N tile in lock step and share one weight stream: each CTA fetches 1/MC of every weight
+// stage and multicasts it into all MC shared memories (cp.async.bulk ... .multicast::cluster), each issues its
+// own cta_group::1 MMAs, and every stage release is committed to all CTAs' "empty" barriers.  The L2 -> SM
+// weight traffic -- which bounds these layers (590 KB per tile at 512 channels) -- drops to 1/MC.
+template <int BN, bool A_SIGNED, bool PLAIN_U8, int STRIDE, bool DW, int MC>
 __global__ void __launch_bounds__((epi_warps_for(PLAIN_U8) + 4) * 32, 1)
 conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant__ TMaps tmaps) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -163,11 +168,17 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     }
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int total_items = g.n_super * g.ntiles_n;
-    const int bid = (int)blockIdx.x;
-    const int nb = (int)gridDim.x;
+    // MC: the cluster is the scheduling unit; cluster item `it` = (group of CLS super-tiles, N tile), CTA rank r takes
+    // super-tile CLS * group + r (a super-tile past the batch is all padding: zero-filled by the TMA, dropped by the epilogue)
+    constexpr int CLS = MC ? MC : 1;
+    const int total_items = ((g.n_super + CLS - 1) / CLS) * g.ntiles_n;
+    const uint32_t rank = MC ? cluster_ctarank() : 0u;
+    constexpr uint16_t CTA_MASK = (uint16_t)((1u << CLS) - 1u);
+    const int bid = (int)blockIdx.x / CLS;
+    const int nb = (int)gridDim.x / CLS;
     const int n_loc = g.N;
     constexpr int pix_off = 0;
+    auto super_of = [&](int it_) { const int sp = it_ / g.ntiles_n; return MC ? sp * CLS + (int)rank : sp; };
     // K loop: dense = every 64-channel group of the input; depthwise = the BN / 64 channel groups
     // of the output tile itself (each through its own diagonal weight block, on its own columns)
     constexpr int GPT = BN / 64;
@@ -186,7 +197,8 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
             // committing thread's own MMAs only, and each warp issues at least one stage of every channel group
             for (int s = 0; s < SA; ++s) { mbar_init(a_full(s), TMA ? 1 : LOADERS); mbar_init(a_empty(s), 2); }
             for (int p = 0; p < PLANES; ++p) tma_prefetch_desc(&tmaps.m[p]);
-            for (int s = 0; s < SB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+            // MC: a weight stage is overwritten in BOTH CTAs, so both CTAs' MMAs must have released it
+            for (int s = 0; s < SB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), CLS); }
             // one arrival per epilogue warp (not 512 serialised atomics)
             for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 2); mbar_init(acc_empty(b), EPI_WARPS); }
             fence_barrier_init();
@@ -196,6 +208,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    if (MC) cluster_sync_all();         // the peer's barriers exist before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // The next layer's launch may begin its own prologue as this grid's CTAs retire; everything
@@ -217,7 +230,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
             const long long t_begin = clock64();
             const int PW = g.PW, BY = g.BY, BS = g.box_slots;
             for (int it = bid; it < total_items; it += nb) {
-                const int st = it / g.ntiles_n;
+                const int st = super_of(it);
                 const int cg0 = tile_group0(it), ncg = tile_ncg(it);
                 const int pi0 = st * TM;
                 const int Y0 = (int)__umulhi((uint32_t)pi0, g.mPW);
@@ -285,8 +298,12 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                         __syncwarp();
                         if (lane < 12) {
                             const size_t kc = (size_t)((fr * 3 + fs) * Ck + kcg * 64) >> 4;
-                            bulk_g2s(sb + fs * B_TILE + j * (BROWS * 16), wsrc + ((kc + j) * g.wrows + n0) * 16, ROWS_B * 16u,
-                                     b_full(slot));
+                            if (!MC)
+                                bulk_g2s(sb + fs * B_TILE + j * (BROWS * 16), wsrc + ((kc + j) * g.wrows + n0) * 16, ROWS_B * 16u,
+                                         b_full(slot));
+                            else if ((uint32_t)(lane % CLS) == rank)    // my share of the stage, into every CTA of the cluster
+                                bulk_g2s_mc(sb + fs * B_TILE + j * (BROWS * 16), wsrc + ((kc + j) * g.wrows + n0) * 16,
+                                            ROWS_B * 16u, b_full(slot), CTA_MASK);
                         }
                         if (++slot == SB) { slot = 0; phase ^= 1; }
                     }
@@ -337,7 +354,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
             int tile_soff = 0;                           // first slot of the tile inside its box-aligned patch
             const int ncg = tile_ncg(it);
             {
-                const int pi0 = (it / g.ntiles_n) * TM;
+                const int pi0 = super_of(it) * TM;
                 const int Y0 = (int)__umulhi((uint32_t)pi0, g.mPW);
                 const int Yb0 = g.BY == 1 ? Y0 : (int)__umulhi((uint32_t)Y0, g.mBY) * g.BY;
                 tile_soff = pi0 - Yb0 * g.PW;
@@ -404,7 +421,8 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                         // the next stage (the other warp's) may be issued; none follows the CTA's very last stage
                         if (!(it + nb >= total_items && cg == ncg - 1 && fr == 2)) turn_pass(me);
                         if (elect_one()) {
-                            umma_commit(b_empty(bslot));
+                            if (MC) umma_commit_mc(b_empty(bslot), CTA_MASK);     // every CTA's loader writes this slot next
+                            else umma_commit(b_empty(bslot));
                             if (fr == my_last_fr) {
                                 umma_commit(a_empty(aslot));                     // my MMAs on this patch
                                 if (cg == ncg - 1) umma_commit(acc_full(buf));   // my MMAs on this tile
@@ -438,8 +456,8 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
         long long w_full = 0, t_issue = 0, t_wait = 0, t_math = 0, t_store = 0;
         const long long t_begin = clock64();
         for (int it = bid; it < total_items; it += nb) {
-            const int st = it / g.ntiles_n;
-            const int n0 = (it - st * g.ntiles_n) * BN;
+            const int st = super_of(it);
+            const int n0 = (it - (it / g.ntiles_n) * g.ntiles_n) * BN;
             int ncols = ep.cout_pad - n0;
             if (ncols > BN) ncols = BN;
             int32_t *bias_s = sbias + buf * BN;
@@ -527,8 +545,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                     } else {
                         const int it2 = it + nb;
                         if (it2 < total_items) {
-                            const int st2 = it2 / g.ntiles_n;
-                            load_carry(unit_pixel(st2), (it2 - st2 * g.ntiles_n) * BN + cbase, cnext);
+                            load_carry(unit_pixel(super_of(it2)), (it2 - (it2 / g.ntiles_n) * g.ntiles_n) * BN + cbase, cnext);
                         }
                     }
                     const int col = n0 + cbase + 16 * q;
@@ -578,6 +595,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
 
     tc_fence_before();
     __syncthreads();
+    if (MC) cluster_sync_all();         // neither CTA leaves while the peer may still multicast into it / arrive on its barriers
     if (warp == MMA_WARP) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
@@ -594,7 +612,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
 
 namespace {
 
-template <int BN, int STRIDE, bool DW = false>
+template <int BN, int STRIDE, bool DW = false, int MC = 0>
 int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     constexpr bool dw = DW;
     constexpr int MB = mb_for(BN);
@@ -697,16 +715,18 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     int num_sms = 0;
     {
         const int rc = f8host::device_once(once, &num_sms, []() -> int {
-            F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, false, STRIDE, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, false, STRIDE, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, true, STRIDE, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, true, STRIDE, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, false, STRIDE, DW, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, false, STRIDE, DW, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, false, true, STRIDE, DW, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            F8_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<BN, true, true, STRIDE, DW, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             return F8_OK;
         });
         if (rc) return rc;
     }
-    long long grid = (long long)g.n_super * g.ntiles_n;
+    constexpr int CLS = MC ? MC : 1;
+    long long grid = (long long)CLS * ((g.n_super + CLS - 1) / CLS) * g.ntiles_n;
     if (grid > num_sms) grid = num_sms;
+    grid -= grid % CLS;                                   // whole clusters
     static const bool want_stats = f8host::debug_env("F8_STATS") != nullptr;
     static long long *stats_dev = nullptr;
     if (want_stats) {
@@ -731,14 +751,15 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
         if (rc != F8_OK) return rc;
     }
     const unsigned th = (epi_warps_for(plain) + 4) * 32;
-    constexpr int CL = 1;
-    f8host::note_kernel("conv3x3_umma<BN=%d,s%d,%s%s>", BN, STRIDE, DW ? "dw" : "dense", plain ? ",plain" : ",generic");
+    constexpr int CL = CLS;
+    f8host::note_kernel("conv3x3_umma<BN=%d,s%d,%s%s%s>", BN, STRIDE, DW ? "dw" : "dense", plain ? ",plain" : ",generic",
+                        MC == 4 ? ",mc4" : (MC == 2 ? ",mc2" : ""));
     if (a.in_signed) {
-        if (plain) F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, true, true, STRIDE, DW>, gr, th, smem_launch, s, CL, g, ep, tmaps));
-        else F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, true, false, STRIDE, DW>, gr, th, smem_launch, s, CL, g, ep, tmaps));
+        if (plain) F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, true, true, STRIDE, DW, MC>, gr, th, smem_launch, s, CL, g, ep, tmaps));
+        else F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, true, false, STRIDE, DW, MC>, gr, th, smem_launch, s, CL, g, ep, tmaps));
     } else {
-        if (plain) F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, false, true, STRIDE, DW>, gr, th, smem_launch, s, CL, g, ep, tmaps));
-        else F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, false, false, STRIDE, DW>, gr, th, smem_launch, s, CL, g, ep, tmaps));
+        if (plain) F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, false, true, STRIDE, DW, MC>, gr, th, smem_launch, s, CL, g, ep, tmaps));
+        else F8_CUDA(f8host::launch_pdl_cluster(conv3x3_umma_kernel<BN, false, false, STRIDE, DW, MC>, gr, th, smem_launch, s, CL, g, ep, tmaps));
     }
     F8_CUDA(cudaGetLastError());
     if (want_stats) {
@@ -801,7 +822,19 @@ int launch_conv3x3_umma(const f8_conv_args &a, cudaStream_t s) {
         a.out_f32 != nullptr)
         return F8_ERR_UNSUPPORTED;
     if (a.stride == 1 && a.hin == a.hout && a.win == a.wout) {
-        if (a.cout_pad > 64) return launch_bn<128, 1>(a, s);
+        if (a.cout_pad > 64) {
+            // clusters of CTAs sharing the weight stream (F8_MC = 0: single CTAs, 2: pairs, 4: quads)
+            static const int mc = [] { const char *e = getenv("F8_MC"); return e ? atoi(e) : 2; }();
+            if (mc == 4) {
+                const int rc = launch_bn<128, 1, false, 4>(a, s);
+                if (rc != F8_ERR_UNSUPPORTED) return rc;
+            }
+            if (mc >= 2) {
+                const int rc = launch_bn<128, 1, false, 2>(a, s);
+                if (rc != F8_ERR_UNSUPPORTED) return rc;
+            }
+            return launch_bn<128, 1>(a, s);
+        }
         return launch_bn<64, 1>(a, s);
     }
     // stride 2: four parity planes of the input; even input sizes only (every F8Net stage)

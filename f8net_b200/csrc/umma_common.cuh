@@ -161,6 +161,20 @@ __device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
 // arrives on the barrier at this offset in BOTH CTAs of the pair once the pair's MMAs are done
+// cluster of CTAs sharing a weight stream (each CTA issues its own cta_group::1 MMAs):
+// the bulk copy lands at the same offset in BOTH CTAs and completes transaction bytes on both CTAs' mbarriers
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+        : "memory");
+}
+// "the MMAs issued so far have completed" delivered to the same mbarrier of BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(cta_mask)
+                 : "memory");
+}
 __device__ __forceinline__ void umma_commit2(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"((uint16_t)3)
