@@ -76,7 +76,11 @@ using namespace f8u;
 // TMA_A (1x1 stride 1 convolutions and nn.Linear): the A tile of a stage is one
 // TMA box {64 channels, 128 pixels} of the activation seen as a (C, M) matrix, landing in the
 // 64-byte-swizzled K-major layout; rows past M are the out-of-bounds zero fill.
-template <int BN, bool A_SIGNED, bool SMALL_C, bool TMA_A>
+// PLAIN (compile time, TMA path): bias + ReLU + one unsigned right-shift consumer and nothing else -- the epilogue of
+// most point-wise layers.  ncu showed the generic epilogue latency bound on tcgen05.ld (IPC 1.1, long-scoreboard
+// stalls, 11 instructions per output value against the 4.5 the arithmetic needs): the specialised one drops the
+// carry cursor and software-pipelines the TMEM loads one 16-column step ahead.
+template <int BN, bool A_SIGNED, bool SMALL_C, bool TMA_A, bool PLAIN = false>
 __global__ void __launch_bounds__(threads_for(BN, TMA_A), (BN <= 128) ? 2 : 1)
 conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const int ntiles_n,
                  const __grid_constant__ CUtensorMap tmap) {
@@ -296,8 +300,8 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
         constexpr int CW = BN / (EPI_WARPS / 4);
         constexpr int NS = CW / 16;                    // steps per tile for this warp
         const int row = lg * 32 + lane;                // TMEM lane == tile row
-        const bool has_carry = ep.carry_in != nullptr;
-        const bool plain = f8::epilogue_is_plain_u8(ep);
+        const bool has_carry = !PLAIN && ep.carry_in != nullptr;
+        const bool plain = PLAIN || f8::epilogue_is_plain_u8(ep);
         const f8::EpiConst kc = f8::epi_const(ep, has_carry);
         // prefetch cursor: (tile, step) of the carry request two steps ahead of the consumer
         int pf_t = blockIdx.x, pf_s = 0;
@@ -342,6 +346,22 @@ conv_umma_kernel(const UGeom g, const f8::Epilogue ep, const int mtiles, const i
             mbar_wait(acc_full_bar(buf), acc_phase);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * BN);
+            if constexpr (PLAIN) {
+                // two register sets: the load of step s + 1 is in flight while step s is requantised and stored
+                int32_t va[16], vb[16];
+                if (cs * CW < ncols) tmem_ld16(trow + (uint32_t)(cs * CW), va);
+#pragma unroll
+                for (int sidx = 0; sidx < NS; ++sidx) {
+                    const int c0 = cs * CW + 16 * sidx;
+                    if (c0 < ncols) {                           // warp-uniform
+                        tmem_ld_wait();
+                        if (sidx + 1 < NS && c0 + 16 < ncols) tmem_ld16(trow + (uint32_t)(c0 + 16), (sidx & 1) ? va : vb);
+                        if (valid)
+                            f8::epilogue16_plain_u8((sidx & 1) ? vb : va, bias_s + c0,
+                                                    ep.out0 + (size_t)m * ep.cout_pad + n0 + c0, ep.shift0);
+                    }
+                }
+            } else
 #pragma unroll
             for (int sidx = 0; sidx < NS; ++sidx) {
                 const int c0 = cs * CW + 16 * sidx;
@@ -817,10 +837,10 @@ constexpr int smem_bytes_for() {
            2 * BN * 4 + 1024;
 }
 
-template <int BN, bool A_SIGNED, bool SMALL_C, bool TMA_A>
+template <int BN, bool A_SIGNED, bool SMALL_C, bool TMA_A, bool PLAIN = false>
 int launch_t(const UGeom &g, const f8::Epilogue &ep, cudaStream_t s) {
     constexpr int smem_bytes = smem_bytes_for<BN, TMA_A>();
-    auto kern = conv_umma_kernel<BN, A_SIGNED, SMALL_C, TMA_A>;
+    auto kern = conv_umma_kernel<BN, A_SIGNED, SMALL_C, TMA_A, PLAIN>;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     if (TMA_A) {
@@ -847,7 +867,8 @@ int launch_t(const UGeom &g, const f8::Epilogue &ep, cudaStream_t s) {
     const int per_sm = (BN <= 128) ? 2 : 1;
     long long grid = (long long)num_sms * per_sm;
     if (grid > total) grid = total;
-    f8host::note_kernel("conv_umma<BN=%d,%s,k%ds%d>", BN, SMALL_C ? "small_c" : (TMA_A ? "tma_a" : "gather"), g.kh, g.stride);
+    f8host::note_kernel("conv_umma<BN=%d,%s%s,k%ds%d>", BN, SMALL_C ? "small_c" : (TMA_A ? "tma_a" : "gather"), PLAIN ? ",plain" : "",
+                        g.kh, g.stride);
     F8_CUDA(f8host::launch_pdl(kern, (unsigned)grid, threads_for(BN, TMA_A), smem_bytes, s, g, ep, mtiles, ntn, tmap));
     F8_CUDA(cudaGetLastError());
     return F8_OK;
@@ -856,6 +877,8 @@ int launch_t(const UGeom &g, const f8::Epilogue &ep, cudaStream_t s) {
 template <int BN>
 int launch_bn(const UGeom &g, const f8::Epilogue &ep, bool sgn, bool small_c, bool tma_a, cudaStream_t s) {
     if (small_c) return sgn ? launch_t<BN, true, true, false>(g, ep, s) : launch_t<BN, false, true, false>(g, ep, s);
+    if (tma_a && f8::epilogue_is_plain_u8(ep))
+        return sgn ? launch_t<BN, true, false, true, true>(g, ep, s) : launch_t<BN, false, false, true, true>(g, ep, s);
     if (tma_a) return sgn ? launch_t<BN, true, false, true>(g, ep, s) : launch_t<BN, false, false, true>(g, ep, s);
     return sgn ? launch_t<BN, true, false, false>(g, ep, s) : launch_t<BN, false, false, false>(g, ep, s);
 }
