@@ -296,7 +296,12 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                         const uint32_t sb = sb_base + slot * B_STAGE;
                         if (lane == 0) mbar_arrive_expect_tx(b_full(slot), 12u * ROWS_B * 16u);
                         __syncwarp();
-                        if (lane < 12) {
+                        if (DW) {
+                            // depthwise: the group's diagonal weight image is chunk-major with 64 rows, so the twelve
+                            // chunks of a filter row are 12 KB of CONTIGUOUS memory in the order shared memory wants:
+                            // one bulk copy (the copy unit retires ~one copy per 100 cycles whatever lane issues it)
+                            if (lane == 0) bulk_g2s(sb, wsrc + (size_t)(fr * 3) * 4 * 64 * 16, 12u * ROWS_B * 16u, b_full(slot));
+                        } else if (lane < 12) {
                             const size_t kc = (size_t)((fr * 3 + fs) * Ck + kcg * 64) >> 4;
                             if (!MC)
                                 bulk_g2s(sb + fs * B_TILE + j * (BROWS * 16), wsrc + ((kc + j) * g.wrows + n0) * 16, ROWS_B * 16u,
