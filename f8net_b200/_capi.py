@@ -57,7 +57,7 @@ class f8_conv_args(ctypes.Structure):
         ("carry_shift", _i32), ("relu", _i32),
         ("carry_out", _vp),
         ("out", _vp * 2), ("out_shift", _i32 * 2), ("out_signed", _i32 * 2),
-        ("out_f32", _vp), ("out_f32_ld", _i32), ("flags", _i32),
+        ("out_f32", _vp), ("out_f32_ld", _i32), ("flags", _i32), ("wpack_stage", _vp),
     ]
 
 
@@ -83,6 +83,8 @@ SYMBOLS = {
     "f8_plan_set_backend": (ctypes.c_int, [_vp, ctypes.c_int]),
     "f8_pack_weights_bytes": (ctypes.c_size_t, [ctypes.c_int] * 7),
     "f8_pack_weights": (ctypes.c_int, [ctypes.c_int, _vp] + [ctypes.c_int] * 6 + [_vp]),
+    "f8_pack_weights_stage3x3_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "f8_pack_weights_stage3x3": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
     "f8_conv_dense": (ctypes.c_int, [ctypes.POINTER(f8_conv_args), ctypes.c_int, _vp]),
     "f8_conv_dw3x3": (ctypes.c_int, [ctypes.POINTER(f8_conv_args), _vp]),
     "f8_maxpool3x3s2": (ctypes.c_int, [ctypes.POINTER(f8_conv_args), _vp]),

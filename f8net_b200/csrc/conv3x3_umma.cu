@@ -78,6 +78,7 @@ struct TMaps {
 struct PGeom {
     const uint8_t *in;
     const uint8_t *wpack;   // [K_pad/16][wrows][16], k = (r*3+s)*C + c
+    const uint8_t *wstage;  // dense: stage-major image [N tile][group][filter row][column][4 chunks][BN][16], or nullptr
     int wrows;
     int N, H, W, C;         // H x W = OUTPUT size per image, C = cin_pad (multiple of 64)
     int Hin, Win;           // input size per image (= H, W for stride 1; 2H, 2W for stride 2)
@@ -301,6 +302,15 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                             // chunks of a filter row are 12 KB of CONTIGUOUS memory in the order shared memory wants:
                             // one bulk copy (the copy unit retires ~one copy per 100 cycles whatever lane issues it)
                             if (lane == 0) bulk_g2s(sb, wsrc + (size_t)(fr * 3) * 4 * 64 * 16, 12u * ROWS_B * 16u, b_full(slot));
+                        } else if (g.wstage) {
+                            // stage-major image: the stage is 12 * BN * 16 contiguous bytes in shared-memory order:
+                            // ONE bulk copy (pairs: each CTA copies its half into both)
+                            const uint8_t *ssrc = g.wstage + ((size_t)((n0 / BN) * (g.C >> 6) + cg) * 3 + fr) * (size_t)(12 * BN * 16);
+                            if (lane == 0) {
+                                if (!MC) bulk_g2s(sb, ssrc, 12u * ROWS_B * 16u, b_full(slot));
+                                else bulk_g2s_mc(sb + rank * (12u / CLS) * ROWS_B * 16u, ssrc + rank * (12u / CLS) * ROWS_B * 16u,
+                                                 (12u / CLS) * ROWS_B * 16u, b_full(slot), CTA_MASK);
+                            }
                         } else if (lane < 12) {
                             const size_t kc = (size_t)((fr * 3 + fs) * Ck + kcg * 64) >> 4;
                             if (!MC)
@@ -692,6 +702,8 @@ int launch_bn(const f8_conv_args &a, cudaStream_t s) {
     g.in = static_cast<const uint8_t *>(a.in);
     g.wpack = static_cast<const uint8_t *>(a.wpack);
     g.wrows = pk.rows;
+    // the stage-major copy of the weights, when its tile width is this kernel's
+    g.wstage = (!dw && a.wpack_stage && ((a.cout_pad > 64 ? 128 : 64) == BN)) ? static_cast<const uint8_t *>(a.wpack_stage) : nullptr;
     if (dw) {       // block-diagonal group images behind the dp4a words of the depthwise pack
         g.wpack += f8host::dw_dense_offset(a.cin_pad);
         g.wrows = 64;

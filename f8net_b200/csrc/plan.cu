@@ -107,6 +107,7 @@ struct PlanOp {
     f8_op op;
     size_t w_off = 0;   // byte offset of the packed weights inside the device blob
     size_t b_off = 0;   // byte offset of the padded bias
+    size_t ws_off = (size_t)-1;   // dense 3x3: byte offset of the stage-major weight image (none: -1)
 };
 
 }  // namespace
@@ -148,6 +149,37 @@ extern "C" size_t f8_pack_weights_bytes(int kind, int cin, int cout, int cin_pad
         return (size_t)p.rows * (size_t)p.K_pad;
     }
     return 0;
+}
+
+extern "C" size_t f8_pack_weights_stage3x3_bytes(int cin_pad, int cout_pad) {
+    if (cin_pad <= 0 || cin_pad % 64 || cout_pad <= 0) return 0;
+    const int T = cout_pad > 64 ? 128 : 64;
+    return (size_t)((cout_pad + T - 1) / T) * T * (size_t)cin_pad * 9;
+}
+
+extern "C" int f8_pack_weights_stage3x3(const void *dense_pack, int cin_pad, int cout_pad, void *dst_host) {
+    if (!dense_pack || !dst_host || !f8_pack_weights_stage3x3_bytes(cin_pad, cout_pad)) {
+        set_error("pack_weights_stage3x3: bad arguments (cin_pad must be a multiple of 64)");
+        return F8_ERR_ARG;
+    }
+    const f8host::DensePack pk = f8host::dense_pack_geometry(cin_pad, cout_pad, 3, 3);
+    const int T = cout_pad > 64 ? 128 : 64, NT = (cout_pad + T - 1) / T, NCG = cin_pad / 64;
+    const uint8_t *src = static_cast<const uint8_t *>(dense_pack);
+    uint8_t *dst = static_cast<uint8_t *>(dst_host);
+    size_t chunk = 0;
+    for (int t = 0; t < NT; ++t)
+        for (int cg = 0; cg < NCG; ++cg)
+            for (int tap = 0; tap < 9; ++tap)
+                for (int j = 0; j < 4; ++j, ++chunk) {
+                    const size_t kc = (size_t)(tap * cin_pad + cg * 64) / 16 + j;         // chunk of the (r, s, c) K order
+                    for (int n = 0; n < T; ++n) {
+                        const int row = t * T + n;
+                        uint8_t *d = dst + (chunk * T + n) * 16;
+                        if (row < pk.rows) std::memcpy(d, src + (kc * pk.rows + row) * 16, 16);
+                        else std::memset(d, 0, 16);
+                    }
+                }
+    return F8_OK;
 }
 
 extern "C" int f8_pack_weights(int kind, const int32_t *weight, int cin, int cout, int cin_pad,
@@ -282,6 +314,10 @@ extern "C" int f8_plan_create(const f8_model_desc *desc, int device, f8_plan **o
                                  kAlign);
                 po.b_off = blob;
                 blob += align_up((size_t)o.cout_pad * sizeof(int32_t), kAlign);
+                if (o.kind == F8_OP_CONV_DENSE && o.kh == 3 && o.kw == 3 && o.pad == 1 && o.cin_pad % 64 == 0) {
+                    po.ws_off = blob;
+                    blob += align_up(f8_pack_weights_stage3x3_bytes(o.cin_pad, o.cout_pad), kAlign);
+                }
             }
         }
         if (!rc && o.kind == F8_OP_CONVERT_INPUT) {
@@ -304,6 +340,10 @@ extern "C" int f8_plan_create(const f8_model_desc *desc, int device, f8_plan **o
         int rc = f8_pack_weights(o.kind == F8_OP_CONV_DW ? o.kind : F8_OP_CONV_DENSE, o.weight, o.cin, o.cout,
                                  o.cin_pad, o.cout_pad, fc ? 1 : o.kh, fc ? 1 : o.kw, host.data() + po.w_off);
         if (rc) { delete p; return rc; }
+        if (po.ws_off != (size_t)-1) {
+            rc = f8_pack_weights_stage3x3(host.data() + po.w_off, o.cin_pad, o.cout_pad, host.data() + po.ws_off);
+            if (rc) { delete p; return rc; }
+        }
         std::memcpy(host.data() + po.b_off, o.bias, (size_t)o.cout * sizeof(int32_t));
         po.op.weight = nullptr;   // host pointers are not kept: the caller owns them
         po.op.bias = nullptr;
@@ -443,6 +483,7 @@ static int run_op(const f8_plan *p, const PlanOp &po, int n, const uint8_t *x, i
     a.in_signed = o.in_signed;
     a.in = o.in_buf == -2 ? x : buf(o.in_buf);
     a.wpack = p->blob + po.w_off;
+    a.wpack_stage = po.ws_off != (size_t)-1 ? p->blob + po.ws_off : nullptr;
     a.bias = reinterpret_cast<const int32_t *>(p->blob + po.b_off);
     a.carry_in = reinterpret_cast<const int32_t *>(buf(o.carry_in_buf));
     a.carry_shift = o.carry_shift;

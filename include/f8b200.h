@@ -253,6 +253,9 @@ typedef struct f8_conv_args {
     float *out_f32;            /* [n*hout*wout, out_f32_ld] or NULL                       */
     int32_t out_f32_ld;
     int32_t flags;             /* f8_op_flags                                              */
+    const void *wpack_stage;   /* optional, dense 3x3 with cin_pad % 64 == 0: the same weights in the
+                                  stage-major order of f8_pack_weights_stage3x3 (one contiguous bulk copy
+                                  per pipeline stage instead of twelve strided ones); NULL = not used   */
 } f8_conv_args;
 
 /* Bytes of the packed weight image for a layer and the packing itself (host -> host).
@@ -261,6 +264,13 @@ F8_API size_t f8_pack_weights_bytes(int kind, int cin, int cout, int cin_pad, in
                              int kw);
 F8_API int f8_pack_weights(int kind, const int32_t *weight, int cin, int cout, int cin_pad,
                     int cout_pad, int kh, int kw, void *dst_host);
+
+/* Stage-major copy of a dense 3x3 pack for the resident-patch tcgen05 kernel: tiles of T = 128 (cout_pad > 64) or
+ * 64 output rows; per tile, per 64-channel input group, per filter row, per filter column: four 16-byte K chunks of
+ * T rows -- exactly the order and granularity in which the kernel's weight ring consumes them.  dense_pack is the
+ * image f8_pack_weights produced for the same layer (host pointers). */
+F8_API size_t f8_pack_weights_stage3x3_bytes(int cin_pad, int cout_pad);
+F8_API int f8_pack_weights_stage3x3(const void *dense_pack, int cin_pad, int cout_pad, void *dst_host);
 
 /* Replaces: int nn.Conv2d.__call__ (groups == 1) / nn.Linear.__call__ + the consumer-side
  * int_op_only_fix_quant, ReLU and residual add around it (fix_resnet.py:28-77). */

@@ -64,6 +64,14 @@ def run_conv(lib, x, w, b, stride, pad, *, depthwise=False, in_signed=False, rel
     a.in_signed = int(in_signed)
     a.in_, a.wpack, a.bias = xd.data_ptr(), wd.data_ptr(), bd.data_ptr()
     keep = [xd, wd, bd]
+    if not depthwise and kh == 3 and kw == 3 and pad == 1 and cin_pad % 64 == 0:
+        # the stage-major copy the plan hands to the resident-patch kernel (f8_pack_weights_stage3x3)
+        dense = pack(lib, kind, w, cin_pad, cout_pad)
+        st = np.zeros(lib.f8_pack_weights_stage3x3_bytes(cin_pad, cout_pad), dtype=np.uint8)
+        C.check(lib.f8_pack_weights_stage3x3(dense.ctypes.data, cin_pad, cout_pad, st.ctypes.data))
+        sd = dev(st)
+        keep.append(sd)
+        a.wpack_stage = sd.data_ptr()
     if carry is not None:
         cd = dev(nchw_to_carry(carry, cout_pad))
         keep.append(cd)

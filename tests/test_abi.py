@@ -41,7 +41,7 @@ int main(void) {
   printf("%zu %zu %zu %zu ", sizeof(f8_op), sizeof(f8_buffer), sizeof(f8_model_desc), sizeof(f8_conv_args));
   printf("%zu %zu %zu %zu ", offsetof(f8_op, weight), offsetof(f8_op, carry_in_buf), offsetof(f8_op, out_buf), offsetof(f8_op, out_f32));
   printf("%zu %zu %zu %zu %zu\n", offsetof(f8_conv_args, in), offsetof(f8_conv_args, carry_shift), offsetof(f8_conv_args, carry_out), offsetof(f8_conv_args, out_f32), offsetof(f8_model_desc, workspace_per_image));
-  printf("%zu %zu %d\n", offsetof(f8_op, flags), offsetof(f8_conv_args, flags), (int)F8_OPF_INT_MAXPOOL);
+  printf("%zu %zu %d %zu\n", offsetof(f8_op, flags), offsetof(f8_conv_args, flags), (int)F8_OPF_INT_MAXPOOL, offsetof(f8_conv_args, wpack_stage));
   return 0; }
 """
     with tempfile.TemporaryDirectory() as td:
@@ -57,7 +57,7 @@ int main(void) {
             C.f8_conv_args.in_.offset, C.f8_conv_args.carry_shift.offset,
             C.f8_conv_args.carry_out.offset, C.f8_conv_args.out_f32.offset,
             C.f8_model_desc.workspace_per_image.offset,
-            C.f8_op.flags.offset, C.f8_conv_args.flags.offset, C.F8_OPF_INT_MAXPOOL]
+            C.f8_op.flags.offset, C.f8_conv_args.flags.offset, C.F8_OPF_INT_MAXPOOL, C.f8_conv_args.wpack_stage.offset]
     assert got == want
 
 
@@ -214,3 +214,24 @@ def test_pack_input_host_every_simd_body(f8lib, isa):
     if r.returncode != 0 and "Illegal instruction" in r.stderr + str(r.returncode):
         pytest.skip("this CPU lacks the instruction set")
     assert r.returncode == 0 and "ISA " + ["scalar", "sse2", "avx2", "avx512"][isa] in r.stdout, (r.stdout, r.stderr[-1500:])
+
+
+def test_pack_stage3x3_is_a_permutation_of_the_dense_pack(f8lib):
+    """f8_pack_weights_stage3x3: tiles of 128 (or 64) output rows; per tile, 64-channel group, filter row, filter
+    column: four 16-byte K chunks of T rows.  Every weight lands where the kernel's stage copy expects it."""
+    rng = np.random.default_rng(11)
+    for cin, cout in [(64, 64), (128, 200), (64, 48)]:
+        cin_pad, cout_pad = (cin + 15) // 16 * 16, (cout + 15) // 16 * 16
+        w = rng.integers(-127, 128, (cout, cin, 3, 3)).astype(np.int32)
+        rc, dense = _pack(f8lib, C.F8_OP_CONV_DENSE, w, cin_pad, cout_pad)
+        assert rc == 0
+        n = f8lib.f8_pack_weights_stage3x3_bytes(cin_pad, cout_pad)
+        T = 128 if cout_pad > 64 else 64
+        assert n == -(-cout_pad // T) * T * cin_pad * 9
+        st = np.full(n, 0x5A, np.uint8)
+        assert f8lib.f8_pack_weights_stage3x3(dense.ctypes.data, cin_pad, cout_pad, st.ctypes.data) == 0
+        img = st.view(np.int8).reshape(-1, cin_pad // 64, 3, 3, 4, T, 16)      # [tile][group][r][s][chunk][row][byte]
+        for o, c, r, s_ in [(0, 0, 0, 0), (cout - 1, cin - 1, 2, 2), (cout // 2, 17, 1, 2), (5, 63, 2, 0)]:
+            assert img[o // T, c // 64, r, s_, (c % 64) // 16, o % T, c % 16] == w[o, c, r, s_]
+        assert not img[-1, :, :, :, :, (cout_pad - 1) % T + 1:, :].any() or cout_pad % T == 0
+    assert f8lib.f8_pack_weights_stage3x3_bytes(48, 64) == 0
