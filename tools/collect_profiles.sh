@@ -26,6 +26,12 @@ if [ -n "$full" ]; then
     rm -f $out/${tag}_full_$a.ncu-rep          # gpurun brings back at most 64 MiB: keep the CSV export only
   done
 fi
+if [ -n "$full" ]; then
+  for tool in memcheck initcheck racecheck; do
+    timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_sanitizer_$tool.log 2>&1
+    echo "exit $?" >> $out/${tag}_sanitizer_$tool.log
+  done
+fi
 du -sh $out
 cat $out/${tag}_tests.log
 cut -c1-300 $out/${tag}_bench_n1.json
