@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libf8b200.so")
 
 F8_ABI_VERSION = 2
-F8_OK, F8_ERR_ARG, F8_ERR_CUDA, F8_ERR_UNSUPPORTED, F8_ERR_NOMEM = 0, -1, -2, -3, -4
+F8_OK, F8_ERR_ARG, F8_ERR_CUDA, F8_ERR_UNSUPPORTED, F8_ERR_NOMEM, F8_ERR_RANGE = 0, -1, -2, -3, -4, -5
 F8_IN_NCHW_I32, F8_IN_NHWC4_8, F8_IN_NCHW_F32, F8_IN_NHWC3_U8 = 0, 1, 2, 3
 F8_OPF_INT_MAXPOOL = 1
 F8_OP_CONVERT_INPUT, F8_OP_CONV_DENSE, F8_OP_CONV_DW, F8_OP_MAXPOOL, F8_OP_POOL_REQUANT, \
@@ -79,6 +79,7 @@ SYMBOLS = {
                                            ctypes.c_size_t, _vp]),
     "f8_host_pack_info": (ctypes.c_char_p, [ctypes.POINTER(ctypes.c_int)]),
     "f8_plan_last_raw_images": (ctypes.c_int, [_vp]),
+    "f8_plan_input_range": (ctypes.c_int, [_vp, ctypes.c_int]),
     "f8_plan_launch_count": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "f8_plan_set_backend": (ctypes.c_int, [_vp, ctypes.c_int]),
     "f8_pack_weights_bytes": (ctypes.c_size_t, [ctypes.c_int] * 7),
@@ -99,7 +100,7 @@ SYMBOLS = {
     "f8_integerize_f32": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_int, _vp]),
     "f8_integerize_u8": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
-    "f8_pack_input_host": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int]),
+    "f8_pack_input_host": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int]),
     "f8_make_input_lut": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float),
                                          ctypes.POINTER(ctypes.c_float), _vp]),
     "f8_last_error": (ctypes.c_char_p, []),

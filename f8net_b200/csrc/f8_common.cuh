@@ -95,6 +95,7 @@ struct Epilogue {
     int cout;                 // logical channel count (float output bound)
     int cout_pad;             // row pitch of the NHWC outputs
     int int_pool;             // max-pool kernels: FXQMaxPool2d (integer max, no float round trip)
+    int carry_pf;             // tcgen05 kernels: the loader warp bulk-prefetches a tile's residual carry into L2
 };
 
 // acc (already including bias) + optional residual carry -> int32 value every output derives from
@@ -343,6 +344,11 @@ void note_kernel(const char *fmt, ...);
 // kernel launchers implemented in the .cu files, called by plan.cu
 namespace f8host {
 inline const char *debug_env(const char *name) { return F8_DBG ? getenv(name) : nullptr; }
+// Residual-carry L2 prefetch of the tcgen05 kernels (results do not depend on it): F8_CARRY_PREFETCH=0 disables
+inline int carry_prefetch_enabled() {
+    static const int on = [] { const char *e = getenv("F8_CARRY_PREFETCH"); return !(e && e[0] == '0') ? 1 : 0; }();
+    return on;
+}
 
 // One-time setup of a kernel family PER DEVICE: cudaFuncSetAttribute (the > 48 KB dynamic shared
 // memory opt-in) applies to the current device only, and so does the SM count a persistent grid is
@@ -428,12 +434,14 @@ inline size_t dw_pack_bytes(int cpad) { return dw_dense_offset(cpad) + (size_t)(
 int launch_maxpool(const f8_conv_args &a, cudaStream_t s);
 int launch_pool_requant(const f8_conv_args &a, cudaStream_t s);
 int launch_pool_fc(const f8_conv_args &a, cudaStream_t s);
+// range_flag: host-mapped word raised when a value lies outside the head's 8 bits ([-128,127] signed,
+// [0,255] unsigned); nullptr = no check
 int launch_convert_input(const int32_t *x, void *out, int n, int h, int w, int is_signed,
-                         cudaStream_t s);
+                         cudaStream_t s, int *range_flag = nullptr);
 int launch_requant_i32(const int32_t *x, int32_t *y, size_t count, int shift, int is_signed,
                        cudaStream_t s);
 int launch_integerize_f32(const float *x, void *out, int n, int h, int w, int normalize, int fraclen,
-                          cudaStream_t s);
+                          cudaStream_t s, int is_signed = 0, int *range_flag = nullptr);
 int launch_integerize_u8(const uint8_t *x, const uint8_t *lut_dev, void *out, int n, int h, int w,
                          cudaStream_t s);
 

@@ -132,6 +132,11 @@ struct f8_plan {
     cudaEvent_t dma_idle = nullptr;          // "the copy engine has executed everything enqueued so far"
     f8hp::Pool *pack_pool = nullptr;         // helper threads of the host-side narrowing (owned)
     int last_raw_images = 0;                 // images of the last run_host the copy engine shipped un-narrowed
+    // input range check: a host-mapped word the narrowing / integerising kernels raise when a value lies
+    // outside the head's 8 bits (no copy, no launch: a store that never executes for well-formed inputs),
+    // and its device alias; host_out_of_range is the same finding of the host-side narrowing
+    int *range_flag = nullptr, *range_flag_dev = nullptr;
+    bool host_out_of_range = false;
     std::vector<std::string> kernel_names;   // per op: the kernel template of the last f8_plan_profile
 };
 
@@ -357,6 +362,15 @@ extern "C" int f8_plan_create(const f8_model_desc *desc, int device, f8_plan **o
         return f8host::cuda_fail(e, "plan_create upload");
     }
     p->blob_bytes = host.size();
+    e = cudaHostAlloc(reinterpret_cast<void **>(&p->range_flag), 64, cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+        *p->range_flag = 0;
+        e = cudaHostGetDevicePointer(reinterpret_cast<void **>(&p->range_flag_dev), p->range_flag, 0);
+    }
+    if (e != cudaSuccess) {
+        f8_plan_destroy(p);
+        return f8host::cuda_fail(e, "plan_create range flag");
+    }
     *out = p;
     return F8_OK;
 }
@@ -366,6 +380,7 @@ extern "C" void f8_plan_destroy(f8_plan *plan) {
     if (plan->blob) cudaFree(plan->blob);
     if (plan->lut_dev) cudaFree(plan->lut_dev);
     if (plan->host_stage) cudaFreeHost(plan->host_stage);
+    if (plan->range_flag) cudaFreeHost(plan->range_flag);
     if (plan->host_stage_free) cudaEventDestroy(plan->host_stage_free);
     if (plan->dma_idle) cudaEventDestroy(plan->dma_idle);
     delete plan->pack_pool;
@@ -467,13 +482,14 @@ static int run_op(const f8_plan *p, const PlanOp &po, int n, const uint8_t *x, i
         if (x_is_nhwc4) return F8_OK;
         if (x_layout == F8_IN_NCHW_F32)
             return f8host::launch_integerize_f32(reinterpret_cast<const float *>(x), buf(o.out_buf[0]), n, o.hin,
-                                                 o.win, p->prep_normalize, p->prep_fraclen, s);
+                                                 o.win, p->prep_normalize, p->prep_fraclen, s, p->head_signed,
+                                                 p->range_flag_dev);
         if (x_layout == F8_IN_NHWC3_U8) {
             if (!p->lut_dev) { set_error("plan_run: call f8_plan_set_input_prep before a uint8 image input"); return F8_ERR_ARG; }
             return f8host::launch_integerize_u8(x, p->lut_dev, buf(o.out_buf[0]), n, o.hin, o.win, s);
         }
         return f8host::launch_convert_input(reinterpret_cast<const int32_t *>(x), buf(o.out_buf[0]),
-                                            n, o.hin, o.win, o.in_signed, s);
+                                            n, o.hin, o.win, p->head_signed, s, p->range_flag_dev);
     }
     f8_conv_args a{};
     a.n = n;
@@ -623,10 +639,13 @@ static int plan_run_impl(f8_plan *plan, const void *x_dev, int x_layout, int n,
 // ---------------------------------------------------------------------------------------
 // Host side of the reference-facing call (host_pack.cpp: SIMD narrowing, per-plan helper threads)
 // ---------------------------------------------------------------------------------------
-extern "C" int f8_pack_input_host(const int32_t *x, int n, int h, int w, void *dst, int threads) {
+extern "C" int f8_pack_input_host(const int32_t *x, int n, int h, int w, void *dst, int threads, int head_signed) {
     if (!x || !dst || n <= 0 || h <= 0 || w <= 0) { set_error("pack_input_host: bad arguments"); return F8_ERR_ARG; }
     static f8hp::Pool *pool = new f8hp::Pool;                // standalone entry point: one process-wide pool
-    pool->run(x, static_cast<uint8_t *>(dst), h, w, 0, (long long)n * h, threads);
+    if (!pool->run(x, static_cast<uint8_t *>(dst), h, w, 0, (long long)n * h, threads, head_signed ? -128 : 0)) {
+        set_error("pack_input_host: input values outside [%d, %d]", head_signed ? -128 : 0, head_signed ? 127 : 255);
+        return F8_ERR_RANGE;
+    }
     return F8_OK;
 }
 
@@ -684,12 +703,14 @@ static int stage_int32_input(f8_plan *plan, const int32_t *x_host, int n, uint8_
         have_evt = true;
         raw_used += cnt;
         return f8host::launch_convert_input(reinterpret_cast<const int32_t *>(dst), x_stage_dev + (size_t)hi * img4, cnt, H, W,
-                                            plan->head_signed, s);
+                                            plan->head_signed, s, plan->range_flag_dev);
     };
     if (raw_ok && raw_cap >= SUB) { const int rc = ship_raw(); if (rc) return rc; }
     while (lo < hi) {
         const int cnt = hi - lo < SUB ? hi - lo : SUB;
-        plan->pack_pool->run(x_host, plan->host_stage, H, W, (long long)lo * H, (long long)(lo + cnt) * H, nthreads);
+        if (!plan->pack_pool->run(x_host, plan->host_stage, H, W, (long long)lo * H, (long long)(lo + cnt) * H, nthreads,
+                                  plan->head_signed ? -128 : 0))
+            plan->host_out_of_range = true;
         F8_CUDA(cudaMemcpyAsync(x_stage_dev + (size_t)lo * img4, plan->host_stage + (size_t)lo * img4, (size_t)cnt * img4,
                                 cudaMemcpyHostToDevice, s));
         lo += cnt;
@@ -735,8 +756,26 @@ extern "C" int f8_plan_run_host(f8_plan *plan, const void *x_host, int x_layout,
     F8_CUDA(cudaMemcpyAsync(logits_host, logits_dev,
                             (size_t)n * plan->num_classes * sizeof(float),
                             cudaMemcpyDeviceToHost, s));
-    if (sync) F8_CUDA(cudaStreamSynchronize(s));
+    if (sync) {
+        F8_CUDA(cudaStreamSynchronize(s));
+        if (f8_plan_input_range(plan, 1)) {
+            set_error("plan_run_host: input values outside the head's 8-bit range [%d, %d]: the reference's head conv "
+                      "consumes the full int32 and would give different logits", plan->head_signed ? -128 : 0,
+                      plan->head_signed ? 127 : 255);
+            return F8_ERR_RANGE;
+        }
+    }
     return F8_OK;
+}
+
+extern "C" int f8_plan_input_range(f8_plan *plan, int clear) {
+    if (!plan) return 0;
+    const bool bad = plan->host_out_of_range || (plan->range_flag && *reinterpret_cast<volatile int *>(plan->range_flag));
+    if (bad && clear) {
+        plan->host_out_of_range = false;
+        if (plan->range_flag) *reinterpret_cast<volatile int *>(plan->range_flag) = 0;
+    }
+    return bad ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -193,33 +193,43 @@ pool_fc_kernel(const int32_t *__restrict__ in, int n, int hw, int cpad, const ui
 }
 
 // x int32 [n,3,h,w] -> out 8-bit [n,h,w,4]; channel 3 = 0.  Keeps the low byte: u8 0..255
-// and s8 -127..127 both survive the truncation unchanged.
+// and s8 -128..127 both survive the truncation unchanged.  The reference's head conv consumes the
+// full int32 (fix_resnet.py:355): a value outside [lo, lo + 255] would give different logits, so
+// it raises *range_flag (host-mapped word of the plan; nullptr = standalone call, no check).
 __global__ void __launch_bounds__(THREADS)
-convert_input_kernel(const int32_t *__restrict__ x, uint32_t *__restrict__ out, int n, int hw) {
+convert_input_kernel(const int32_t *__restrict__ x, uint32_t *__restrict__ out, int n, int hw, int lo,
+                     int *range_flag) {
     const long long total = (long long)n * hw;
     // programmatic dependent launch: the NHWC4 buffer written here may still be read by the
     // head conv of the previous chunk / pass
     f8::pdl_trigger();
     f8::pdl_wait();
+    uint32_t wide = 0;
     for (long long idx = blockIdx.x * (long long)THREADS + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * THREADS) {
         const int img = (int)(idx / hw);
         const int px = (int)(idx - (long long)img * hw);
         const int32_t *src = x + (size_t)img * 3 * hw + px;
-        const uint32_t c0 = (uint32_t)__ldg(src) & 0xffu;
-        const uint32_t c1 = (uint32_t)__ldg(src + hw) & 0xffu;
-        const uint32_t c2 = (uint32_t)__ldg(src + 2 * (size_t)hw) & 0xffu;
-        out[idx] = c0 | (c1 << 8) | (c2 << 16);
+        const uint32_t v0 = (uint32_t)__ldg(src), v1 = (uint32_t)__ldg(src + hw), v2 = (uint32_t)__ldg(src + 2 * (size_t)hw);
+        wide |= (v0 - (uint32_t)lo) | (v1 - (uint32_t)lo) | (v2 - (uint32_t)lo);
+        out[idx] = (v0 & 0xffu) | ((v1 & 0xffu) << 8) | ((v2 & 0xffu) << 16);
+    }
+    if (range_flag && (wide & ~0xffu)) {                       // never taken for well-formed inputs
+        *reinterpret_cast<volatile int *>(range_flag) = 1;
+        __threadfence_system();
     }
 }
 
 // forward_loss's integerisation (fix_train.py:676-692) of the float32 NCHW tensor, in float32
 // with round-half-even exactly as torch does: (255 * x).round().int()  or
-// clamp(round(x * 2^fl), -127, 127); the low byte is kept (like the int32 path).
+// clamp(round(x * 2^fl), -127, 127); the low byte is kept and a value outside the head's 8 bits
+// (x < 0 -- the reference asserts input >= 0, fix_train.py:689 --, x > 1, NaN) raises *range_flag
+// (like the int32 path).
 __global__ void __launch_bounds__(THREADS)
 integerize_f32_kernel(const float *__restrict__ x, uint32_t *__restrict__ out, int n, int hw, int normalize,
-                      float scale) {
+                      float scale, int lo, int *range_flag) {
     const long long total = (long long)n * hw;
+    uint32_t wide = 0;
     for (long long idx = blockIdx.x * (long long)THREADS + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * THREADS) {
         const int img = (int)(idx / hw);
@@ -232,9 +242,15 @@ integerize_f32_kernel(const float *__restrict__ x, uint32_t *__restrict__ out, i
             int32_t v;
             if (normalize) v = (int32_t)fminf(fmaxf(r, -127.0f), 127.0f);
             else v = f8::f2i_x86(r);
+            // NaN: torch's clamp keeps it and .int() gives INT_MIN; fmaxf drops it -- out of range either way
+            wide |= ((uint32_t)v - (uint32_t)lo) | (r != r ? 0x100u : 0u);
             q[c] = (uint32_t)v & 0xffu;
         }
         out[idx] = q[0] | (q[1] << 8) | (q[2] << 16);
+    }
+    if (range_flag && (wide & ~0xffu)) {
+        *reinterpret_cast<volatile int *>(range_flag) = 1;
+        __threadfence_system();
     }
 }
 
@@ -349,21 +365,23 @@ int launch_pool_fc(const f8_conv_args &a, cudaStream_t s) {
     return F8_OK;
 }
 
-int launch_convert_input(const int32_t *x, void *out, int n, int h, int w, int, cudaStream_t s) {
+int launch_convert_input(const int32_t *x, void *out, int n, int h, int w, int is_signed, cudaStream_t s,
+                         int *range_flag) {
     const long long total = (long long)n * h * w;
     note_kernel("convert_input");
-    F8_CUDA(launch_pdl(convert_input_kernel, grid_for(total), THREADS, 0, s, x, static_cast<uint32_t *>(out), n, h * w));
+    F8_CUDA(launch_pdl(convert_input_kernel, grid_for(total), THREADS, 0, s, x, static_cast<uint32_t *>(out), n, h * w,
+                       is_signed ? -128 : 0, range_flag));
     F8_CUDA(cudaGetLastError());
     return F8_OK;
 }
 
 int launch_integerize_f32(const float *x, void *out, int n, int h, int w, int normalize, int fraclen,
-                          cudaStream_t s) {
+                          cudaStream_t s, int is_signed, int *range_flag) {
     const long long total = (long long)n * h * w;
     const float scale = normalize ? ldexpf(1.0f, fraclen) : 255.0f;
     note_kernel("integerize_f32");
     integerize_f32_kernel<<<grid_for(total), THREADS, 0, s>>>(x, static_cast<uint32_t *>(out), n, h * w,
-                                                              normalize, scale);
+                                                              normalize, scale, is_signed ? -128 : 0, range_flag);
     F8_CUDA(cudaGetLastError());
     return F8_OK;
 }

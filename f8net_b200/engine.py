@@ -48,12 +48,16 @@ def infer_arch(sd):
     return f"resnet{depth}"
 
 
+class InputRangeError(ValueError):
+    """An input tensor held values outside the head's 8-bit range (see ``Engine.check_input_range``)."""
+
+
 class Engine:
     """One compiled plan on one GPU.  Stateless at inference like the reference's IntModel:
     the only mutable state is scratch memory, so use one Engine per stream."""
 
     def __init__(self, net: NetSpec, state_dict, device=None, chunk: int = 256, backend=None,
-                 keep_buffers: bool = False, fuse_tail=None):
+                 keep_buffers: bool = False, fuse_tail=None, range_check: bool = True):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("f8net_b200 needs a CUDA device (sm_100a); there is no CPU path")
@@ -71,6 +75,7 @@ class Engine:
         self.plan: Plan = build_plan(net, _to_numpy_sd(state_dict), fuse_head=(int(backend) == 1),
                                      fuse_tail=bool(fuse_tail), keep_buffers=keep_buffers)
         self.keep_buffers = bool(keep_buffers)
+        self.range_check = bool(range_check)
         self._last = None                      # (n, chunk) of the most recent run_device
         self.chunk = int(chunk)
         desc, keep = self.plan.to_desc()
@@ -193,10 +198,29 @@ class Engine:
         chunk = min(int(chunk or self.chunk), n)
         ws = self._workspace(chunk)
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        # asynchronous: an out-of-range input of an EARLIER call surfaces here (or in check_input_range)
+        self._raise_if_out_of_range("an earlier asynchronous call")
         C.check(self.lib.f8_plan_run(self._h, x.data_ptr(), layout, n, out.data_ptr(),
                                      ws.data_ptr(), ws.numel(), chunk, st.cuda_stream))
         self._last = (n, chunk)
         return out
+
+    def _raise_if_out_of_range(self, who):
+        if self.lib.f8_plan_input_range(self._h, 1) and self.range_check:
+            lo, hi = (-128, 127) if self.net.head.sym else (0, 255)
+            raise InputRangeError(
+                f"{who} had input values outside the head's 8-bit range [{lo}, {hi}] (or NaN): the "
+                f"reference's head conv consumes the full int32 (fix_resnet.py:355) and forward_loss asserts "
+                f"input >= 0 (fix_train.py:689); the engine computed from the low bytes, its logits differ")
+
+    def check_input_range(self, stream=None):
+        """The always-on input range check for asynchronous calls (``run_device`` / ``__call__`` on a CUDA
+        tensor / ``run_host(sync=False)``): waits for ``stream`` (default: the current one) and raises
+        InputRangeError if any input since the last check lay outside the head's 8 bits.  Synchronous
+        ``run_host`` calls raise by themselves.  ``Engine(range_check=False)`` never raises."""
+        torch = self._torch
+        (stream if stream is not None else torch.cuda.current_stream(self.device)).synchronize()
+        self._raise_if_out_of_range("an input since the last check")
 
     def read_buffer(self, index):
         """Debug / parity aid: plan buffer ``index`` (see ``plan.bufs``) as the most recent single-pass
@@ -232,10 +256,15 @@ class Engine:
         chunk = min(int(chunk or self.chunk), n)
         ws = self._workspace(chunk)
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
-        C.check(self.lib.f8_plan_run_host(self._h, x.data_ptr(), layout, n, out.data_ptr(),
-                                          self._stage.data_ptr(), self._logits.data_ptr(),
-                                          ws.data_ptr(), ws.numel(), chunk, int(bool(sync)),
-                                          st.cuda_stream))
+        rc = self.lib.f8_plan_run_host(self._h, x.data_ptr(), layout, n, out.data_ptr(),
+                                       self._stage.data_ptr(), self._logits.data_ptr(),
+                                       ws.data_ptr(), ws.numel(), chunk, int(bool(sync)),
+                                       st.cuda_stream)
+        if rc == C.F8_ERR_RANGE:
+            if self.range_check:
+                raise InputRangeError(C.lib().f8_last_error().decode())
+            return out
+        C.check(rc)
         return out
 
     def profile(self, x, chunk=None):
@@ -270,8 +299,12 @@ class Engine:
 
     def __call__(self, x, strict=False):
         """``IntModel.forward(x)``: int32 NCHW in, float32 logits out, on x's device.
-        ``strict`` checks that x lies in the head's 8-bit range (the reference assumes it,
-        fix_train.py:682-692; the engine keeps the low byte)."""
+        The engine keeps the low byte of every input value where the reference's head conv consumes the
+        full int32 (fix_train.py:682-692 hands it 8-bit-range integers).  Out-of-range inputs are always
+        detected (InputRangeError): by this call for a CPU tensor, by the next call or
+        ``check_input_range()`` for a CUDA tensor (the call is asynchronous).  ``strict`` checks up front,
+        with two extra passes over x, against the symmetric range the reference's own preparation
+        produces (+-127 for a signed head)."""
         torch = self._torch
         if strict and x.dtype == torch.int32:
             lo, hi = (-127, 127) if self.net.head.sym else (0, 255)
@@ -294,12 +327,13 @@ class Engine:
 
 def compile(model_or_state_dict, arch: Optional[str] = None, head_signed: Optional[bool] = None,
             device=None, chunk: int = 256, backend=None, quant_maxpool: bool = False,
-            keep_buffers: bool = False, fuse_tail=None) -> Engine:
+            keep_buffers: bool = False, fuse_tail=None, range_check: bool = True) -> Engine:
     """Build an Engine from a reference ``IntModel`` (module tree walked for stride / groups /
     input_symmetric), or from its ``state_dict()`` plus the architecture name -- the
     attributes the dict lacks are then re-derived from the architecture (SURVEY.md 8(b));
     ``head_signed`` mirrors FLAGS.normalize (fix_resnet.py:437-438) and defaults to False;
-    ``quant_maxpool`` mirrors FLAGS.quant_maxpool (FXQMaxPool2d head pool, fix_resnet.py:331-334)."""
+    ``quant_maxpool`` mirrors FLAGS.quant_maxpool (FXQMaxPool2d head pool, fix_resnet.py:331-334);
+    ``range_check=False`` keeps out-of-range inputs silent (low byte used), see ``Engine.check_input_range``."""
     if hasattr(model_or_state_dict, "state_dict") and hasattr(model_or_state_dict, "head"):
         net = graph_from_module(model_or_state_dict)
         sd = model_or_state_dict.state_dict()
@@ -313,4 +347,4 @@ def compile(model_or_state_dict, arch: Optional[str] = None, head_signed: Option
             raise ValueError(f"unknown arch {arch!r}")
         net = graph_for(arch, bool(head_signed), quant_maxpool=bool(quant_maxpool))
     return Engine(net, sd, device=device, chunk=chunk, backend=backend, keep_buffers=keep_buffers,
-                  fuse_tail=fuse_tail)
+                  fuse_tail=fuse_tail, range_check=range_check)

@@ -47,7 +47,9 @@ typedef enum f8_status {
     F8_ERR_ARG = -1,          /* malformed descriptor / null pointer / shape mismatch          */
     F8_ERR_CUDA = -2,         /* a CUDA runtime call failed; see f8_last_error()               */
     F8_ERR_UNSUPPORTED = -3,  /* valid for the reference but outside this engine (e.g. shift>30)*/
-    F8_ERR_NOMEM = -4
+    F8_ERR_NOMEM = -4,
+    F8_ERR_RANGE = -5         /* input values outside the head's 8 bits: the logits were computed from the low
+                                 bytes and differ from the reference's (f8_plan_input_range)                  */
 } f8_status;
 
 /* Layout of the input handed to f8_plan_run (reference call surface: model(x) with x int32
@@ -172,7 +174,8 @@ F8_API int f8_plan_run(f8_plan *plan, const void *x_dev, int x_layout, int n, fl
  * with float32 arithmetic and round-half-even exactly as torch computes them; for uint8 pixels p
  * the float tensor is x = (p / 255 - mean[c]) / std[c] (mean 0 / std 1 when normalize = 0).
  * Defaults without this call: normalize = the head's signedness, fraclen = 8 (unsigned) or the
- * head's input_fraclen given here.  The low byte of x_int is kept, like F8_IN_NCHW_I32. */
+ * head's input_fraclen given here.  The low byte of x_int is kept, like F8_IN_NCHW_I32, and a value
+ * outside the head's 8 bits is recorded (f8_plan_input_range). */
 F8_API int f8_plan_set_input_prep(f8_plan *plan, int normalize, int fraclen, const float *mean3,
                            const float *std3);
 
@@ -194,6 +197,19 @@ F8_API int f8_plan_set_input_prep(f8_plan *plan, int normalize, int fraclen, con
 F8_API int f8_plan_run_host(f8_plan *plan, const void *x_host, int x_layout, int n, float *logits_host,
                      void *x_stage_dev, float *logits_dev, void *workspace_dev,
                      size_t workspace_bytes, int chunk, int sync, void *stream);
+
+/* Input range check, always on.  The reference hands IntModel.forward 8-bit-range integers in int32
+ * (fix_train.py:682-692) but its head conv consumes the full int32 (fix_resnet.py:355), and forward_loss
+ * asserts input >= 0 on the float tensor (fix_train.py:689); the engine keeps the low byte.  Every narrowing
+ * step of a plan (host SIMD narrowing, the device kernels behind F8_IN_NCHW_I32 and F8_IN_NCHW_F32) therefore
+ * records whether it saw a value outside [0, 255] (unsigned head) or [-128, 127] (signed head; NaN counts as
+ * outside), at no cost for well-formed inputs: the device kernels raise a host-mapped word.
+ *   f8_plan_run_host(sync != 0) returns F8_ERR_RANGE for such a call (the logits are written, computed from
+ *     the low bytes) and clears the record;
+ *   asynchronous calls (f8_plan_run, f8_plan_run_host(sync = 0)) cannot know yet: the record stays raised
+ *     until this function reads it, after the caller has synchronised the stream.
+ * Returns 1 when an input since the last clear was out of range, else 0; clear != 0 resets the record. */
+F8_API int f8_plan_input_range(f8_plan *plan, int clear);
 
 /* How the host side of f8_plan_run_host narrows int32 inputs on this machine: returns the SIMD body
  * ("avx512" | "avx2" | "sse2" | "scalar"), *threads = helper threads per plan. */
@@ -307,8 +323,10 @@ F8_API int f8_integerize_u8(const uint8_t *x, const uint8_t *lut_dev, void *out,
                      void *stream);
 /* Host-only (no CUDA call): the narrowing f8_plan_run_host applies to an F8_IN_NCHW_I32 host tensor.
  * x int32 [n,3,h,w] -> dst bytes [n,h,w,4] = the low byte of each channel value, channel 3 = 0 (what
- * f8_convert_input produces on the device).  threads <= 1: the calling thread only. */
-F8_API int f8_pack_input_host(const int32_t *x, int n, int h, int w, void *dst, int threads);
+ * f8_convert_input produces on the device).  threads <= 1: the calling thread only.  Returns F8_ERR_RANGE
+ * (dst is still written) when a value lies outside [0, 255] (head_signed = 0) or [-128, 127] (head_signed
+ * != 0): the same pass that narrows also ORs (value - low bound) of everything it reads. */
+F8_API int f8_pack_input_host(const int32_t *x, int n, int h, int w, void *dst, int threads, int head_signed);
 F8_API int f8_make_input_lut(int normalize, int fraclen, const float *mean3, const float *std3,
                       uint8_t *lut_host768);
 /* Replaces: int_op_only_fix_quant as a standalone op (fix_quant_ops.py:90-114):

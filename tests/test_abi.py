@@ -181,9 +181,38 @@ def test_pack_input_host_low_bytes_nhwc4(f8lib):
             want[..., :3] = (x.transpose(0, 2, 3, 1) & 0xff).astype(np.uint8)
             for threads in (0, 1, 3, 16):
                 out = np.full((n, h, w, 4), 0x55, np.uint8)
-                assert f8lib.f8_pack_input_host(x.ctypes.data, n, h, w, out.ctypes.data, threads) == 0
+                assert f8lib.f8_pack_input_host(x.ctypes.data, n, h, w, out.ctypes.data, threads, int(lo < 0)) == 0
                 assert np.array_equal(out, want), (n, h, w, lo, threads)
-    assert f8lib.f8_pack_input_host(None, 1, 1, 1, None, 1) != 0
+    assert f8lib.f8_pack_input_host(None, 1, 1, 1, None, 1, 0) != 0
+
+
+def test_pack_input_host_reports_out_of_range_values(f8lib):
+    """The narrowing pass is also the range check (the reference's head conv consumes the full
+    int32, fix_resnet.py:355): one value outside the head's 8 bits anywhere -- vector body, row tail, any
+    channel, any helper thread's share -- gives F8_ERR_RANGE, with the low bytes still written; the bounds
+    themselves pass.  Unsigned head: [0, 255]; signed head: [-128, 127]."""
+    from f8net_b200 import _capi as C
+    rng = np.random.default_rng(17)
+    n, h, w = 3, 70, 37                                     # 37 = two AVX-512 vectors + a 5-wide tail
+    for signed, lo, hi in [(0, 0, 255), (1, -128, 127)]:
+        base = rng.integers(lo, hi + 1, (n, 3, h, w)).astype(np.int32)
+        base[0, 0, 0, 0], base[n - 1, 2, h - 1, w - 1] = lo, hi            # the bounds are in range
+        out = np.zeros((n, h, w, 4), np.uint8)
+        for threads in (1, 4):
+            assert f8lib.f8_pack_input_host(base.ctypes.data, n, h, w, out.ctypes.data, threads, signed) == 0
+        spots = [(0, 0, 0, 0), (1, 1, 35, 36), (2, 2, 69, 20), (0, 1, 10, 31), (2, 0, 64, 33)]
+        for bad in (lo - 1, hi + 1, 1 << 20, -(1 << 31), 0x100 + lo if lo else 0x1ff):
+            for spot in spots:
+                x = base.copy()
+                x[spot] = bad
+                for threads in (1, 4):
+                    rc = f8lib.f8_pack_input_host(x.ctypes.data, n, h, w, out.ctypes.data, threads, signed)
+                    assert rc == C.F8_ERR_RANGE, (signed, bad, spot, threads, rc)
+                    assert np.array_equal(out[..., :3], (x.transpose(0, 2, 3, 1) & 0xff).astype(np.uint8))
+        # the other head's range is out of range here
+        other = rng.integers(-128, 0, (n, 3, h, w)).astype(np.int32) if not signed else \
+            rng.integers(128, 256, (n, 3, h, w)).astype(np.int32)
+        assert f8lib.f8_pack_input_host(other.ctypes.data, n, h, w, out.ctypes.data, 2, signed) == C.F8_ERR_RANGE
 
 
 @pytest.mark.parametrize("isa", [0, 1, 2, 3])
@@ -199,15 +228,20 @@ def test_pack_input_host_every_simd_body(f8lib, isa):
         "name = lib.f8_host_pack_info(ctypes.byref(t)).decode()\n"
         "rng = np.random.default_rng(5)\n"
         "for n, h, w in [(2, 7, 224), (3, 5, 37), (1, 3, 16), (2, 2, 9)]:\n"
-        "    x = rng.integers(-127, 256, (n, 3, h, w)).astype(np.int32)\n"
+        "    x = rng.integers(0, 256, (n, 3, h, w)).astype(np.int32)\n"
         "    want = np.zeros((n, h, w, 4), np.uint8)\n"
         "    want[..., :3] = (x.transpose(0, 2, 3, 1) & 0xff).astype(np.uint8)\n"
         "    for off in (0, 4, 16):\n"
         "        buf = np.full(n * h * w * 4 + 64 + off, 0x55, np.uint8)\n"
         "        base = (-buf.ctypes.data) % 64 + off\n"
         "        out = buf[base:base + n * h * w * 4]\n"
-        "        assert lib.f8_pack_input_host(x.ctypes.data, n, h, w, out.ctypes.data, 3) == 0\n"
+        "        assert lib.f8_pack_input_host(x.ctypes.data, n, h, w, out.ctypes.data, 3, 0) == 0\n"
         "        assert np.array_equal(out.reshape(n, h, w, 4), want), (n, h, w, off)\n"
+        "        for k in range(w):\n"
+        "            y = x.copy(); y[n - 1, k % 3, h - 1, k] = 256 + k\n"
+        "            assert lib.f8_pack_input_host(y.ctypes.data, n, h, w, out.ctypes.data, 1, 0) == C.F8_ERR_RANGE, (w, k)\n"
+        "            y[n - 1, k % 3, h - 1, k] = -1 - k\n"
+        "            assert lib.f8_pack_input_host(y.ctypes.data, n, h, w, out.ctypes.data, 2, 0) == C.F8_ERR_RANGE, (w, k)\n"
         "print('ISA', name, t.value)\n")
     env = dict(os.environ, F8_HOST_PACK_ISA=str(isa))
     r = subprocess.run([sys.executable, "-c", code], env=env, cwd=ROOT, capture_output=True, text=True, timeout=120)

@@ -1,13 +1,15 @@
 #!/bin/bash
-# round-2: new bench line (configs array, parity block, per-template roofline, int8 peak) at N=1 and N=2,
-# NCCL gathered-logits test on two GPUs
+# round-2 step: input range check tests + residual-carry L2 prefetch A/B (per-layer tables with the prefetch off / on)
+tag=${1:-r02b}
 out=gpurun_out
-python -m pytest tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -n 5 > $out/r02b_multi_tests.log
-python bench.py --steps 20 --warmup 5 > $out/r02b_bench_n1.json 2> $out/r02b_bench_n1.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-  bench.py --gpus 2 --steps 20 --warmup 5 > $out/r02b_bench_n2.json 2> $out/r02b_bench_n2.err
-python bench.py --impl reference --steps 2 --warmup 1 > $out/r02b_bench_ref.json 2>/dev/null
-cat $out/r02b_multi_tests.log
-tail -n 5 $out/r02b_bench_n1.err $out/r02b_bench_n2.err
-cut -c1-600 $out/r02b_bench_n1.json
-cut -c1-600 $out/r02b_bench_n2.json
+mkdir -p $out
+timeout 90 python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1 || { echo "SMOKE FAILED/HUNG"; tail -n 5 $out/${tag}_smoke.log; exit 1; }
+timeout 300 python -m pytest tests/test_gpu_input.py tests/test_gpu_kernels.py -m gpu -x -q 2>&1 | tail -n 12 > $out/${tag}_tests_a.log
+cat $out/${tag}_tests_a.log
+for a in resnet18 resnet50 mobilenet_v2; do
+  F8_CARRY_PREFETCH=0 timeout 90 python tools/profile_ops.py --arch $a --batch 256 --chunk 256 > $out/${tag}_per_layer_${a}_pf0.txt 2>&1
+  timeout 90 python tools/profile_ops.py --arch $a --batch 256 --chunk 256 > $out/${tag}_per_layer_${a}_pf1.txt 2>&1
+  head -n 1 $out/${tag}_per_layer_${a}_pf0.txt $out/${tag}_per_layer_${a}_pf1.txt
+done
+timeout 420 python -m pytest tests/test_gpu_nets.py -m gpu -x -q 2>&1 | tail -n 6 > $out/${tag}_tests_b.log
+cat $out/${tag}_tests_b.log
