@@ -95,7 +95,6 @@ struct Epilogue {
     int cout;                 // logical channel count (float output bound)
     int cout_pad;             // row pitch of the NHWC outputs
     int int_pool;             // max-pool kernels: FXQMaxPool2d (integer max, no float round trip)
-    int carry_pf;             // tcgen05 kernels: the loader warp bulk-prefetches a tile's residual carry into L2
 };
 
 // acc (already including bias) + optional residual carry -> int32 value every output derives from
@@ -344,11 +343,6 @@ void note_kernel(const char *fmt, ...);
 // kernel launchers implemented in the .cu files, called by plan.cu
 namespace f8host {
 inline const char *debug_env(const char *name) { return F8_DBG ? getenv(name) : nullptr; }
-// Residual-carry L2 prefetch of the tcgen05 kernels (results do not depend on it): F8_CARRY_PREFETCH=0 disables
-inline int carry_prefetch_enabled() {
-    static const int on = [] { const char *e = getenv("F8_CARRY_PREFETCH"); return !(e && e[0] == '0') ? 1 : 0; }();
-    return on;
-}
 
 // One-time setup of a kernel family PER DEVICE: cudaFuncSetAttribute (the > 48 KB dynamic shared
 // memory opt-in) applies to the current device only, and so does the SM count a persistent grid is
