@@ -219,6 +219,14 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     f8::pdl_trigger();
     if (warp != WLOAD_WARP) f8::pdl_wait();
 
+    // Register re-balancing (generic epilogue only): 20 warps x 96 registers is the launch allocation and the pool
+    // setmaxnreg works in (it is per CTA: an increase can only take what a decrease has released).  The four
+    // producer / issuer warps (one warpgroup, one setmaxnreg for all four) drop to 64 and release 128 x 32 registers,
+    // the sixteen epilogue warps (four warpgroups) take 512 x 8 = the same amount and run with 104 -- room for a
+    // residual-carry ring two 16-column steps deep without spilling.  Each setmaxnreg dominates the code that runs
+    // under it (ptxas budgets a region by the value that reaches it).
+    if (warp >= EPI_WARPS) {
+    if (!PLAIN_U8) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (TMA && warp >= LOADER_WARP0 && warp < MMA_WARP) {
         // =========================== patch loader (TMA) ===========================
         // One warp; lane l issues the tensor load of box l of the stage: a box is one padded row
@@ -459,7 +467,9 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
             g.stats[blockIdx.x * 16 + 8] = w_b;
             g.stats[blockIdx.x * 16 + 15] = ((t_begin - t_entry) << 32) | ((t_first_a - t_entry) & 0xffffffffll);
         }
+    }
     } else {
+        if (!PLAIN_U8) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // =========================== epilogue (warps 0-15) ========================
         const int lg = warp & 3;                       // TMEM lane group of this warp
         const int cw0 = (warp >> 2) * CW;              // this warp's column slice of the tile
@@ -467,7 +477,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
         int buf = 0, acc_phase = 0;
         int bias_n0[2] = {-1, -1};                     // N tile whose bias each buffer's shared copy holds
         bool epi_primed = false;
-        int4 cnext[4] = {};            // prefetched residual carry of the next 16-column step
+        int4 cr0[4] = {}, cr1[4] = {};   // residual carry of the even / odd 16-column steps, requested two steps ahead
         long long w_full = 0, t_issue = 0, t_wait = 0, t_math = 0, t_store = 0;
         const long long t_begin = clock64();
         for (int it = bid; it < total_items; it += nb) {
@@ -544,25 +554,27 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                     }
                 };
                 const int pix = unit_pixel(st);
-                if (!epi_primed) {                // very first step of this CTA
-                    load_carry(pix, n0 + cbase, cnext);
+                if (!epi_primed) {                // very first steps of this CTA
+                    load_carry(pix, n0 + cbase, cr0);
+                    load_carry(pix, n0 + cbase + 16, cr1);
                     epi_primed = true;
                 }
+                // the next tile of this CTA: its first two steps are requested during this tile's last two
+                const int it2 = it + nb;
+                const int pix2 = it2 < total_items ? unit_pixel(super_of(it2)) : -1;
+                const int col2 = (it2 - (it2 / g.ntiles_n) * g.ntiles_n) * BN + cbase;
                 F8_TIMED_WAIT(w_full, mbar_wait(acc_full(buf), acc_phase));
                 tc_fence_after();
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
+                    // step q's carry was requested two steps ago (a step is ~2 us under load, a DRAM round trip under
+                    // load not much less: one step of lead left a quarter of the epilogue's time waiting for it)
                     int4 c[4];
+                    int4 (&ring)[4] = (q & 1) ? cr1 : cr0;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) c[k] = cnext[k];
-                    if (q < 3) {
-                        load_carry(pix, n0 + cbase + 16 * (q + 1), cnext);
-                    } else {
-                        const int it2 = it + nb;
-                        if (it2 < total_items) {
-                            load_carry(unit_pixel(super_of(it2)), (it2 - (it2 / g.ntiles_n) * g.ntiles_n) * BN + cbase, cnext);
-                        }
-                    }
+                    for (int k = 0; k < 4; ++k) c[k] = ring[k];
+                    if (q < 2) load_carry(pix, n0 + cbase + 16 * (q + 2), ring);
+                    else load_carry(pix2, col2 + 16 * (q - 2), ring);
                     const int col = n0 + cbase + 16 * q;
                     if (col < ep.cout_pad) {                               // warp-uniform
                         int32_t v[16];
