@@ -191,12 +191,16 @@ __device__ __forceinline__ void epilogue16(int32_t (&v)[16], const int32_t *bias
 // where floor folds the residual clamp (INT_MIN+1) and the ReLU (0) into one max.
 struct EpiConst {
     int sv, sc;        // residual alignment: v <<= sv ; carry <<= sc   (one of them is 0)
+    uint32_t mv, mc;   // the same as wrapping multipliers 2^sv, 2^sc: v * mv + carry * mc is two multiply-adds
+                       // (FMA pipe) instead of two shifts and an add on the ALU pipe the requantisation lives on
     int floor;         // lower bound applied after bias / residual: 0 (ReLU), INT_MIN+1 (clamp) or INT_MIN
 };
 __device__ __forceinline__ EpiConst epi_const(const Epilogue &ep, bool has_carry) {
     EpiConst k;
     k.sv = has_carry && ep.carry_shift < 0 ? -ep.carry_shift : 0;
     k.sc = has_carry && ep.carry_shift > 0 ? ep.carry_shift : 0;
+    k.mv = 1u << k.sv;          // shifts are at most 30 (check_shift, plan.cu)
+    k.mc = 1u << k.sc;
     k.floor = ep.relu ? 0 : (has_carry ? -2147483647 : (int)0x80000000);
     return k;
 }
@@ -209,10 +213,10 @@ __device__ __forceinline__ void epilogue16_math(int32_t (&v)[16], const int32_t 
         uint32_t t2 = (uint32_t)v[q + 2] + (uint32_t)b.z, t3 = (uint32_t)v[q + 3] + (uint32_t)b.w;
         if (has_carry) {                       // warp-uniform
             const int4 cc = c[q >> 2];
-            t0 = (t0 << k.sv) + ((uint32_t)cc.x << k.sc);
-            t1 = (t1 << k.sv) + ((uint32_t)cc.y << k.sc);
-            t2 = (t2 << k.sv) + ((uint32_t)cc.z << k.sc);
-            t3 = (t3 << k.sv) + ((uint32_t)cc.w << k.sc);
+            t0 = t0 * k.mv + (uint32_t)cc.x * k.mc;
+            t1 = t1 * k.mv + (uint32_t)cc.y * k.mc;
+            t2 = t2 * k.mv + (uint32_t)cc.z * k.mc;
+            t3 = t3 * k.mv + (uint32_t)cc.w * k.mc;
         }
         v[q + 0] = max((int32_t)t0, k.floor); v[q + 1] = max((int32_t)t1, k.floor);
         v[q + 2] = max((int32_t)t2, k.floor); v[q + 3] = max((int32_t)t3, k.floor);
