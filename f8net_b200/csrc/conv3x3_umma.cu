@@ -853,7 +853,12 @@ int launch_conv3x3_umma(const f8_conv_args &a, cudaStream_t s) {
     if (a.stride == 1 && a.hin == a.hout && a.win == a.wout) {
         if (a.cout_pad > 64) {
             // clusters of CTAs sharing the weight stream (F8_MC = 0: single CTAs, 2: pairs, 4: quads)
-            static const int mc = [] { const char *e = getenv("F8_MC"); return e ? atoi(e) : 2; }();
+            static const int mc_all = [] { const char *e = getenv("F8_MC"); return e ? atoi(e) : 2; }();
+            // launches with the generic epilogue (residual layers) may be given their own cluster size
+            static const int mc_gen = [] { const char *e = getenv("F8_MC_GENERIC"); return e ? atoi(e) : -1; }();
+            const bool plain = a.carry_in == nullptr && a.carry_out == nullptr && a.out[1] == nullptr && a.out[0] != nullptr &&
+                               a.out_shift[0] > 0 && !a.out_signed[0];
+            const int mc = (!plain && mc_gen >= 0) ? mc_gen : mc_all;
             if (mc == 4) {
                 const int rc = launch_bn<128, 1, false, 4>(a, s);
                 if (rc != F8_ERR_UNSUPPORTED) return rc;
