@@ -38,6 +38,24 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+
+def _claim_stdout():
+    """stdout carries exactly one JSON line.  Libraries write there too (NCCL prints its version banner to fd 1 under
+    NCCL_DEBUG=VERSION, which the GPU boxes set): file descriptor 1 is pointed at stderr for the life of the process
+    and the JSON line goes to a private duplicate of the original stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
+RESULT_OUT = None
+
+
+def emit(line):
+    out = RESULT_OUT if RESULT_OUT is not None else sys.stdout
+    print(json.dumps(line), file=out, flush=True)
+
 METRIC = "images/sec (int_op_only, bit-exact)"
 UNIT = "images/s"
 NAMES = {"resnet18": "ResNet18", "resnet50": "ResNet50", "mobilenet_v1": "MobileNet V1",
@@ -150,7 +168,7 @@ def reference_arm(args):
                              "sample": sample, "note": PORT_NOTE},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -602,11 +620,13 @@ def gpu_arm(args):
             "e2e": e2e, "e2e_uint8_input": e2e_u8, "gpu_launches": launches, "clocks": clocks,
             "roofline": roofline, "configs": configs, "cpu_baseline": cb,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 def main():
+    global RESULT_OUT
     args = parse()
+    RESULT_OUT = _claim_stdout()
     if args.impl == "reference":
         reference_arm(args)
     else:
