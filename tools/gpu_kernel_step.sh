@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-2 step: kernel change under test -> smoke, kernel + net parity, per-layer tables
+# one kernel iteration on the GPU box: smoke (90 s cap: a deadlocked kernel must not eat the budget), kernel parity, per-layer tables, whole-net + per-layer-in-net parity
 tag=${1:-r02e}
 archs=${2:-"resnet18 resnet50"}
 out=gpurun_out
