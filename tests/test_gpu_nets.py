@@ -169,12 +169,18 @@ def test_input_validation(cuda, f8lib):
     eng(torch.rand((1, 3, 224, 224)), strict=True)
 
 
-@pytest.mark.parametrize("switch,arch", [("F8_PAIR", "resnet18"), ("F8_CPA", "mobilenet_v2"), ("F8_PDL", "resnet18")])
-def test_switchable_kernel_paths_stay_exact(cuda, f8lib, switch, arch):
-    """Kernel variants kept behind environment switches: the CTA-pair form of the 3x3
-    kernel (F8_PAIR=1), the cp.async operand loader of the point-wise kernel (F8_CPA=1) and plain
-    stream order instead of programmatic dependent launch (F8_PDL=0).  The library reads the switches
-    once, so each runs in its own process: odd batch (ragged halves / tiles) against the oracle."""
+@pytest.mark.parametrize("switch,value,arch", [
+    ("F8_MC", "0", "resnet18"), ("F8_MC", "4", "resnet18"), ("F8_MC_GENERIC", "0", "resnet50"),
+    ("F8_CPA", "1", "mobilenet_v2"), ("F8_PDL", "0", "resnet18"), ("F8_GATHER_NO_TMA", "1", "mobilenet_v2"),
+    ("F8_NO_CONV1X1_RES", "1", "mobilenet_v2"), ("F8_DW_CUDA_CORE", "1", "mobilenet_v1")])
+def test_switchable_kernel_paths_stay_exact(cuda, f8lib, switch, value, arch):
+    """Kernel variants kept behind environment switches: the 3x3 kernel as single CTAs / clusters of four instead of
+    pairs sharing the weight stream (F8_MC=0|4; F8_MC_GENERIC for the residual launches alone), the cp.async operand
+    loader of the point-wise kernel (F8_CPA=1), plain stream order instead of programmatic dependent launch
+    (F8_PDL=0), the gather kernel instead of the TMA / resident-weight point-wise kernels (F8_GATHER_NO_TMA,
+    F8_NO_CONV1X1_RES), the CUDA-core depthwise kernel instead of the tensor-core one (F8_DW_CUDA_CORE).  None of them
+    may change a bit.  The library reads the switches once, so each runs in its own process: odd batch (ragged
+    halves / tiles) against the oracle."""
     import subprocess
     import sys
     code = (
@@ -190,7 +196,7 @@ def test_switchable_kernel_paths_stay_exact(cuda, f8lib, switch, arch):
         "assert np.array_equal(y, nets.forward(arch, sd, x, hs)), 'logits differ'\n"
         "print('exact')\n")
     env = dict(os.environ)
-    env[switch] = "0" if switch == "F8_PDL" else "1"
+    env[switch] = value
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
+    r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "exact" in r.stdout, r.stderr[-2000:]
