@@ -132,6 +132,21 @@ def test_full_batch_properties(cuda, f8lib, arch):
     assert np.array_equal(yc[idx], want)
 
 
+@pytest.mark.parametrize("arch", ARCHS)
+def test_full_batch_every_image_against_the_oracle(cuda, f8lib, arch):
+    """The bench configuration itself -- 256 images, one pass (chunk 256) -- with EVERY image's logits compared with
+    the CPU oracle (the full batch was covered by a 4-image spot check plus invariances).  The oracle
+    runs 32 images at a time to bound host memory; a few seconds per network on the GPU box's cores."""
+    hs = synth.HEAD_SIGNED[arch]
+    n = 256
+    sd = synth.make_state_dict(arch, hs)
+    x = synth.make_input(arch, n, hs, seed=31337)
+    y = _engine(arch, sd, chunk=n)(torch.from_numpy(x).cuda()).cpu().numpy()
+    for i0 in range(0, n, 32):
+        want = nets.forward(arch, sd, x[i0:i0 + 32], hs)
+        assert np.array_equal(y[i0:i0 + 32], want), (arch, i0)
+
+
 def test_compile_from_module_like_object_and_bound_method(cuda, f8lib):
     """compile() accepts the state_dict, or the bound method the reference pickles
     (fix_train.py:946 saves {'model': model_wrapper.state_dict} without calling it)."""
