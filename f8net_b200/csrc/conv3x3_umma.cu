@@ -132,7 +132,7 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
     constexpr int LOADER_WARP0 = EPI_WARPS;
     constexpr int MMA_WARP = EPI_WARPS + 1;       // one TMA warp, one MMA warp, one weight loader:
     constexpr int WLOAD_WARP = EPI_WARPS + 2;
-    constexpr int MMA_WARP2 = EPI_WARPS + 3;      // 20 warps leave the epilogue a 96-register cap
+    constexpr int MMA_WARP2 = EPI_WARPS + 3;      // 20 warps: 96 registers each at launch (generic epilogue: setmaxnreg below)
     constexpr int MB = mb_for(BN);
     constexpr int TM = 128 * MB;
     constexpr int SB_MAX = sb_for(BN, PLAIN_U8);
@@ -530,8 +530,8 @@ conv3x3_umma_kernel(const PGeom g, const f8::Epilogue ep, const __grid_constant_
                 // Warp (lg, u) owns rows [32*lg, 32*lg+32) of unit u (one M segment x 64 columns) and
                 // walks it in four steps of 16 columns.  int32 carries live in the pixel-interleaved
                 // layout of f8_common.cuh: the warp's 32 (nearly) consecutive pixels make every
-                // 16-byte carry access a contiguous 512-byte run.  The carry of step q+1 (or of the
-                // next tile's first step) is loaded into registers while step q is computed.
+                // 16-byte carry access a contiguous 512-byte run.  The carries of steps q+1 and q+2 (running
+                // over into the next tile's first steps) are in flight in registers while step q is computed.
                 constexpr int UPS = BN / 64;                 // units per segment
                 const bool has_carry = ep.carry_in != nullptr;
                 const f8::EpiConst kc = f8::epi_const(ep, has_carry);
