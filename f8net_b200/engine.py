@@ -256,6 +256,7 @@ class Engine:
         chunk = min(int(chunk or self.chunk), n)
         ws = self._workspace(chunk)
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        self._raise_if_out_of_range("an earlier asynchronous call")
         rc = self.lib.f8_plan_run_host(self._h, x.data_ptr(), layout, n, out.data_ptr(),
                                        self._stage.data_ptr(), self._logits.data_ptr(),
                                        ws.data_ptr(), ws.numel(), chunk, int(bool(sync)),
