@@ -147,3 +147,18 @@ def test_fused_tail_plan_keeps_the_algorithmic_work():
         assert sum(r["bytes_per_image"] for r in wa) == sum(r["bytes_per_image"] for r in wb)
         assert sum(r["ops"] for r in wa) == sum(r["ops"] for r in wb)
         assert network_work(net)[1] == sum(r["bytes_per_image"] for r in wb)
+
+
+def test_roofline_accounting_reproduces_the_survey_table():
+    """the per-image algorithmic work `roofline.achieved` must be computed from -- MACs, algorithmic
+    HBM bytes (8-bit activations once in / once out per layer + the int32 residual carries) and int8 weight bytes of
+    the four networks, probed from the reference's own layer shapes."""
+    from f8net_b200.roofline import network_work
+    table = {   # arch: (MACs/img in M, algorithmic MB/img, weights MB)
+        "resnet18": (1814.1, 10.69, 11.68), "resnet50": (4089.2, 65.93, 25.50),
+        "mobilenet_v1": (568.7, 10.19, 4.21), "mobilenet_v2": (300.8, 15.18, 3.47)}
+    for arch, (macs_m, mb, w_mb) in table.items():
+        ops, nbytes, wbytes = network_work(graph_for(arch, synth.HEAD_SIGNED[arch]))
+        assert abs(ops / 2 / 1e6 - macs_m) < 0.06, (arch, ops)
+        assert abs(nbytes / 1e6 - mb) < 0.006, (arch, nbytes)
+        assert abs(wbytes / 1e6 - w_mb) < 0.006, (arch, wbytes)
